@@ -1,0 +1,170 @@
+/*
+ * mg_b200.h -- C ABI of the B200-native geometric multigrid engine.
+ *
+ * Drop-in boundary for the multigrid hot path of MisterPup/PDE-MultiGrid.  The reference exposes
+ * this path as three C++ classes with all-public members and no FFI:
+ *     MultiGrid3D  NOCUDA_TESI/POISSON_3D(TESI)/MultiGrid3D.h:6-33   (GPU twin CUDA_TESI/CUDA Poisson 3D/MultiGrid3D.h:6-37)
+ *     MultiGrid2D  NOCUDA_TESI/PDE Lyapunov 2D/MultiGrid2D.h:6-37    (GPU twin CUDA_TESI/CUDA Lyapunov 2D/MultiGrid2D.h:6-33)
+ *     MultiGrid1D  NOCUDA_TESI/EQUAZIONE 1D/MultiGrid1D.h:6-31       (GPU twin CUDA_TESI/CUDA 1D/MultiGrid1D.h:6-31)
+ * Every entry point below names the reference method it replaces.  include/compat/ holds header-
+ * compatible C++ shim classes (same class, member and method names) built on this ABI, so the
+ * reference's own main() files compile unchanged against libmg_b200.so.
+ *
+ * Conventions
+ *   - plain C: opaque handles, plain pointers and sizes, no C++ or torch types;
+ *   - every call returns MG_OK (0) or an MG_ERR_* code; mg_last_error() gives the message of the
+ *     last failure on the calling thread (the reference aborts through assert(), N3/MultiGrid3D.cpp:60-62);
+ *   - host arrays use the reference layout: dense, x fastest, idx = x + y*sx + z*sx*sy
+ *     (N3/MultiGrid3D.cpp:518-531); the engine keeps its own pitched layout on the device;
+ *   - `dtype` selects float (what the reference is written in) or double (what BASELINE.json asks for);
+ *   - `residual_mode`: MG_REF_COMPAT reproduces the reference residual bug-for-bug (sign defects at
+ *     N3/MultiGrid3D.cpp:723 and N1/MultiGrid1D.cpp:210), MG_CORRECTED flips those signs;
+ *   - there is NO CPU fallback: without a CUDA device every create() fails with MG_ERR_CUDA;
+ *   - one handle = one host thread; work is enqueued on the handle's stream; getters and *_host calls
+ *     synchronise, the rest is asynchronous until mg*_sync().
+ */
+#ifndef MG_B200_H
+#define MG_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_OK 0
+#define MG_ERR_ARG 1   /* bad argument / size mismatch (reference: assert) */
+#define MG_ERR_CUDA 2  /* CUDA runtime failure, or no device */
+#define MG_ERR_NOMEM 3
+#define MG_ERR_STATE 4 /* call not valid in the handle's current state */
+#define MG_ERR_COMM 5  /* NCCL / multi-GPU failure */
+
+#define MG_F32 0
+#define MG_F64 1
+
+#define MG_REF_COMPAT 0
+#define MG_CORRECTED 1
+
+#define MG_FIELD_V 0 /* Grid?D::h_v  approximate solution / error */
+#define MG_FIELD_F 1 /* Grid?D::h_f  right-hand side / restricted residual */
+
+/* smoother implementation (results are bit-identical; the choice only affects speed) */
+#define MG_SMOOTHER_AUTO 0
+#define MG_SMOOTHER_COLOUR 1 /* one colour per launch, in place */
+#define MG_SMOOTHER_FUSED 2  /* red+black (and several sweeps) per HBM pass, z-marching smem tiles */
+
+typedef struct mg3d_s mg3d_t;
+typedef struct mg2d_s mg2d_t;
+typedef struct mg1d_s mg1d_t;
+
+const char* mg_last_error(void);
+const char* mg_version(void);
+int mg_device_count(void); /* 0 when no CUDA device is usable */
+
+/* ------------------------------------------------------------------ 3D Poisson ------------- */
+/* MultiGrid3D::MultiGrid3D + InitGrids (N3/MultiGrid3D.cpp:5-47): builds numGrids=(int)log2(n-1)
+   levels, n_l=(n_{l-1}-1)/2+1, and initialises every level like Grid3D's ctor (InitV: boundary 0,
+   InitF: f=-3*PI*PI*sin(PI x)sin(PI y)sin(PI z), N3/Grid3D.cpp:61-96); interior v is zeroed. */
+int mg3d_create(mg3d_t** out, const int finest_size_xyz[3], const double range[6], int dtype, int residual_mode);
+/* same, on `nranks` GPUs (one process each): z-slab partition, halo exchange over NCCL.
+   nccl_unique_id: 128 bytes from mg_comm_unique_id() on rank 0, broadcast by the caller. */
+int mg3d_create_dist(mg3d_t** out, const int finest_size_xyz[3], const double range[6], int dtype, int residual_mode,
+                     int rank, int nranks, const void* nccl_unique_id);
+int mg_comm_unique_id(void* out128);
+int mg3d_destroy(mg3d_t* mg); /* ~MultiGrid3D */
+int mg3d_num_levels(const mg3d_t* mg);         /* MultiGrid3D::numGrids */
+int mg3d_level_size(const mg3d_t* mg, int level); /* grids3D[level]->sizeX */
+double mg3d_level_h(const mg3d_t* mg, int level); /* grids3D[level]->h_x */
+int mg3d_set_smoother(mg3d_t* mg, int smoother, int sweeps_per_pass);
+int mg3d_sync(mg3d_t* mg);
+void* mg3d_stream(mg3d_t* mg); /* cudaStream_t the handle enqueues on (for event timing) */
+long long mg3d_kernel_launches(const mg3d_t* mg); /* kernels launched by this handle so far */
+
+/* grids3D[level]->h_v / h_f  <->  host dense array of n_l^3 values */
+int mg3d_set_field(mg3d_t* mg, int level, int field, const void* host_dense);
+int mg3d_get_field(mg3d_t* mg, int level, int field, void* host_dense);
+/* re-run Grid3D::InitV/InitF on every level (device side) and zero the interior of v */
+int mg3d_init_problem(mg3d_t* mg);
+
+int mg3d_relax(mg3d_t* mg, int level, int ncycles);                 /* Relax(grids3D[level], ncycles) */
+int mg3d_residual(mg3d_t* mg, int level, void* host_out);           /* CalculateResidual(grids3D[level]) -> caller-owned n^3 */
+int mg3d_residual_norm(mg3d_t* mg, int level, double* l2, double* linf); /* norms of that residual (the reference has none) */
+int mg3d_restrict(mg3d_t* mg, int fine_level, int field);           /* Restrict(fine->field, ..., coarse->field, ...) */
+int mg3d_residual_restrict(mg3d_t* mg, int fine_level);             /* Restrict(CalculateResidual(fine), coarse->h_f) + setToValue(coarse->h_v,0,true), fused */
+int mg3d_interpolate(mg3d_t* mg, int fine_level);                   /* Interpolate(fine->h_v, ..., coarse->h_v, ...) */
+int mg3d_interpolate_correct(mg3d_t* mg, int fine_level);           /* Interpolate(tmp, coarse->h_v) + ApplyCorrection(fine->h_v, tmp), fused */
+int mg3d_set_to_value(mg3d_t* mg, int level, int field, double value, int modify_boundaries); /* setToValue / Set */
+int mg3d_vcycle(mg3d_t* mg, int level, int v1, int v2);             /* VCycle(gridID, v1, v2) */
+int mg3d_fmg(mg3d_t* mg, int level, int v0, int v1, int v2);        /* FullMultiGridVCycle(gridID, v0, v1, v2) */
+
+/* reference-facing calls on HOST arrays (NOCUDA signatures, N3/MultiGrid3D.h:16-27): upload, run, download */
+int mg3d_restrict_host(mg3d_t* mg, const void* fine, const int fsize_xyz[3], void* coarse, const int csize_xyz[3]);
+int mg3d_interpolate_host(mg3d_t* mg, void* fine, const int fsize_xyz[3], const void* coarse, const int csize_xyz[3]);
+int mg3d_apply_correction_host(mg3d_t* mg, void* fine, const int fsize_xyz[3], const void* error, const int esize_xyz[3]);
+int mg3d_set_to_value_host(mg3d_t* mg, void* grid, const int size_xyz[3], double value, int modify_boundaries);
+/* end-to-end: upload finest v,f -> `cycles` x VCycle(0,v1,v2) -> download finest v */
+int mg3d_vcycle_host(mg3d_t* mg, void* v_host, const void* f_host, int v1, int v2, int cycles);
+
+/* ------------------------------------------------------------------ 2D Lyapunov ------------ */
+/* MultiGrid2D::MultiGrid2D + InitGrids + InitA (N2/MultiGrid2D.cpp:5-60); A4 = row-major 2x2 by value
+   (the reference's InitA overflows its 2-float buffer); alfa is int as in the reference. */
+int mg2d_create(mg2d_t** out, const int finest_size_xy[2], const double range[4], const double A4[4], int alfa,
+                int dtype);
+int mg2d_destroy(mg2d_t* mg);
+int mg2d_num_levels(const mg2d_t* mg);
+int mg2d_level_size(const mg2d_t* mg, int level);
+double mg2d_level_h(const mg2d_t* mg, int level);
+int mg2d_sync(mg2d_t* mg);
+void* mg2d_stream(mg2d_t* mg);
+long long mg2d_kernel_launches(const mg2d_t* mg);
+int mg2d_set_field(mg2d_t* mg, int level, int field, const void* host_dense);
+int mg2d_get_field(mg2d_t* mg, int level, int field, void* host_dense);
+int mg2d_init_problem(mg2d_t* mg); /* Grid2D::InitV/InitF, N2/Grid2D.cpp:50-80 */
+int mg2d_relax(mg2d_t* mg, int level, int ncycles);
+int mg2d_residual(mg2d_t* mg, int level, void* host_out);
+int mg2d_residual_norm(mg2d_t* mg, int level, double* l2, double* linf);
+int mg2d_restrict(mg2d_t* mg, int fine_level, int field);
+int mg2d_residual_restrict(mg2d_t* mg, int fine_level);
+int mg2d_interpolate(mg2d_t* mg, int fine_level);
+int mg2d_interpolate_correct(mg2d_t* mg, int fine_level);
+int mg2d_set_to_value(mg2d_t* mg, int level, int field, double value, int modify_boundaries);
+int mg2d_vcycle(mg2d_t* mg, int level, int v1, int v2);
+int mg2d_fmg(mg2d_t* mg, int level, int v0, int v1, int v2);
+int mg2d_mean_abs_error(mg2d_t* mg, double* mae); /* PrintMeanAbsoluteError, C2/Grid2D.cu:123-154 */
+int mg2d_restrict_host(mg2d_t* mg, const void* fine, const int fsize_xy[2], void* coarse, const int csize_xy[2]);
+int mg2d_interpolate_host(mg2d_t* mg, void* fine, const int fsize_xy[2], const void* coarse, const int csize_xy[2]);
+int mg2d_apply_correction_host(mg2d_t* mg, void* fine, const int fsize_xy[2], const void* error, const int esize_xy[2]);
+int mg2d_set_to_value_host(mg2d_t* mg, void* grid, const int size_xy[2], double value, int modify_boundaries);
+int mg2d_vcycle_host(mg2d_t* mg, void* v_host, const void* f_host, int v1, int v2, int cycles);
+
+/* ------------------------------------------------------------------ 1D equation ------------ */
+/* MultiGrid1D::MultiGrid1D + InitGrids (N1/MultiGrid1D.cpp:5-31) */
+int mg1d_create(mg1d_t** out, int finest_size, const double range[2], int dtype, int residual_mode);
+int mg1d_destroy(mg1d_t* mg);
+int mg1d_num_levels(const mg1d_t* mg);
+int mg1d_level_size(const mg1d_t* mg, int level);
+double mg1d_level_h(const mg1d_t* mg, int level);
+int mg1d_sync(mg1d_t* mg);
+void* mg1d_stream(mg1d_t* mg);
+long long mg1d_kernel_launches(const mg1d_t* mg);
+int mg1d_set_field(mg1d_t* mg, int level, int field, const void* host_dense);
+int mg1d_get_field(mg1d_t* mg, int level, int field, void* host_dense);
+int mg1d_init_problem(mg1d_t* mg); /* Grid1D::InitV/InitF, N1/Grid1D.cpp:30-43 */
+int mg1d_relax(mg1d_t* mg, int level, int ncycles);
+int mg1d_residual(mg1d_t* mg, int level, void* host_out);
+int mg1d_residual_norm(mg1d_t* mg, int level, double* l2, double* linf);
+int mg1d_restrict(mg1d_t* mg, int fine_level, int field);
+int mg1d_residual_restrict(mg1d_t* mg, int fine_level);
+int mg1d_interpolate(mg1d_t* mg, int fine_level);
+int mg1d_interpolate_correct(mg1d_t* mg, int fine_level);
+int mg1d_set_to_value(mg1d_t* mg, int level, int field, double value, int modify_boundaries);
+int mg1d_vcycle(mg1d_t* mg, int level, int v1, int v2);
+int mg1d_fmg(mg1d_t* mg, int level, int v0, int v1, int v2);
+int mg1d_restrict_host(mg1d_t* mg, const void* fine, int fsize, void* coarse, int csize);
+int mg1d_interpolate_host(mg1d_t* mg, void* fine, int fsize, const void* coarse, int csize);
+int mg1d_apply_correction_host(mg1d_t* mg, void* fine, int fsize, const void* error, int esize);
+int mg1d_set_to_value_host(mg1d_t* mg, void* grid, int size, double value, int modify_boundaries);
+int mg1d_vcycle_host(mg1d_t* mg, void* v_host, const void* f_host, int v1, int v2, int cycles);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MG_B200_H */

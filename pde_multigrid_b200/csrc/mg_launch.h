@@ -1,0 +1,128 @@
+/*
+ * mg_launch.h -- internal C interface between the C host drivers (mg*_host.c) and the CUDA
+ * translation units (mg*_kernels.cu).  Not part of the public ABI (that is include/mg_b200.h).
+ *
+ * Device layout (all levels, all fields): pitched, x fastest.
+ *     element (x,y,zl) of a 3D slab lives at  base[x + y*pitch + zl*plane],  plane = pitch*n
+ *     pitch = n rounded up to 128 bytes, base 256-byte aligned -> every row starts 128-B aligned,
+ *     every row stride is a multiple of 16 B (TMA-addressable; the reference's dense rows of
+ *     (2^k+1)*8 B are not).
+ * A slab holds local planes zl = 0..nzl-1 which are the global planes z = z0 .. z0+nzl-1; on one
+ * GPU z0 = 0 and nzl = n.  Multi-GPU slabs carry ghost planes at both ends.
+ *
+ * Real-valued parameters travel as double; for MG_F32 they hold float values exactly (computed
+ * in float on the host, widened) and the kernels narrow them back without rounding.
+ */
+#ifndef MG_LAUNCH_H
+#define MG_LAUNCH_H
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    int n;           /* global points per axis (cubic: sizeX = sizeY = sizeZ, N3/Grid3D.cpp:10-11) */
+    int pitch;       /* elements per row */
+    long long plane; /* elements per z-plane */
+    int z0;          /* global z of local plane 0 */
+    int nzl;         /* local planes stored */
+} mg_geom3d;
+
+/* coefficient block of one 3D level, all values exactly representable in the level's dtype */
+typedef struct {
+    double hx2, hy2, hz2; /* h*h per axis, N3/MultiGrid3D.cpp:498-500 */
+    double cx, cy, cz;    /* hy2*hz2, hx2*hz2, hx2*hy2 */
+    double den;           /* 2*(cx + cy + cz), N3/MultiGrid3D.cpp:532 */
+    double rden;          /* RN(1/den) */
+} mg_coef3d;
+
+/* every launcher returns the number of kernels it launched (>= 0) or -1 on a launch error */
+
+/* one colour of one RB Gauss-Seidel sweep, in place, on local planes [zl_lo, zl_hi) */
+int mgk3d_relax_colour(cudaStream_t s, int dtype, void* v, const void* f, mg_geom3d g, mg_coef3d c, int colour,
+                       int zl_lo, int zl_hi);
+/* r = CalculateResidual, full array incl. zero boundary, local planes [zl_lo, zl_hi) */
+int mgk3d_residual(cudaStream_t s, int dtype, const void* v, const void* f, void* r, mg_geom3d g, mg_coef3d c,
+                   int corrected, int zl_lo, int zl_hi);
+/* partial sums of r^2 and max|r| over local planes [zl_lo, zl_hi), residual computed on the fly;
+   out2 = {sum, max} (device doubles), scratch >= 2*MGK_NORM_BLOCKS doubles */
+#define MGK_NORM_BLOCKS 1184
+int mgk3d_residual_norm(cudaStream_t s, int dtype, const void* v, const void* f, mg_geom3d g, mg_coef3d c,
+                        int corrected, int zl_lo, int zl_hi, double* scratch, double* out2);
+/* coarse = Restrict(fine) on coarse local planes [czl_lo, czl_hi) */
+int mgk3d_restrict(cudaStream_t s, int dtype, const void* fine, mg_geom3d gf, void* coarse, mg_geom3d gc,
+                   int czl_lo, int czl_hi);
+/* coarse_f = Restrict(CalculateResidual(v,f)), coarse_v = 0 (boundary included), fused: the fine
+   residual only ever exists in shared memory */
+int mgk3d_residual_restrict(cudaStream_t s, int dtype, const void* v, const void* f, mg_geom3d gf, mg_coef3d c,
+                            int corrected, void* coarse_f, void* coarse_v, mg_geom3d gc, int czl_lo, int czl_hi);
+/* fine interior = Interpolate(coarse) (add == 0) or fine interior += Interpolate(coarse) (add != 0) */
+int mgk3d_interpolate(cudaStream_t s, int dtype, void* fine, mg_geom3d gf, const void* coarse, mg_geom3d gc, int add,
+                      int zl_lo, int zl_hi);
+/* fine interior += err interior (ApplyCorrection on two fine arrays) */
+int mgk3d_apply_correction(cudaStream_t s, int dtype, void* fine, const void* err, mg_geom3d g, int zl_lo, int zl_hi);
+/* setToValue */
+int mgk3d_set(cudaStream_t s, int dtype, void* a, mg_geom3d g, double value, int modify_boundaries, int zl_lo,
+              int zl_hi);
+/* Grid3D::InitF from per-axis tables sx,sy,sz (device doubles, n each) = sin(PI*coord) computed with
+   the host libm exactly like the reference: f = (T)(-3*PI*PI*sx*sy*sz), N3/Grid3D.cpp:92 */
+int mgk3d_init_f(cudaStream_t s, int dtype, void* f, mg_geom3d g, const double* sx, const double* sy,
+                 const double* sz, int zl_lo, int zl_hi);
+
+/* ---- 2D (pitched: element (x,y) at base[x + y*pitch]) ---- */
+typedef struct {
+    int n;
+    int pitch;
+} mg_geom2d;
+
+typedef struct {
+    double hx, hy, xa, ya; /* N2/Grid2D.cpp:24-35 */
+    double A[4];           /* matrixA, N2/MultiGrid2D.cpp:45-60 */
+    int alfa;
+} mg_coef2d;
+
+int mgk2d_relax_colour(cudaStream_t s, int dtype, void* v, const void* f, mg_geom2d g, mg_coef2d c, int colour);
+int mgk2d_residual(cudaStream_t s, int dtype, const void* v, const void* f, void* r, mg_geom2d g, mg_coef2d c);
+int mgk2d_residual_norm(cudaStream_t s, int dtype, const void* v, const void* f, mg_geom2d g, mg_coef2d c,
+                        double* scratch, double* out2);
+int mgk2d_restrict(cudaStream_t s, int dtype, const void* fine, mg_geom2d gf, void* coarse, mg_geom2d gc);
+int mgk2d_residual_restrict(cudaStream_t s, int dtype, const void* v, const void* f, mg_geom2d gf, mg_coef2d c,
+                            void* coarse_f, void* coarse_v, mg_geom2d gc);
+int mgk2d_interpolate(cudaStream_t s, int dtype, void* fine, mg_geom2d gf, const void* coarse, mg_geom2d gc, int add);
+int mgk2d_apply_correction(cudaStream_t s, int dtype, void* fine, const void* err, mg_geom2d g);
+int mgk2d_set(cudaStream_t s, int dtype, void* a, mg_geom2d g, double value, int modify_boundaries);
+int mgk2d_init_v(cudaStream_t s, int dtype, void* v, mg_geom2d g, mg_coef2d c);
+/* sum |v - (2x^2-4xy+2y^2)| over all points, C2/Grid2D.cu:123-154 */
+int mgk2d_abs_error_sum(cudaStream_t s, int dtype, const void* v, mg_geom2d g, mg_coef2d c, double* scratch,
+                        double* out2);
+
+/* ---- 1D: the whole hierarchy lives in one device arena; one persistent CTA runs whole cycles ---- */
+#define MG1D_MAX_LEVELS 32
+typedef struct {
+    int nlevels;
+    int n[MG1D_MAX_LEVELS];
+    long long off_v[MG1D_MAX_LEVELS]; /* element offsets into the arena */
+    long long off_f[MG1D_MAX_LEVELS];
+    long long off_e[MG1D_MAX_LEVELS]; /* e1[j] = exp(x_j) + 1 computed with the host libm (N1/MultiGrid1D.cpp:101) */
+    long long off_d[MG1D_MAX_LEVELS]; /* d[j]  = exp(x_j) + 1 + h */
+    double h[MG1D_MAX_LEVELS];
+} mg_hier1d;
+
+int mgk1d_relax(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int level, int ncycles);
+int mgk1d_residual(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int level, int corrected, void* r_out);
+int mgk1d_residual_norm(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int level, int corrected, double* out2);
+int mgk1d_restrict(cudaStream_t s, int dtype, const void* fine, int fn, void* coarse, int cn);
+int mgk1d_residual_restrict(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int level, int corrected);
+int mgk1d_interpolate(cudaStream_t s, int dtype, void* fine, int fn, const void* coarse, int cn, int add);
+int mgk1d_apply_correction(cudaStream_t s, int dtype, void* fine, const void* err, int n);
+int mgk1d_set(cudaStream_t s, int dtype, void* a, int n, double value, int modify_boundaries);
+/* whole V-cycles / FMG in ONE launch: a single persistent CTA walks the hierarchy (2 055 points at n=1025) */
+int mgk1d_cycle(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int level, int v0, int v1, int v2, int corrected,
+                int fmg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
