@@ -1,0 +1,376 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native multigrid engine.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[3] at N=1, the configuration the metric is quoted on): 3D Poisson
+1025^3 fp64, V(2,2) cycles on the reference problem (f = -3 pi^2 sin sin sin, v = 0 on the boundary).
+A "step" is one V(2,2) cycle.  For N > 1 (launched by torchrun, one rank per GPU) the same 1025^3 grid
+is z-slab partitioned over the ranks: strong scaling.
+
+One JSON line on stdout (rank 0):
+  value      V-cycles/s with all fields resident in HBM, CUDA events on the engine's stream, max over ranks
+  e2e        the same metric through the C-ABI call with HOST buffers (mg3d_vcycle_host): pinned host
+             v,f -> device, one V(2,2), v -> host, every step
+  roofline   the dominant kernel (finest-level smoother launch): algorithmic bytes / live event time
+  cpu_baseline  the reference CPU solver (oracle/_ref, compiled unmodified) on this box's host, bounded sample
+`--impl reference` times that CPU solver as the measured arm instead (no GPU work at all).
+
+Only this file's cpu_baseline / --impl reference legs touch oracle/; the GPU arm never does.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NU1 = NU2 = 2
+
+
+def level_sizes(n):
+    num = int(np.floor(np.log2(n - 1)))
+    s = [n]
+    for _ in range(1, num):
+        s.append((s[-1] - 1) // 2 + 1)
+    return s
+
+
+def algorithmic_bytes_per_cycle(n, B, dim=3, nu1=NU1, nu2=NU2):
+    """smoother reads v,f and writes v once per RB sweep; residual->restrict reads v,f
+    and writes coarse f; coarse v zeroed; prolong+correct reads coarse v, reads+writes fine v."""
+    N = [s ** dim for s in level_sizes(n)]
+    tot = 0
+    for l, Nl in enumerate(N):
+        tot += (nu1 + nu2) * 3 * B * Nl
+        if l + 1 < len(N):
+            tot += 4 * B * Nl + 3 * B * N[l + 1]
+    return tot
+
+
+def updates_per_cycle(n, dim=3, nu1=NU1, nu2=NU2):
+    return (nu1 + nu2) * sum((s - 2) ** dim for s in level_sizes(n))
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            with open(self.path) as fh:
+                for line in fh:
+                    c = [x.strip() for x in line.split(",")]
+                    if len(c) < 9:
+                        continue
+                    try:
+                        sm.append(float(c[1]))
+                        smax.append(float(c[2]))
+                    except ValueError:
+                        continue
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                         c[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(name)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def host_cpu_info():
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except Exception:
+        pass
+    return model, os.cpu_count()
+
+
+def time_reference_cpu(n_sample, steps, warmup, dtype=np.float64):
+    """The reference's own CPU implementation of the path (NOCUDA_TESI VCycle(0,2,2), single-threaded as
+    shipped), from oracle/_ref when it is present, else the plain-C port.  Returns seconds per cycle."""
+    from oracle import port, ref
+    if ref.available():
+        o = ref.RefMG(3, dtype, corrected=True, n=n_sample)
+        kind = "reference"
+    else:
+        o = port.PortMG(3, dtype, corrected=True, n=n_sample)
+        kind = "port"
+    for _ in range(warmup):
+        o.vcycle(0, NU1, NU2)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.vcycle(0, NU1, NU2)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    o.close()
+    return dt, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n_sample = args.cpu_n
+    sec, kind = time_reference_cpu(n_sample, args.steps, args.warmup)
+    scale = updates_per_cycle(n_sample) / updates_per_cycle(args.n)
+    value = scale / sec
+    model, cores = host_cpu_info()
+    sample = ("each step = one V(2,2) cycle of the reference NOCUDA_TESI solver (%s, g++ -O2, 1 thread: the reference is "
+              "single-threaded) at %d^3 fp64, sign-corrected residual; V-cycles/s scaled to %d^3 by grid-point updates "
+              "(x%.5f); the reference cannot use more host threads" % (kind, n_sample, args.n, scale))
+    line = {
+        "impl": "reference", "metric": "3D Poisson V(2,2) cycles/s", "value": value, "unit": "V-cycles/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 / scale,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D Poisson %d^3 fp64 V(2,2), reference problem (BASELINE.json configs[3])" % args.n,
+                   "sample_grid": n_sample, "host_cpu": model, "host_cores": cores},
+        "grid_point_updates_per_s": updates_per_cycle(n_sample) / sec,
+        "cpu_baseline": {"value": value, "unit": "V-cycles/s", "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "V-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1025, help="finest grid size per axis (2^k+1)")
+    ap.add_argument("--dtype", default="f64", choices=["f32", "f64"])
+    ap.add_argument("--cpu-n", type=int, default=257, help="grid of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--smoother", default="auto", choices=["auto", "colour", "fused"])
+    ap.add_argument("--sweeps-per-pass", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import pde_multigrid_b200 as mg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("--gpus %d needs one rank per GPU: launch with python -m torch.distributed.run "
+                         "--nproc-per-node %d bench.py --gpus %d ..." % (args.gpus, args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    uid = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import ctypes
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            raw = (ctypes.c_ubyte * 128)()
+            mg._lib.check(mg.lib().mg_comm_unique_id(raw))
+            buf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().tolist())
+
+    np_dtype = np.float64 if args.dtype == "f64" else np.float32
+    B = np.dtype(np_dtype).itemsize
+    n = args.n
+    eng = mg.MultiGrid3D(n, dtype=np_dtype, residual_mode=mg.MG_CORRECTED, rank=rank, nranks=world, nccl_unique_id=uid)
+    if args.smoother != "auto" or args.sweeps_per_pass:
+        code = {"auto": mg.MG_SMOOTHER_AUTO, "colour": mg.MG_SMOOTHER_COLOUR, "fused": mg.MG_SMOOTHER_FUSED}[args.smoother]
+        eng.set_smoother(code, max(args.sweeps_per_pass, 1))
+    stream = torch.cuda.ExternalStream(eng.stream)
+
+    def barrier():
+        eng.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    r0 = eng.residual_norm(0)
+    for _ in range(args.warmup):
+        eng.VCycle(0, NU1, NU2)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng._call("profile", 1)
+    l0 = eng.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        eng.VCycle(0, NU1, NU2)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.kernel_launches - l0
+    eng._call("profile", 0)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    r1 = eng.residual_norm(0)
+
+    # ---- per-operator breakdown from the live event timers (this rank) ----
+    import ctypes
+    ops = {"relax": 0, "residual_restrict": 1, "interpolate_correct": 2, "other": 3}
+    breakdown = []
+    for l in range(eng.numGrids):
+        row = {"level": l, "n": eng.level_size(l)}
+        for name, op in ops.items():
+            ms, kl, calls = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_longlong()
+            eng._call("profile_read", ctypes.c_int(l), ctypes.c_int(op), ctypes.byref(ms), ctypes.byref(kl), ctypes.byref(calls))
+            if calls.value:
+                row[name] = {"ms": ms.value / args.steps, "launches": kl.value // args.steps}
+        breakdown.append(row)
+
+    peak, peak_src = measured_peak_gbs()
+    bytes_cycle = algorithmic_bytes_per_cycle(n, B)
+    N0 = n ** 3
+    relax0 = breakdown[0].get("relax", {"ms": 0.0, "launches": 0})
+    roofline = None
+    if relax0["launches"]:
+        # the smoother call at the finest level: (nu1+nu2) RB sweeps per cycle, 3*B*N0 algorithmic bytes per sweep
+        # (read v, read f, write v) spread over the launches the smoother needs for them
+        alg_per_launch = (NU1 + NU2) * 3 * B * (N0 / world) / relax0["launches"]
+        avg_ms = relax0["ms"] / relax0["launches"]
+        achieved = alg_per_launch / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+                tj = json.load(fh)
+            key = "relax_n%d_%s_%s" % (n, args.dtype, tj.get("current", ""))
+            traffic = tj.get("kernels", {}).get(key)
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "kernel": "finest-level smoother launch (Relax, level 0)", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_ms,
+                    "launches_per_cycle": relax0["launches"],
+                    "share_of_step": relax0["ms"] / ms_step}
+
+    # ---- end to end through the C-ABI call with HOST buffers ----
+    e2e = None
+    if not args.no_e2e and world == 1:
+        hv = torch.zeros(N0, dtype=torch.float64 if B == 8 else torch.float32).pin_memory()
+        hf = torch.empty(N0, dtype=hv.dtype).pin_memory()
+        hf_np = hf.numpy().reshape(n, n, n)
+        hv_np = hv.numpy().reshape(n, n, n)
+        hf_np[...] = eng.get_f(0)
+        eng.vcycle_host(hv_np, hf_np, NU1, NU2, 1)  # warm-up (allocates the staging buffer)
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            eng.vcycle_host(hv_np, hf_np, NU1, NU2, 1)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        e2e = {"value": 1.0 / dt, "unit": "V-cycles/s", "h2d_bytes_per_step": 2 * N0 * B, "d2h_bytes_per_step": N0 * B,
+               "steps": args.e2e_steps, "ms_per_step": dt * 1e3,
+               "call": "mg3d_vcycle_host (pinned host v,f -> device, VCycle(0,2,2), v -> host)",
+               "timer": "host wall clock around the synchronous C-ABI call"}
+        del hv, hf
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, kind = time_reference_cpu(args.cpu_n, args.cpu_steps, 0)
+        scale = updates_per_cycle(args.cpu_n) / updates_per_cycle(n)
+        cpu_baseline = {"value": scale / sec, "unit": "V-cycles/s", "cores": 1, "kind": kind,
+                        "grid_point_updates_per_s": updates_per_cycle(args.cpu_n) / sec,
+                        "sample": "%d V(2,2) cycles of the reference NOCUDA_TESI solver (g++ -O2, 1 thread: it is single-threaded) "
+                                  "at %d^3 fp64, sign-corrected residual, %.2f s/cycle; V-cycles/s scaled to %d^3 by grid-point "
+                                  "updates (x%.5f)" % (args.cpu_steps, args.cpu_n, sec, n, scale)}
+
+    if rank == 0:
+        model, cores = host_cpu_info()
+        value = 1e3 / ms_step
+        line = {
+            "metric": "3D Poisson V(2,2) cycles/s", "value": value, "unit": "V-cycles/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "3D Poisson %d^3 %s V(%d,%d), reference problem (BASELINE.json configs[3]), "
+                                   "sign-corrected residual" % (n, "fp64" if B == 8 else "fp32", NU1, NU2),
+                       "levels": eng.numGrids, "partition": "z-slabs x%d" % world,
+                       "l2": "fields are %.1f GB per level-0 array, far larger than the 126 MB L2: no flush needed" % (N0 * B / 1e9),
+                       "smoother": args.smoother, "host_cpu": model, "host_cores": cores},
+            "grid_point_updates_per_s": updates_per_cycle(n) * value,
+            "algorithmic_bytes_per_cycle": bytes_cycle,
+            "hbm_roofline_cycle": {"achieved_gbs": bytes_cycle / (ms_step * 1e-3) / 1e9 / world, "peak_gbs": peak,
+                                   "frac": bytes_cycle / (ms_step * 1e-3) / 1e9 / world / peak, "per": "GPU"},
+            "residual_l2": {"before": r0[0], "after": r1[0]},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(launches), "breakdown_ms_per_cycle": breakdown,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

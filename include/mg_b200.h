@@ -51,6 +51,13 @@ extern "C" {
 #define MG_SMOOTHER_COLOUR 1 /* one colour per launch, in place */
 #define MG_SMOOTHER_FUSED 2  /* red+black (and several sweeps) per HBM pass, z-marching smem tiles */
 
+/* operator classes of the per-operator device timers (mg?d_profile_read) */
+#define MG_OP_RELAX 0             /* Relax */
+#define MG_OP_RESIDUAL_RESTRICT 1 /* CalculateResidual + Restrict + setToValue(coarse v) */
+#define MG_OP_INTERPOLATE 2       /* Interpolate (+ ApplyCorrection) */
+#define MG_OP_OTHER 3             /* Restrict(f), setToValue, halo exchange ... */
+#define MG_OP_COUNT 4
+
 typedef struct mg3d_s mg3d_t;
 typedef struct mg2d_s mg2d_t;
 typedef struct mg1d_s mg1d_t;
@@ -77,6 +84,10 @@ int mg3d_set_smoother(mg3d_t* mg, int smoother, int sweeps_per_pass);
 int mg3d_sync(mg3d_t* mg);
 void* mg3d_stream(mg3d_t* mg); /* cudaStream_t the handle enqueues on (for event timing) */
 long long mg3d_kernel_launches(const mg3d_t* mg); /* kernels launched by this handle so far */
+/* per-level, per-operator device time: CUDA events recorded on the handle's stream around every
+   operator call while enabled.  enable != 0 resets the counters and starts, 0 stops. */
+int mg3d_profile(mg3d_t* mg, int enable);
+int mg3d_profile_read(mg3d_t* mg, int level, int op, double* ms_total, long long* kernel_launches, long long* calls);
 
 /* grids3D[level]->h_v / h_f  <->  host dense array of n_l^3 values */
 int mg3d_set_field(mg3d_t* mg, int level, int field, const void* host_dense);

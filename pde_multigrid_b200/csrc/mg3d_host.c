@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include "mg_host_common.h"
+#include "mg_profile.h"
 
 typedef struct {
     mg_geom3d g;
@@ -34,8 +35,14 @@ struct mg3d_s {
     double* d_scratch; /* 2*MGK_NORM_BLOCKS partials + 2 outputs */
     double* d_tables;  /* 3*n0 doubles: sin tables of InitF */
     double* h_out2;    /* pinned */
+    void* staging;     /* dense device staging buffer for large host<->device field copies */
+    size_t staging_bytes;
     long long launches;
+    mg_prof prof;
 };
+
+#define PROF_BEGIN(mg, level, op) mg_prof_begin(&(mg)->prof, (mg)->stream, (level), (op), (mg)->launches)
+#define PROF_END(mg) mg_prof_end(&(mg)->prof, (mg)->stream, (mg)->launches)
 
 /* h = range/(real)(n-1) (N3/Grid3D.cpp:31-45) and the products of N3/MultiGrid3D.cpp:498-500,532,
    computed in the level's own precision exactly like the reference does on the host */
@@ -158,6 +165,8 @@ int mg3d_destroy(mg3d_t* mg)
     if (mg->d_scratch) cudaFree(mg->d_scratch);
     if (mg->d_tables) cudaFree(mg->d_tables);
     if (mg->h_out2) cudaFreeHost(mg->h_out2);
+    if (mg->staging) cudaFree(mg->staging);
+    mg_prof_free(&mg->prof);
     free(mg->lv);
     free(mg);
     return MG_OK;
@@ -179,6 +188,25 @@ int mg3d_set_smoother(mg3d_t* mg, int smoother, int sweeps_per_pass)
     return MG_OK;
 }
 
+int mg3d_profile(mg3d_t* mg, int enable)
+{
+    if (!mg) return mg_fail(MG_ERR_ARG, "null handle");
+    return mg_prof_enable(&mg->prof, mg->stream, enable);
+}
+
+int mg3d_profile_read(mg3d_t* mg, int level, int op, double* ms_total, long long* kernel_launches, long long* calls)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (op < 0 || op >= MG_OP_COUNT) return mg_fail(MG_ERR_ARG, "bad op %d", op);
+    st = mg_prof_collect(&mg->prof, mg->stream);
+    if (st) return st;
+    if (ms_total) *ms_total = mg->prof.ms[level][op];
+    if (kernel_launches) *kernel_launches = mg->prof.kl[level][op];
+    if (calls) *calls = mg->prof.calls[level][op];
+    return MG_OK;
+}
+
 int mg3d_sync(mg3d_t* mg)
 {
     if (!mg) return mg_fail(MG_ERR_ARG, "null handle");
@@ -186,10 +214,31 @@ int mg3d_sync(mg3d_t* mg)
     return MG_OK;
 }
 
-/* dense host array (x fastest, idx = x + y*n + z*n*n) <-> pitched device field */
+/* dense host array (x fastest, idx = x + y*n + z*n*n) <-> pitched device field.  Small fields go
+   through cudaMemcpy2D; large ones through one linear copy into a dense device staging buffer and a
+   repack kernel (a 2D copy of 10^6 rows is descriptor-bound, a linear copy runs at PCIe speed). */
+#define MG_STAGING_THRESHOLD ((size_t)32 << 20)
+
+static int staging_reserve(mg3d_t* mg, size_t bytes)
+{
+    if (mg->staging_bytes >= bytes) return MG_OK;
+    if (mg->staging) { MG_CUDA(cudaStreamSynchronize(mg->stream)); cudaFree(mg->staging); mg->staging = NULL; mg->staging_bytes = 0; }
+    MG_CUDA(cudaMalloc(&mg->staging, bytes));
+    mg->staging_bytes = bytes;
+    return MG_OK;
+}
+
 static int copy_in(mg3d_t* mg, void* dev, const mg_geom3d* g, const void* host)
 {
     size_t es = mg_esize(mg->dtype);
+    size_t dense = (size_t)g->n * g->n * (size_t)g->nzl * es;
+    if (dense >= MG_STAGING_THRESHOLD) {
+        int st = staging_reserve(mg, dense);
+        if (st) return st;
+        MG_CUDA(cudaMemcpyAsync(mg->staging, host, dense, cudaMemcpyHostToDevice, mg->stream));
+        MG_LAUNCH(mg->launches, mgk_copy_rows(mg->stream, mg->dtype, dev, g->pitch, mg->staging, g->n, g->n, (long long)g->n * g->nzl));
+        return MG_OK;
+    }
     MG_CUDA(cudaMemcpy2DAsync(dev, (size_t)g->pitch * es, host, (size_t)g->n * es, (size_t)g->n * es,
                               (size_t)g->n * (size_t)g->nzl, cudaMemcpyHostToDevice, mg->stream));
     return MG_OK;
@@ -198,8 +247,16 @@ static int copy_in(mg3d_t* mg, void* dev, const mg_geom3d* g, const void* host)
 static int copy_out(mg3d_t* mg, void* host, const void* dev, const mg_geom3d* g)
 {
     size_t es = mg_esize(mg->dtype);
-    MG_CUDA(cudaMemcpy2DAsync(host, (size_t)g->n * es, dev, (size_t)g->pitch * es, (size_t)g->n * es,
-                              (size_t)g->n * (size_t)g->nzl, cudaMemcpyDeviceToHost, mg->stream));
+    size_t dense = (size_t)g->n * g->n * (size_t)g->nzl * es;
+    if (dense >= MG_STAGING_THRESHOLD) {
+        int st = staging_reserve(mg, dense);
+        if (st) return st;
+        MG_LAUNCH(mg->launches, mgk_copy_rows(mg->stream, mg->dtype, mg->staging, g->n, dev, g->pitch, g->n, (long long)g->n * g->nzl));
+        MG_CUDA(cudaMemcpyAsync(host, mg->staging, dense, cudaMemcpyDeviceToHost, mg->stream));
+    } else {
+        MG_CUDA(cudaMemcpy2DAsync(host, (size_t)g->n * es, dev, (size_t)g->pitch * es, (size_t)g->n * es,
+                                  (size_t)g->n * (size_t)g->nzl, cudaMemcpyDeviceToHost, mg->stream));
+    }
     MG_CUDA(cudaStreamSynchronize(mg->stream));
     return MG_OK;
 }
@@ -268,9 +325,12 @@ static int relax_level(mg3d_t* mg, int level, int ncycles)
     mg_level3d* L = &mg->lv[level];
     const int lo = L->own_lo > 1 ? L->own_lo : 1;
     const int hi = L->own_hi < L->g.nzl - 1 ? L->own_hi : L->g.nzl - 1;
+    if (ncycles <= 0) return MG_OK;
+    PROF_BEGIN(mg, level, MG_OP_RELAX);
     for (int k = 0; k < ncycles; k++)
         for (int colour = 0; colour < 2; colour++)
             MG_LAUNCH(mg->launches, mgk3d_relax_colour(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, colour, lo, hi));
+    PROF_END(mg);
     return MG_OK;
 }
 
@@ -340,7 +400,9 @@ static int interpolate_level(mg3d_t* mg, int fine_level, int add)
     mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
     const int lo = F->own_lo > 1 ? F->own_lo : 1;
     const int hi = F->own_hi < F->g.nzl - 1 ? F->own_hi : F->g.nzl - 1;
+    PROF_BEGIN(mg, fine_level, MG_OP_INTERPOLATE);
     MG_LAUNCH(mg->launches, mgk3d_interpolate(mg->stream, mg->dtype, F->v, F->g, C->v, C->g, add, lo, hi));
+    PROF_END(mg);
     return MG_OK;
 }
 
@@ -378,8 +440,10 @@ static int vcycle_rec(mg3d_t* mg, int level, int v1, int v2)
     if (st) return st;
     if (level != mg->nlevels - 1) {
         mg_level3d *F = &mg->lv[level], *C = &mg->lv[level + 1];
+        PROF_BEGIN(mg, level, MG_OP_RESIDUAL_RESTRICT);
         MG_LAUNCH(mg->launches, mgk3d_residual_restrict(mg->stream, mg->dtype, F->v, F->f, F->g, F->c, mg->mode == MG_CORRECTED,
                                                         C->f, C->v, C->g, C->own_lo, C->own_hi));
+        PROF_END(mg);
         st = vcycle_rec(mg, level + 1, v1, v2);
         if (st) return st;
         st = interpolate_level(mg, level, 1);
@@ -402,7 +466,9 @@ static int fmg_rec(mg3d_t* mg, int level, int v0, int v1, int v2)
     int st;
     if (level != mg->nlevels - 1) {
         mg_level3d *F = &mg->lv[level], *C = &mg->lv[level + 1];
+        PROF_BEGIN(mg, level, MG_OP_OTHER);
         MG_LAUNCH(mg->launches, mgk3d_restrict(mg->stream, mg->dtype, F->f, F->g, C->f, C->g, C->own_lo, C->own_hi));
+        PROF_END(mg);
         st = fmg_rec(mg, level + 1, v0, v1, v2);
         if (st) return st;
         st = interpolate_level(mg, level, 0);

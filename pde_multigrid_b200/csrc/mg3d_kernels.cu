@@ -360,6 +360,17 @@ __global__ void k_init_f(T* __restrict__ f, mg_geom3d g, const double* __restric
     f[(long long)zl * g.plane + (long long)y * g.pitch + x] = (T)__dmul_rn(__dmul_rn(__dmul_rn(k, sx[x]), sy[y]), sz[z]);
 }
 
+template <typename T>
+__global__ void k_copy_rows(T* __restrict__ dst, long long dpitch, const T* __restrict__ src, long long spitch, int width,
+                            long long rows)
+{
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const T* s = src + r * spitch;
+        T* d = dst + r * dpitch;
+        for (int x = threadIdx.x; x < width; x += blockDim.x) d[x] = s[x];
+    }
+}
+
 inline int launch_ok() { return cudaPeekAtLastError() == cudaSuccess ? 1 : -1; }
 
 inline dim3 block2d(int nx) { int bx = nx >= 128 ? 128 : (nx >= 64 ? 64 : 32); return dim3(bx, 256 / bx, 1); }
@@ -479,6 +490,19 @@ int mgk3d_set(cudaStream_t s, int dtype, void* a, mg_geom3d g, double value, int
         k_set<float><<<grid, block, 0, s>>>((float*)a, g, (float)value, modify_boundaries, zl_lo);
     else
         k_set<double><<<grid, block, 0, s>>>((double*)a, g, value, modify_boundaries, zl_lo);
+    return launch_ok();
+}
+
+int mgk_copy_rows(cudaStream_t s, int dtype, void* dst, long long dpitch, const void* src, long long spitch, int width,
+                  long long rows)
+{
+    if (rows <= 0 || width <= 0) return 0;
+    const int threads = width >= 256 ? 256 : (width >= 64 ? 64 : 32);
+    const long long want = rows < (1LL << 20) ? rows : (1LL << 20);
+    if (dtype == 0)
+        k_copy_rows<float><<<(unsigned)want, threads, 0, s>>>((float*)dst, dpitch, (const float*)src, spitch, width, rows);
+    else
+        k_copy_rows<double><<<(unsigned)want, threads, 0, s>>>((double*)dst, dpitch, (const double*)src, spitch, width, rows);
     return launch_ok();
 }
 

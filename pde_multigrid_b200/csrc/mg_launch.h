@@ -71,6 +71,11 @@ int mgk3d_set(cudaStream_t s, int dtype, void* a, mg_geom3d g, double value, int
 int mgk3d_init_f(cudaStream_t s, int dtype, void* f, mg_geom3d g, const double* sx, const double* sy,
                  const double* sz, int zl_lo, int zl_hi);
 
+/* rows x width elements, row strides dpitch / spitch (elements): dense <-> pitched repacking at the
+   ABI boundary (all dimensions: a 3D slab is n*nzl rows) */
+int mgk_copy_rows(cudaStream_t s, int dtype, void* dst, long long dpitch, const void* src, long long spitch, int width,
+                  long long rows);
+
 /* ---- 2D (pitched: element (x,y) at base[x + y*pitch]) ---- */
 typedef struct {
     int n;
