@@ -126,6 +126,8 @@ double mg2d_level_h(const mg2d_t* mg, int level);
 int mg2d_sync(mg2d_t* mg);
 void* mg2d_stream(mg2d_t* mg);
 long long mg2d_kernel_launches(const mg2d_t* mg);
+int mg2d_profile(mg2d_t* mg, int enable);
+int mg2d_profile_read(mg2d_t* mg, int level, int op, double* ms_total, long long* kernel_launches, long long* calls);
 int mg2d_set_field(mg2d_t* mg, int level, int field, const void* host_dense);
 int mg2d_get_field(mg2d_t* mg, int level, int field, void* host_dense);
 int mg2d_init_problem(mg2d_t* mg); /* Grid2D::InitV/InitF, N2/Grid2D.cpp:50-80 */
@@ -156,6 +158,8 @@ double mg1d_level_h(const mg1d_t* mg, int level);
 int mg1d_sync(mg1d_t* mg);
 void* mg1d_stream(mg1d_t* mg);
 long long mg1d_kernel_launches(const mg1d_t* mg);
+int mg1d_profile(mg1d_t* mg, int enable);
+int mg1d_profile_read(mg1d_t* mg, int level, int op, double* ms_total, long long* kernel_launches, long long* calls);
 int mg1d_set_field(mg1d_t* mg, int level, int field, const void* host_dense);
 int mg1d_get_field(mg1d_t* mg, int level, int field, void* host_dense);
 int mg1d_init_problem(mg1d_t* mg); /* Grid1D::InitV/InitF, N1/Grid1D.cpp:30-43 */

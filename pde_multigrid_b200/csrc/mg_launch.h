@@ -118,6 +118,9 @@ typedef struct {
 int mgk1d_relax(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int level, int ncycles);
 int mgk1d_residual(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int level, int corrected, void* r_out);
 int mgk1d_residual_norm(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int level, int corrected, double* out2);
+/* level operators inside the arena: which = 0 Restrict(f) level->level+1, 1 Interpolate level+1 -> v of level,
+   2 Interpolate + ApplyCorrection */
+int mgk1d_level_op(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int level, int which);
 int mgk1d_restrict(cudaStream_t s, int dtype, const void* fine, int fn, void* coarse, int cn);
 int mgk1d_residual_restrict(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int level, int corrected);
 int mgk1d_interpolate(cudaStream_t s, int dtype, void* fine, int fn, const void* coarse, int cn, int add);
