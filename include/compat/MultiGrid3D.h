@@ -1,0 +1,86 @@
+/* include/compat/MultiGrid3D.h -- shim with the public interface of the reference's MultiGrid3D
+   (NOCUDA_TESI/POISSON_3D(TESI)/MultiGrid3D.h:6-33) over libmg_b200.so.  Every operator runs on the
+   GPU; the host arrays grids3D[l]->h_v / h_f are kept current after each call, which is what the
+   reference's main() relies on (N3/Poisson3DSolver.cpp:25-26). */
+#ifndef MULTIGRID3D_H
+#define MULTIGRID3D_H
+
+#include "Grid3D.h"
+
+class MultiGrid3D
+{
+	public:
+		Grid3D** grids3D;
+		int numGrids;
+		mg3d_t* engine; // the C-ABI handle behind this object
+
+		MultiGrid3D(int finestGridSizeXYZ[], float range[]) { InitGrids(finestGridSizeXYZ, range); }
+		~MultiGrid3D()
+		{
+			for (int i = 0; i < numGrids; i++) delete grids3D[i];
+			free(grids3D);
+			mg3d_destroy(engine);
+		}
+		void InitGrids(int finestGridSizeXYZ[], float range[])
+		{
+			double r[6];
+			for (int i = 0; i < 6; i++) r[i] = range[i];
+			MG_CHECK(mg3d_create(&engine, finestGridSizeXYZ, r, MG_F32, MG_REF_COMPAT));
+			numGrids = mg3d_num_levels(engine);
+			grids3D = (Grid3D**)malloc(numGrids * sizeof(Grid3D*));
+			for (int l = 0; l < numGrids; l++) {
+				int n = mg3d_level_size(engine, l);
+				int s[3] = {n, n, n};
+				grids3D[l] = new Grid3D(s, range, engine, l);
+			}
+		}
+
+		void Restrict(float* fine, int fsizeXYZ[], float* coarse, int csizeXYZ[]) { MG_CHECK(mg3d_restrict_host(engine, fine, fsizeXYZ, coarse, csizeXYZ)); }
+		void Interpolate(float* fine, int fsizeXYZ[], float* coarse, int csizeXYZ[]) { MG_CHECK(mg3d_interpolate_host(engine, fine, fsizeXYZ, coarse, csizeXYZ)); }
+		void Relax(Grid3D* curGrid, int ncycles)
+		{
+			int l = level_of(curGrid);
+			curGrid->push(engine, l);
+			MG_CHECK(mg3d_relax(engine, l, ncycles));
+			curGrid->pull(engine, l);
+		}
+		void setToValue(float* grid, int sizeXYZ[], float value, bool modifyBoundaries) { MG_CHECK(mg3d_set_to_value_host(engine, grid, sizeXYZ, value, modifyBoundaries)); }
+		float* CalculateResidual(Grid3D* fine) // caller owns the returned buffer, as in the reference
+		{
+			int l = level_of(fine);
+			fine->push(engine, l);
+			float* r = (float*)malloc((size_t)fine->sizeX * fine->sizeY * fine->sizeZ * sizeof(float));
+			MG_CHECK(mg3d_residual(engine, l, r));
+			return r;
+		}
+		void ApplyCorrection(float* fine, int fsizeXYZ[], float* error, int esizeXYZ[]) { MG_CHECK(mg3d_apply_correction_host(engine, fine, fsizeXYZ, error, esizeXYZ)); }
+
+		void VCycle(int gridID, int v1, int v2)
+		{
+			push_all();
+			MG_CHECK(mg3d_vcycle(engine, gridID, v1, v2));
+			pull_all();
+		}
+		void FullMultiGridVCycle(int gridID, int v0, int v1, int v2)
+		{
+			push_all();
+			MG_CHECK(mg3d_fmg(engine, gridID, v0, v1, v2));
+			pull_all();
+		}
+
+		void PrintGrid(int gridID) { grids3D[gridID]->PrintGrid_v(mg_compat_open_log("log/log_v.txt")); }
+		void PrintAllGrids_v() { int fd = mg_compat_open_log("log/log_v.txt"); for (int i = 0; i < numGrids; i++) grids3D[i]->PrintGrid_v(fd); }
+		void PrintAllGrids_f() { int fd = mg_compat_open_log("log/log_f.txt"); for (int i = 0; i < numGrids; i++) grids3D[i]->PrintGrid_f(fd); }
+		void PrintDiff() { grids3D[0]->PrintDiff(mg_compat_open_log("log/diff.txt")); }
+
+	private:
+		int level_of(Grid3D* g)
+		{
+			for (int l = 0; l < numGrids; l++) if (grids3D[l] == g) return l;
+			fprintf(stderr, "MultiGrid3D: grid does not belong to this hierarchy\n");
+			abort();
+		}
+		void push_all() { for (int l = 0; l < numGrids; l++) grids3D[l]->push(engine, l); }
+		void pull_all() { for (int l = 0; l < numGrids; l++) grids3D[l]->pull(engine, l); }
+};
+#endif
