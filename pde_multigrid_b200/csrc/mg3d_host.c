@@ -61,6 +61,7 @@ static void level_coefs(int dtype, int n, const double* range, double h[3], mg_c
         c->hx2 = hx2; c->hy2 = hy2; c->hz2 = hz2;
         c->cx = cx; c->cy = cy; c->cz = cz;
         c->den = den; c->rden = rden;
+        c->ihx2 = 1.0f / hx2; c->ihy2 = 1.0f / hy2; c->ihz2 = 1.0f / hz2;
     } else {
         double xr = range[1] - range[0], yr = range[3] - range[2], zr = range[5] - range[4];
         double hx = xr / (double)(n - 1), hy = yr / (double)(n - 1), hz = zr / (double)(n - 1);
@@ -71,12 +72,28 @@ static void level_coefs(int dtype, int n, const double* range, double h[3], mg_c
         c->hx2 = hx2; c->hy2 = hy2; c->hz2 = hz2;
         c->cx = cx; c->cy = cy; c->cz = cz;
         c->den = den; c->rden = 1.0 / den;
+        c->ihx2 = 1.0 / hx2; c->ihy2 = 1.0 / hy2; c->ihz2 = 1.0 / hz2;
     }
+    /* exact-arithmetic shortcuts (mg_exact.cuh): a power of two has frexp mantissa 0.5; den = 6*2^e has 0.75 */
+    int e;
+    c->fast_h = frexp(c->hx2, &e) == 0.5 && frexp(c->hy2, &e) == 0.5 && frexp(c->hz2, &e) == 0.5;
+    c->fast_den = c->fast_h && frexp(c->den, &e) == 0.75;
+    if (getenv("MG_B200_IEEE_DIV")) c->fast_h = c->fast_den = 0;
+}
+
+static void set_geom(mg_geom3d* g, int n, int dtype, int z0, int nzl)
+{
+    g->n = n;
+    g->hp = mg_pitch((n + 1) / 2, dtype);
+    g->plane = (long long)g->hp * n;
+    g->cstride = g->plane * nzl;
+    g->z0 = z0;
+    g->nzl = nzl;
 }
 
 static size_t field_bytes(const mg_level3d* L, int dtype)
 {
-    return mg_align256((size_t)L->g.plane * (size_t)L->g.nzl * mg_esize(dtype));
+    return mg_align256(2 * (size_t)L->g.cstride * mg_esize(dtype));
 }
 
 static int check_level(const mg3d_t* mg, int level)
@@ -119,11 +136,7 @@ int mg3d_create(mg3d_t** out, const int sz[3], const double range[6], int dtype,
     int nl = n;
     for (int l = 0; l < mg->nlevels; l++) {
         mg_level3d* L = &mg->lv[l];
-        L->g.n = nl;
-        L->g.pitch = mg_pitch(nl, dtype);
-        L->g.plane = (long long)L->g.pitch * nl;
-        L->g.z0 = 0;
-        L->g.nzl = nl;
+        set_geom(&L->g, nl, dtype, 0, nl);
         L->own_lo = 0;
         L->own_hi = nl;
         level_coefs(dtype, nl, range, L->h, &L->c);
@@ -214,11 +227,8 @@ int mg3d_sync(mg3d_t* mg)
     return MG_OK;
 }
 
-/* dense host array (x fastest, idx = x + y*n + z*n*n) <-> pitched device field.  Small fields go
-   through cudaMemcpy2D; large ones through one linear copy into a dense device staging buffer and a
-   repack kernel (a 2D copy of 10^6 rows is descriptor-bound, a linear copy runs at PCIe speed). */
-#define MG_STAGING_THRESHOLD ((size_t)32 << 20)
-
+/* dense host array (x fastest, idx = x + y*n + z*n*n) <-> colour-split device field: one linear copy
+   between the host array and a dense device staging buffer, plus a repack kernel. */
 static int staging_reserve(mg3d_t* mg, size_t bytes)
 {
     if (mg->staging_bytes >= bytes) return MG_OK;
@@ -230,33 +240,21 @@ static int staging_reserve(mg3d_t* mg, size_t bytes)
 
 static int copy_in(mg3d_t* mg, void* dev, const mg_geom3d* g, const void* host)
 {
-    size_t es = mg_esize(mg->dtype);
-    size_t dense = (size_t)g->n * g->n * (size_t)g->nzl * es;
-    if (dense >= MG_STAGING_THRESHOLD) {
-        int st = staging_reserve(mg, dense);
-        if (st) return st;
-        MG_CUDA(cudaMemcpyAsync(mg->staging, host, dense, cudaMemcpyHostToDevice, mg->stream));
-        MG_LAUNCH(mg->launches, mgk_copy_rows(mg->stream, mg->dtype, dev, g->pitch, mg->staging, g->n, g->n, (long long)g->n * g->nzl));
-        return MG_OK;
-    }
-    MG_CUDA(cudaMemcpy2DAsync(dev, (size_t)g->pitch * es, host, (size_t)g->n * es, (size_t)g->n * es,
-                              (size_t)g->n * (size_t)g->nzl, cudaMemcpyHostToDevice, mg->stream));
+    size_t dense = (size_t)g->n * g->n * (size_t)g->nzl * mg_esize(mg->dtype);
+    int st = staging_reserve(mg, dense);
+    if (st) return st;
+    MG_CUDA(cudaMemcpyAsync(mg->staging, host, dense, cudaMemcpyHostToDevice, mg->stream));
+    MG_LAUNCH(mg->launches, mgk3d_repack(mg->stream, mg->dtype, dev, *g, mg->staging, 1, 0, g->nzl));
     return MG_OK;
 }
 
 static int copy_out(mg3d_t* mg, void* host, const void* dev, const mg_geom3d* g)
 {
-    size_t es = mg_esize(mg->dtype);
-    size_t dense = (size_t)g->n * g->n * (size_t)g->nzl * es;
-    if (dense >= MG_STAGING_THRESHOLD) {
-        int st = staging_reserve(mg, dense);
-        if (st) return st;
-        MG_LAUNCH(mg->launches, mgk_copy_rows(mg->stream, mg->dtype, mg->staging, g->n, dev, g->pitch, g->n, (long long)g->n * g->nzl));
-        MG_CUDA(cudaMemcpyAsync(host, mg->staging, dense, cudaMemcpyDeviceToHost, mg->stream));
-    } else {
-        MG_CUDA(cudaMemcpy2DAsync(host, (size_t)g->n * es, dev, (size_t)g->pitch * es, (size_t)g->n * es,
-                                  (size_t)g->n * (size_t)g->nzl, cudaMemcpyDeviceToHost, mg->stream));
-    }
+    size_t dense = (size_t)g->n * g->n * (size_t)g->nzl * mg_esize(mg->dtype);
+    int st = staging_reserve(mg, dense);
+    if (st) return st;
+    MG_LAUNCH(mg->launches, mgk3d_repack(mg->stream, mg->dtype, (void*)dev, *g, mg->staging, 0, 0, g->nzl));
+    MG_CUDA(cudaMemcpyAsync(host, mg->staging, dense, cudaMemcpyDeviceToHost, mg->stream));
     MG_CUDA(cudaStreamSynchronize(mg->stream));
     return MG_OK;
 }
@@ -501,18 +499,11 @@ static int cubic(const int s[3], int* n)
     return MG_OK;
 }
 
-static void temp_geom(int n, int dtype, mg_geom3d* g)
-{
-    g->n = n;
-    g->pitch = mg_pitch(n, dtype);
-    g->plane = (long long)g->pitch * n;
-    g->z0 = 0;
-    g->nzl = n;
-}
+static void temp_geom(int n, int dtype, mg_geom3d* g) { set_geom(g, n, dtype, 0, n); }
 
 static int temp_alloc(mg3d_t* mg, const mg_geom3d* g, void** p)
 {
-    MG_CUDA(cudaMalloc(p, (size_t)g->plane * g->nzl * mg_esize(mg->dtype)));
+    MG_CUDA(cudaMalloc(p, 2 * (size_t)g->cstride * mg_esize(mg->dtype)));
     return MG_OK;
 }
 

@@ -5,7 +5,17 @@
 // the reference expression by expression through the non-contracting helpers of
 // mg_exact.cuh, so results are bit-identical to the CPU solver for float and double.
 //
-// All stages are HBM-bound stencils (<= 2 flop/B): no tensor cores.  Layout: see mg_launch.h.
+// DEVICE LAYOUT: colour-split.  Every field (v, f on every level) is stored as two arrays, one per
+// red-black colour c = (x+y+z) & 1, each compacted along x:
+//     element (x,y,zl) lives at  base[c*cstride + zl*plane + y*hp + (x>>1)]
+// A red half-sweep then reads ONLY the black array of v, the red array of f and writes ONLY the red
+// array of v, all with unit stride: 12 B/point per half-sweep in fp64, i.e. exactly the algorithmic
+// 24 B/point per RB sweep of SURVEY.md 8(d).  With interleaved colours the same kernel pulls every
+// 32-B sector of v and f and writes every sector of v (48 B/point per sweep; measured: profiles/
+// r1_v1_relax_colour_ncu_full.txt).  Neighbours of a point of colour c at half-index i in row (y,z),
+// q = x & 1:  O/E = other[i-1+q], other[i+q];  N/S = other[i -/+ hp];  D/U = other[i -/+ plane].
+//
+// All stages are HBM-bound stencils (<= 2 flop/B): no tensor cores.
 #include <stdint.h>
 
 #include "mg_exact.cuh"
@@ -17,7 +27,7 @@ namespace {
 
 template <typename T>
 struct Coef3 {
-    T hx2, hy2, hz2, cx, cy, cz, den, rden;
+    T hx2, hy2, hz2, cx, cy, cz, den, rden, ihx2, ihy2, ihz2;
 };
 
 template <typename T>
@@ -27,12 +37,21 @@ Coef3<T> narrow(const mg_coef3d& c)
     r.hx2 = (T)c.hx2; r.hy2 = (T)c.hy2; r.hz2 = (T)c.hz2;
     r.cx = (T)c.cx; r.cy = (T)c.cy; r.cz = (T)c.cz;
     r.den = (T)c.den; r.rden = (T)c.rden;
+    r.ihx2 = (T)c.ihx2; r.ihy2 = (T)c.ihy2; r.ihz2 = (T)c.ihz2;
     return r;
 }
 
+__device__ __forceinline__ long long off3(const mg_geom3d& g, int x, int y, int zl)
+{
+    const int c = (x + y + g.z0 + zl) & 1;
+    return (long long)c * g.cstride + (long long)zl * g.plane + (long long)y * g.hp + (x >> 1);
+}
+
 // N3/MultiGrid3D.cpp:532 -- left-to-right sum of the six weighted neighbours, minus f*hx2*hy2*hz2,
-// true division by 2*(hy2*hz2 + hx2*hz2 + hx2*hy2).  O/E = x-1/x+1, N/S = y-1/y+1, D/U = z-1/z+1.
-template <typename T>
+// divided by 2*(hy2*hz2 + hx2*hz2 + hx2*hy2).  O/E = x-1/x+1, N/S = y-1/y+1, D/U = z-1/z+1.
+// FAST: the divisor is 6*2^e (cubic grid, power-of-two h: the reference problem) -> correctly rounded
+// quotient from the host reciprocal in 3 pipe ops (mg_exact.cuh); otherwise IEEE division.
+template <typename T, bool FAST>
 __device__ __forceinline__ T relax_point(T O, T E, T N, T S, T D, T U, T f, const Coef3<T>& c)
 {
     T s = add(mul(O, c.cx), mul(E, c.cx));
@@ -41,24 +60,35 @@ __device__ __forceinline__ T relax_point(T O, T E, T N, T S, T D, T U, T f, cons
     s = add(s, mul(D, c.cz));
     s = add(s, mul(U, c.cz));
     s = sub(s, mul(mul(mul(f, c.hx2), c.hy2), c.hz2));
-    return div(s, c.den);
+    return FAST ? div_by_const(s, c.den, c.rden) : div(s, c.den);
 }
 
-// N3/MultiGrid3D.cpp:723 (REF_COMPAT, minus S / minus U) or the sign-corrected form.
-template <typename T>
+// N3/MultiGrid3D.cpp:723 (REF_COMPAT, minus S / minus U) or the sign-corrected form.  FAST: every h^2
+// is a power of two, so x/h^2 == x*(1/h^2) exactly.
+template <typename T, bool FAST>
 __device__ __forceinline__ T residual_point(T O, T E, T N, T S, T D, T U, T vc, T f, const Coef3<T>& c, int corrected)
 {
-    T v2 = mul(T(2), vc);
-    T tx = div(add(sub(O, v2), E), c.hx2);
-    T ty, tz;
-    if (corrected) {
-        ty = div(add(sub(N, v2), S), c.hy2);
-        tz = div(add(sub(D, v2), U), c.hz2);
-    } else {
-        ty = div(sub(sub(N, v2), S), c.hy2);
-        tz = div(sub(sub(D, v2), U), c.hz2);
-    }
+    const T v2 = mul(T(2), vc);
+    const T ax = add(sub(O, v2), E);
+    const T ay = corrected ? add(sub(N, v2), S) : sub(sub(N, v2), S);
+    const T az = corrected ? add(sub(D, v2), U) : sub(sub(D, v2), U);
+    const T tx = FAST ? mul(ax, c.ihx2) : div(ax, c.hx2);
+    const T ty = FAST ? mul(ay, c.ihy2) : div(ay, c.hy2);
+    const T tz = FAST ? mul(az, c.ihz2) : div(az, c.hz2);
     return sub(sub(sub(f, tx), ty), tz);
+}
+
+// residual at interior fine point (x,y,zl) read from the colour-split arrays
+template <typename T, bool FAST>
+__device__ __forceinline__ T residual_at(const T* __restrict__ v, const T* __restrict__ f, const mg_geom3d& g, int x, int y,
+                                         int zl, const Coef3<T>& c, int corrected)
+{
+    const int col = (x + y + g.z0 + zl) & 1, q = x & 1;
+    const long long idx = (long long)zl * g.plane + (long long)y * g.hp + (x >> 1);
+    const T* own = v + (long long)col * g.cstride + idx;
+    const T* oth = v + (long long)(col ^ 1) * g.cstride + idx;
+    return residual_point<T, FAST>(oth[q - 1], oth[q], oth[-g.hp], oth[g.hp], oth[-g.plane], oth[g.plane], own[0],
+                                   f[(long long)col * g.cstride + idx], c, corrected);
 }
 
 // N3/MultiGrid3D.cpp:180 with the exact grouping.  R(dx,dy,dz) reads the fine value at offset
@@ -86,61 +116,62 @@ __device__ __forceinline__ T restrict_point(Getter R)
     return add(add(add(t1, t2), t3), t4);
 }
 
-// N3/MultiGrid3D.cpp:216-331: trilinear prolongation by parity of (y,x,z); c points at the coarse
-// value (cx,cy,cz) = (fx/2, fy/2, fz/2); summation orders as written in the reference.
-template <typename T>
-__device__ __forceinline__ T interp_point(const T* __restrict__ c, int cp, long long cq, int ox, int oy, int oz)
+// N3/MultiGrid3D.cpp:216-331: trilinear prolongation by parity of (y,x,z).  C(dx,dy,dz) reads the coarse
+// value (fx/2+dx, fy/2+dy, fz/2+dz); summation orders as written in the reference.
+template <typename T, typename Getter>
+__device__ __forceinline__ T interp_point(Getter C, int ox, int oy, int oz)
 {
     if (!oz) {
         if (!oy) {
-            if (!ox) return c[0];                                    // PPP :216
-            return mul(T(0.5f), add(c[0], c[1]));                    // PDP :222  O + E
+            if (!ox) return C(0, 0, 0);                                                    // PPP :216
+            return mul(T(0.5f), add(C(0, 0, 0), C(1, 0, 0)));                              // PDP :222  O + E
         }
-        if (!ox) return mul(T(0.5f), add(c[0], c[cp]));              // DPP :233  N + S
-        return mul(T(0.25f), add(add(add(c[0], c[1]), c[cp]), c[cp + 1]));  // DDP :244  NO+NE+SO+SE
+        if (!ox) return mul(T(0.5f), add(C(0, 0, 0), C(0, 1, 0)));                         // DPP :233  N + S
+        return mul(T(0.25f), add(add(add(C(0, 0, 0), C(1, 0, 0)), C(0, 1, 0)), C(1, 1, 0)));  // DDP :244
     }
     if (!oy) {
-        if (!ox) return mul(T(0.5f), add(c[0], c[cq]));              // PPD :261  S + N
-        return mul(T(0.25f), add(add(add(c[cq], c[cq + 1]), c[0]), c[1]));  // PDD :272
+        if (!ox) return mul(T(0.5f), add(C(0, 0, 0), C(0, 0, 1)));                         // PPD :261  S + N
+        return mul(T(0.25f), add(add(add(C(0, 0, 1), C(1, 0, 1)), C(0, 0, 0)), C(1, 0, 0)));  // PDD :272
     }
-    if (!ox) return mul(T(0.25f), add(add(add(c[0], c[cq]), c[cp]), c[cp + cq]));  // DPD :287
+    if (!ox) return mul(T(0.25f), add(add(add(C(0, 0, 0), C(0, 0, 1)), C(0, 1, 0)), C(0, 1, 1)));  // DPD :287
     // DDD :302  USO + UNO + UNE + USE + DSO + DNO + DNE + DSE
-    T s = add(c[0], c[cq]);
-    s = add(s, c[cq + 1]);
-    s = add(s, c[1]);
-    s = add(s, c[cp]);
-    s = add(s, c[cp + cq]);
-    s = add(s, c[cp + cq + 1]);
-    s = add(s, c[cp + 1]);
+    T s = add(C(0, 0, 0), C(0, 0, 1));
+    s = add(s, C(1, 0, 1));
+    s = add(s, C(1, 0, 0));
+    s = add(s, C(0, 1, 0));
+    s = add(s, C(0, 1, 1));
+    s = add(s, C(1, 1, 1));
+    s = add(s, C(1, 1, 0));
     return mul(T(0.125f), s);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Smoother, one colour per launch, in place (MG_SMOOTHER_COLOUR).  Red points only read black
-// neighbours and vice versa, so there is no race (unlike the reference's CUDARelax, which updates
-// both colours in one launch behind a block-local barrier, C3/MultiGrid3D.cu:635-673).
-// Thread t of a row owns the t-th point of the requested colour: x = 2t+1 or 2t+2.
+// Smoother: one colour per launch, in place.  Points of colour `colour` only read the other colour's
+// array, so there is no race (unlike the reference's CUDARelax, which updates both colours in one launch
+// behind a block-local barrier, C3/MultiGrid3D.cu:635-673).  Thread (i, y, zl) owns half-index i of row
+// (y, zl): x = 2i + q with q = (colour + y + z) & 1.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void k_relax_colour(T* __restrict__ v, const T* __restrict__ f, mg_geom3d g, Coef3<T> c, int colour,
-                               int zl_lo)
+template <typename T, bool FAST>
+__global__ void __launch_bounds__(256)
+k_relax_colour(T* __restrict__ v, const T* __restrict__ f, mg_geom3d g, Coef3<T> c, int colour, int zl_lo)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     const int zl = zl_lo + blockIdx.z;
-    const int z = g.z0 + zl;
     if (y > g.n - 2) return;
-    const int x = 2 * t + 2 - ((y + z + colour) & 1);  // x = (y+z+colour) mod 2, x >= 1
-    if (x > g.n - 2) return;
-    const long long i = (long long)zl * g.plane + (long long)y * g.pitch + x;
-    T O = v[i - 1], E = v[i + 1], N = v[i - g.pitch], S = v[i + g.pitch], D = v[i - g.plane], U = v[i + g.plane];
-    v[i] = relax_point<T>(O, E, N, S, D, U, f[i], c);
+    const int q = (colour + y + g.z0 + zl) & 1;
+    const int x = 2 * i + q;
+    if (x < 1 || x > g.n - 2) return;
+    const long long idx = (long long)zl * g.plane + (long long)y * g.hp + i;
+    const T* oth = v + (long long)(colour ^ 1) * g.cstride + idx;
+    const long long own = (long long)colour * g.cstride + idx;
+    v[own] = relax_point<T, FAST>(oth[q - 1], oth[q], oth[-g.hp], oth[g.hp], oth[-g.plane], oth[g.plane], f[own], c);
 }
 
 // ---------------------------------------------------------------------------------------------
-// CalculateResidual into a full array (only used when the caller asks for the residual itself).
+// CalculateResidual into a full (colour-split) array; only used when the caller asks for it.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool FAST>
 __global__ void k_residual(const T* __restrict__ v, const T* __restrict__ f, T* __restrict__ r, mg_geom3d g,
                            Coef3<T> c, int corrected, int zl_lo)
 {
@@ -149,13 +180,10 @@ __global__ void k_residual(const T* __restrict__ v, const T* __restrict__ f, T* 
     const int zl = zl_lo + blockIdx.z;
     const int z = g.z0 + zl;
     if (x >= g.n || y >= g.n) return;
-    const long long i = (long long)zl * g.plane + (long long)y * g.pitch + x;
-    if (x == 0 || x == g.n - 1 || y == 0 || y == g.n - 1 || z == 0 || z == g.n - 1) {
-        r[i] = T(0);
-        return;
-    }
-    r[i] = residual_point<T>(v[i - 1], v[i + 1], v[i - g.pitch], v[i + g.pitch], v[i - g.plane], v[i + g.plane], v[i],
-                             f[i], c, corrected);
+    T out = T(0);
+    if (!(x == 0 || x == g.n - 1 || y == 0 || y == g.n - 1 || z == 0 || z == g.n - 1))
+        out = residual_at<T, FAST>(v, f, g, x, y, zl, c, corrected);
+    r[off3(g, x, y, zl)] = out;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -181,9 +209,10 @@ __device__ __forceinline__ void block_reduce_sum_max(double& s, double& m, doubl
     }
 }
 
-template <typename T>
-__global__ void k_residual_norm(const T* __restrict__ v, const T* __restrict__ f, mg_geom3d g, Coef3<T> c,
-                                int corrected, int zl_lo, int zl_hi, double* __restrict__ part)
+template <typename T, bool FAST>
+__global__ void __launch_bounds__(256)
+k_residual_norm(const T* __restrict__ v, const T* __restrict__ f, mg_geom3d g, Coef3<T> c, int corrected, int zl_lo,
+                int zl_hi, double* __restrict__ part)
 {
     __shared__ double sh[64];
     double s = 0.0, m = 0.0;
@@ -194,12 +223,8 @@ __global__ void k_residual_norm(const T* __restrict__ v, const T* __restrict__ f
         const int y = 1 + (int)(row % ni);
         const int z = g.z0 + zl;
         if (z == 0 || z == g.n - 1) continue;
-        const long long base = (long long)zl * g.plane + (long long)y * g.pitch;
         for (int x = 1 + threadIdx.x; x <= g.n - 2; x += blockDim.x) {
-            const long long i = base + x;
-            T r = residual_point<T>(v[i - 1], v[i + 1], v[i - g.pitch], v[i + g.pitch], v[i - g.plane], v[i + g.plane],
-                                    v[i], f[i], c, corrected);
-            double rd = (double)r;
+            const double rd = (double)residual_at<T, FAST>(v, f, g, x, y, zl, c, corrected);
             s += rd * rd;
             m = fmax(m, fabs(rd));
         }
@@ -231,16 +256,13 @@ __global__ void k_restrict(const T* __restrict__ fine, mg_geom3d gf, T* __restri
     const int czl = czl_lo + blockIdx.z;
     const int cz = gc.z0 + czl;
     if (cx >= gc.n || cy >= gc.n) return;
-    const long long ci = (long long)czl * gc.plane + (long long)cy * gc.pitch + cx;
-    const long long fi = (long long)(2 * cz - gf.z0) * gf.plane + (long long)(2 * cy) * gf.pitch + 2 * cx;
-    if (cx == 0 || cx == gc.n - 1 || cy == 0 || cy == gc.n - 1 || cz == 0 || cz == gc.n - 1) {
-        coarse[ci] = fine[fi];  // N3/MultiGrid3D.cpp:113-119
-        return;
-    }
-    const T* p = fine + fi;
-    const int fp = gf.pitch;
-    const long long fq = gf.plane;
-    coarse[ci] = restrict_point<T>([&](int dx, int dy, int dz) { return p[dx + dy * fp + dz * fq]; });
+    const int fx = 2 * cx, fy = 2 * cy, fzl = 2 * cz - gf.z0;
+    T out;
+    if (cx == 0 || cx == gc.n - 1 || cy == 0 || cy == gc.n - 1 || cz == 0 || cz == gc.n - 1)
+        out = fine[off3(gf, fx, fy, fzl)];  // N3/MultiGrid3D.cpp:113-119
+    else
+        out = restrict_point<T>([&](int dx, int dy, int dz) { return fine[off3(gf, fx + dx, fy + dy, fzl + dz)]; });
+    coarse[off3(gc, cx, cy, czl)] = out;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -249,7 +271,7 @@ __global__ void k_restrict(const T* __restrict__ fine, mg_geom3d gf, T* __restri
 // (2CX+1)(2CY+1)(2CZ+1) fine points around the tile into shared memory (fine boundary = 0 as in
 // CalculateResidual) and restricts from there.  The fine residual never goes to HBM.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int CX, int CY, int CZ>
+template <typename T, bool FAST, int CX, int CY, int CZ>
 __global__ void __launch_bounds__(256)
 k_residual_restrict(const T* __restrict__ v, const T* __restrict__ f, mg_geom3d gf, Coef3<T> c, int corrected,
                     T* __restrict__ cf, T* __restrict__ cv, mg_geom3d gc, int czl_lo, int czl_hi)
@@ -269,11 +291,7 @@ k_residual_restrict(const T* __restrict__ v, const T* __restrict__ f, mg_geom3d 
         T val = T(0);
         if (fx >= 1 && fx <= n - 2 && fy >= 1 && fy <= n - 2 && fz >= 1 && fz <= n - 2) {
             const int fzl = fz - gf.z0;
-            if (fzl >= 1 && fzl <= gf.nzl - 2) {
-                const long long idx = (long long)fzl * gf.plane + (long long)fy * gf.pitch + fx;
-                val = residual_point<T>(v[idx - 1], v[idx + 1], v[idx - gf.pitch], v[idx + gf.pitch], v[idx - gf.plane],
-                                        v[idx + gf.plane], v[idx], f[idx], c, corrected);
-            }
+            if (fzl >= 1 && fzl <= gf.nzl - 2) val = residual_at<T, FAST>(v, f, gf, fx, fy, fzl, c, corrected);
         }
         r[lz][ly][lx] = val;
     }
@@ -283,24 +301,25 @@ k_residual_restrict(const T* __restrict__ v, const T* __restrict__ f, mg_geom3d 
         const int tx = i % CX, ty = (i / CX) % CY, tz = i / (CX * CY);
         const int cx = cx0 + tx, cy = cy0 + ty, czl = czl0 + tz, cz = cz0 + tz;
         if (cx >= gc.n || cy >= gc.n || czl >= czl_hi) continue;
-        const long long ci = (long long)czl * gc.plane + (long long)cy * gc.pitch + cx;
         T out = T(0);  // boundary: injection of the (zero) boundary residual, N3/MultiGrid3D.cpp:113-119 + :705
         if (!(cx == 0 || cx == gc.n - 1 || cy == 0 || cy == gc.n - 1 || cz == 0 || cz == gc.n - 1)) {
             const int lx = 2 * tx + 1, ly = 2 * ty + 1, lz = 2 * tz + 1;
             out = restrict_point<T>([&](int dx, int dy, int dz) { return r[lz + dz][ly + dy][lx + dx]; });
         }
+        const long long ci = off3(gc, cx, cy, czl);
         cf[ci] = out;
         cv[ci] = T(0);  // setToValue(coarse->h_v, 0, true), N3/MultiGrid3D.cpp:634
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Interpolate (+ ApplyCorrection when add != 0).  A thread owns the fine pair (2i, 2i+1) of a row,
-// so x-parity is compile-time per statement and (y,z) parity is uniform per row: no divergence.
+// Interpolate (+ ApplyCorrection when add != 0).  Thread (i, y, zl) owns the fine pair x = 2i, 2i+1 of
+// row (y, zl): both live at half-index i, one in each colour array (coalesced, no divergence: x-parity
+// is per statement, (y,z) parity is uniform per row).
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void k_interpolate(T* __restrict__ fine, mg_geom3d gf, const T* __restrict__ coarse, mg_geom3d gc, int add_,
-                              int zl_lo)
+__global__ void __launch_bounds__(256)
+k_interpolate(T* __restrict__ fine, mg_geom3d gf, const T* __restrict__ coarse, mg_geom3d gc, int add_, int zl_lo)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // pair index: x = 2i, 2i+1
     const int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
@@ -309,15 +328,18 @@ __global__ void k_interpolate(T* __restrict__ fine, mg_geom3d gf, const T* __res
     if (y > gf.n - 2 || 2 * i > gf.n - 2) return;
     const int oy = y & 1, oz = z & 1;
     const int cy = y >> 1, czl = (z >> 1) - gc.z0;
-    const T* c = coarse + (long long)czl * gc.plane + (long long)cy * gc.pitch + i;
-    T* p = fine + (long long)zl * gf.plane + (long long)y * gf.pitch + 2 * i;
+    auto C = [&](int dx, int dy, int dz) { return coarse[off3(gc, i + dx, cy + dy, czl + dz)]; };
+    const int c0 = (y + z) & 1;  // colour of the even-x point of the pair
+    const long long idx = (long long)zl * gf.plane + (long long)y * gf.hp + i;
     if (i >= 1) {  // x = 2i even, interior
-        T e = interp_point<T>(c, gc.pitch, gc.plane, 0, oy, oz);
-        p[0] = add_ ? add(p[0], e) : e;
+        T* p = fine + (long long)c0 * gf.cstride + idx;
+        const T e = interp_point<T>(C, 0, oy, oz);
+        *p = add_ ? add(*p, e) : e;
     }
     if (2 * i + 1 <= gf.n - 2) {
-        T e = interp_point<T>(c, gc.pitch, gc.plane, 1, oy, oz);
-        p[1] = add_ ? add(p[1], e) : e;
+        T* p = fine + (long long)(c0 ^ 1) * gf.cstride + idx;
+        const T e = interp_point<T>(C, 1, oy, oz);
+        *p = add_ ? add(*p, e) : e;
     }
 }
 
@@ -328,7 +350,7 @@ __global__ void k_apply_correction(T* __restrict__ fine, const T* __restrict__ e
     const int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     const int zl = zl_lo + blockIdx.z;
     if (x > g.n - 2 || y > g.n - 2) return;
-    const long long i = (long long)zl * g.plane + (long long)y * g.pitch + x;
+    const long long i = off3(g, x, y, zl);
     fine[i] = add(fine[i], err[i]);
 }
 
@@ -341,7 +363,7 @@ __global__ void k_set(T* __restrict__ a, mg_geom3d g, T value, int modify_bounda
     const int z = g.z0 + zl;
     if (x >= g.n || y >= g.n) return;
     if (!modify_boundaries && (x == 0 || x == g.n - 1 || y == 0 || y == g.n - 1 || z == 0 || z == g.n - 1)) return;
-    a[(long long)zl * g.plane + (long long)y * g.pitch + x] = value;
+    a[off3(g, x, y, zl)] = value;
 }
 
 // N3/Grid3D.cpp:92: h_f = -3*PI*PI*sin(PI*x)*sin(PI*y)*sin(PI*z) evaluated left to right in double,
@@ -357,35 +379,81 @@ __global__ void k_init_f(T* __restrict__ f, mg_geom3d g, const double* __restric
     if (x >= g.n || y >= g.n) return;
     const double PI = 3.141592653589793;
     const double k = __dmul_rn(__dmul_rn(-3.0, PI), PI);
-    f[(long long)zl * g.plane + (long long)y * g.pitch + x] = (T)__dmul_rn(__dmul_rn(__dmul_rn(k, sx[x]), sy[y]), sz[z]);
+    f[off3(g, x, y, zl)] = (T)__dmul_rn(__dmul_rn(__dmul_rn(k, sx[x]), sy[y]), sz[z]);
 }
 
-template <typename T>
-__global__ void k_copy_rows(T* __restrict__ dst, long long dpitch, const T* __restrict__ src, long long spitch, int width,
-                            long long rows)
+// dense (reference layout: x fastest, idx = x + y*n + zl*n*n) <-> colour-split device field
+template <typename T, int TO_DEVICE>
+__global__ void k_repack(T* __restrict__ split, mg_geom3d g, T* __restrict__ dense, int zl_lo)
 {
-    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
-        const T* s = src + r * spitch;
-        T* d = dst + r * dpitch;
-        for (int x = threadIdx.x; x < width; x += blockDim.x) d[x] = s[x];
-    }
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int zl = zl_lo + blockIdx.z;
+    if (x >= g.n || y >= g.n) return;
+    const long long d = (long long)(zl - zl_lo) * g.n * g.n + (long long)y * g.n + x;
+    if (TO_DEVICE) split[off3(g, x, y, zl)] = dense[d];
+    else dense[d] = split[off3(g, x, y, zl)];
 }
 
 inline int launch_ok() { return cudaPeekAtLastError() == cudaSuccess ? 1 : -1; }
 
 inline dim3 block2d(int nx) { int bx = nx >= 128 ? 128 : (nx >= 64 ? 64 : 32); return dim3(bx, 256 / bx, 1); }
 
+// launch geometry of the row-of-half-indices kernels (relax, interpolate): `cols` threads per row
+inline void half_row_launch(int cols, int n, int nz, dim3& block, dim3& grid)
+{
+    int bx = 32;
+    while (bx < 128 && bx < cols) bx <<= 1;
+    int by = 256 / bx;
+    if (by > n - 2) by = n - 2;
+    if (by < 1) by = 1;
+    block = dim3(bx, by, 1);
+    grid = dim3((cols + bx - 1) / bx, (n - 2 + by - 1) / by, nz);
+}
+
 template <typename T>
 int relax_colour_t(cudaStream_t s, T* v, const T* f, mg_geom3d g, mg_coef3d c, int colour, int zl_lo, int zl_hi)
 {
     if (zl_hi <= zl_lo || g.n < 3) return 0;
-    const int halfw = (g.n - 1) / 2;
-    int bx = halfw < 128 ? halfw : 128;
-    int by = 256 / bx;
-    if (by > g.n - 2) by = g.n - 2;
-    if (by < 1) by = 1;
-    dim3 block(bx, by, 1), grid((halfw + bx - 1) / bx, (g.n - 2 + by - 1) / by, zl_hi - zl_lo);
-    k_relax_colour<T><<<grid, block, 0, s>>>(v, f, g, narrow<T>(c), colour, zl_lo);
+    dim3 block, grid;
+    half_row_launch((g.n - 1) / 2, g.n, zl_hi - zl_lo, block, grid);
+    if (c.fast_den) k_relax_colour<T, true><<<grid, block, 0, s>>>(v, f, g, narrow<T>(c), colour, zl_lo);
+    else k_relax_colour<T, false><<<grid, block, 0, s>>>(v, f, g, narrow<T>(c), colour, zl_lo);
+    return launch_ok();
+}
+
+template <typename T>
+int residual_t(cudaStream_t s, const T* v, const T* f, T* r, mg_geom3d g, mg_coef3d c, int corrected, int zl_lo, int zl_hi)
+{
+    if (zl_hi <= zl_lo) return 0;
+    dim3 block = block2d(g.n), grid((g.n + block.x - 1) / block.x, (g.n + block.y - 1) / block.y, zl_hi - zl_lo);
+    if (c.fast_h) k_residual<T, true><<<grid, block, 0, s>>>(v, f, r, g, narrow<T>(c), corrected, zl_lo);
+    else k_residual<T, false><<<grid, block, 0, s>>>(v, f, r, g, narrow<T>(c), corrected, zl_lo);
+    return launch_ok();
+}
+
+template <typename T>
+int residual_norm_t(cudaStream_t s, const T* v, const T* f, mg_geom3d g, mg_coef3d c, int corrected, int zl_lo, int zl_hi,
+                    double* scratch, double* out2)
+{
+    const int nb = MGK_NORM_BLOCKS;
+    if (c.fast_h) k_residual_norm<T, true><<<nb, 256, 0, s>>>(v, f, g, narrow<T>(c), corrected, zl_lo, zl_hi, scratch);
+    else k_residual_norm<T, false><<<nb, 256, 0, s>>>(v, f, g, narrow<T>(c), corrected, zl_lo, zl_hi, scratch);
+    k_norm_final<<<1, 256, 0, s>>>(scratch, nb, out2);
+    return launch_ok() < 0 ? -1 : 2;
+}
+
+template <typename T>
+int residual_restrict_t(cudaStream_t s, const T* v, const T* f, mg_geom3d gf, mg_coef3d c, int corrected, T* cf, T* cv,
+                        mg_geom3d gc, int czl_lo, int czl_hi)
+{
+    if (czl_hi <= czl_lo) return 0;
+    constexpr int CX = 16, CY = 8, CZ = 4;
+    dim3 grid((gc.n + CX - 1) / CX, (gc.n + CY - 1) / CY, (czl_hi - czl_lo + CZ - 1) / CZ);
+    if (c.fast_h)
+        k_residual_restrict<T, true, CX, CY, CZ><<<grid, 256, 0, s>>>(v, f, gf, narrow<T>(c), corrected, cf, cv, gc, czl_lo, czl_hi);
+    else
+        k_residual_restrict<T, false, CX, CY, CZ><<<grid, 256, 0, s>>>(v, f, gf, narrow<T>(c), corrected, cf, cv, gc, czl_lo, czl_hi);
     return launch_ok();
 }
 
@@ -405,25 +473,15 @@ int mgk3d_relax_colour(cudaStream_t s, int dtype, void* v, const void* f, mg_geo
 int mgk3d_residual(cudaStream_t s, int dtype, const void* v, const void* f, void* r, mg_geom3d g, mg_coef3d c,
                    int corrected, int zl_lo, int zl_hi)
 {
-    if (zl_hi <= zl_lo) return 0;
-    dim3 block = block2d(g.n), grid((g.n + block.x - 1) / block.x, (g.n + block.y - 1) / block.y, zl_hi - zl_lo);
-    if (dtype == 0)
-        k_residual<float><<<grid, block, 0, s>>>((const float*)v, (const float*)f, (float*)r, g, narrow<float>(c), corrected, zl_lo);
-    else
-        k_residual<double><<<grid, block, 0, s>>>((const double*)v, (const double*)f, (double*)r, g, narrow<double>(c), corrected, zl_lo);
-    return launch_ok();
+    return DISPATCH(dtype, residual_t<float>(s, (const float*)v, (const float*)f, (float*)r, g, c, corrected, zl_lo, zl_hi),
+                    residual_t<double>(s, (const double*)v, (const double*)f, (double*)r, g, c, corrected, zl_lo, zl_hi));
 }
 
 int mgk3d_residual_norm(cudaStream_t s, int dtype, const void* v, const void* f, mg_geom3d g, mg_coef3d c,
                         int corrected, int zl_lo, int zl_hi, double* scratch, double* out2)
 {
-    const int nb = MGK_NORM_BLOCKS;
-    if (dtype == 0)
-        k_residual_norm<float><<<nb, 256, 0, s>>>((const float*)v, (const float*)f, g, narrow<float>(c), corrected, zl_lo, zl_hi, scratch);
-    else
-        k_residual_norm<double><<<nb, 256, 0, s>>>((const double*)v, (const double*)f, g, narrow<double>(c), corrected, zl_lo, zl_hi, scratch);
-    k_norm_final<<<1, 256, 0, s>>>(scratch, nb, out2);
-    return launch_ok() < 0 ? -1 : 2;
+    return DISPATCH(dtype, residual_norm_t<float>(s, (const float*)v, (const float*)f, g, c, corrected, zl_lo, zl_hi, scratch, out2),
+                    residual_norm_t<double>(s, (const double*)v, (const double*)f, g, c, corrected, zl_lo, zl_hi, scratch, out2));
 }
 
 int mgk3d_restrict(cudaStream_t s, int dtype, const void* fine, mg_geom3d gf, void* coarse, mg_geom3d gc, int czl_lo,
@@ -441,28 +499,17 @@ int mgk3d_restrict(cudaStream_t s, int dtype, const void* fine, mg_geom3d gf, vo
 int mgk3d_residual_restrict(cudaStream_t s, int dtype, const void* v, const void* f, mg_geom3d gf, mg_coef3d c,
                             int corrected, void* coarse_f, void* coarse_v, mg_geom3d gc, int czl_lo, int czl_hi)
 {
-    if (czl_hi <= czl_lo) return 0;
-    constexpr int CX = 16, CY = 8, CZ = 4;
-    dim3 grid((gc.n + CX - 1) / CX, (gc.n + CY - 1) / CY, (czl_hi - czl_lo + CZ - 1) / CZ);
-    if (dtype == 0)
-        k_residual_restrict<float, CX, CY, CZ><<<grid, 256, 0, s>>>((const float*)v, (const float*)f, gf, narrow<float>(c), corrected,
-                                                                    (float*)coarse_f, (float*)coarse_v, gc, czl_lo, czl_hi);
-    else
-        k_residual_restrict<double, CX, CY, CZ><<<grid, 256, 0, s>>>((const double*)v, (const double*)f, gf, narrow<double>(c), corrected,
-                                                                     (double*)coarse_f, (double*)coarse_v, gc, czl_lo, czl_hi);
-    return launch_ok();
+    return DISPATCH(dtype,
+                    residual_restrict_t<float>(s, (const float*)v, (const float*)f, gf, c, corrected, (float*)coarse_f, (float*)coarse_v, gc, czl_lo, czl_hi),
+                    residual_restrict_t<double>(s, (const double*)v, (const double*)f, gf, c, corrected, (double*)coarse_f, (double*)coarse_v, gc, czl_lo, czl_hi));
 }
 
 int mgk3d_interpolate(cudaStream_t s, int dtype, void* fine, mg_geom3d gf, const void* coarse, mg_geom3d gc, int add,
                       int zl_lo, int zl_hi)
 {
     if (zl_hi <= zl_lo || gf.n < 3) return 0;
-    const int pairs = (gf.n - 1) / 2;  // pair i covers x = 2i, 2i+1 <= n-2
-    int bx = pairs < 128 ? pairs : 128;
-    int by = 256 / bx;
-    if (by > gf.n - 2) by = gf.n - 2;
-    if (by < 1) by = 1;
-    dim3 block(bx, by, 1), grid((pairs + bx - 1) / bx, (gf.n - 2 + by - 1) / by, zl_hi - zl_lo);
+    dim3 block, grid;
+    half_row_launch((gf.n - 1) / 2, gf.n, zl_hi - zl_lo, block, grid);  // pair i covers x = 2i, 2i+1 <= n-2
     if (dtype == 0)
         k_interpolate<float><<<grid, block, 0, s>>>((float*)fine, gf, (const float*)coarse, gc, add, zl_lo);
     else
@@ -493,19 +540,6 @@ int mgk3d_set(cudaStream_t s, int dtype, void* a, mg_geom3d g, double value, int
     return launch_ok();
 }
 
-int mgk_copy_rows(cudaStream_t s, int dtype, void* dst, long long dpitch, const void* src, long long spitch, int width,
-                  long long rows)
-{
-    if (rows <= 0 || width <= 0) return 0;
-    const int threads = width >= 256 ? 256 : (width >= 64 ? 64 : 32);
-    const long long want = rows < (1LL << 20) ? rows : (1LL << 20);
-    if (dtype == 0)
-        k_copy_rows<float><<<(unsigned)want, threads, 0, s>>>((float*)dst, dpitch, (const float*)src, spitch, width, rows);
-    else
-        k_copy_rows<double><<<(unsigned)want, threads, 0, s>>>((double*)dst, dpitch, (const double*)src, spitch, width, rows);
-    return launch_ok();
-}
-
 int mgk3d_init_f(cudaStream_t s, int dtype, void* f, mg_geom3d g, const double* sx, const double* sy,
                  const double* sz, int zl_lo, int zl_hi)
 {
@@ -515,6 +549,20 @@ int mgk3d_init_f(cudaStream_t s, int dtype, void* f, mg_geom3d g, const double* 
         k_init_f<float><<<grid, block, 0, s>>>((float*)f, g, sx, sy, sz, zl_lo);
     else
         k_init_f<double><<<grid, block, 0, s>>>((double*)f, g, sx, sy, sz, zl_lo);
+    return launch_ok();
+}
+
+int mgk3d_repack(cudaStream_t s, int dtype, void* split, mg_geom3d g, void* dense, int to_device, int zl_lo, int zl_hi)
+{
+    if (zl_hi <= zl_lo) return 0;
+    dim3 block = block2d(g.n), grid((g.n + block.x - 1) / block.x, (g.n + block.y - 1) / block.y, zl_hi - zl_lo);
+    if (dtype == 0) {
+        if (to_device) k_repack<float, 1><<<grid, block, 0, s>>>((float*)split, g, (float*)dense, zl_lo);
+        else k_repack<float, 0><<<grid, block, 0, s>>>((float*)split, g, (float*)dense, zl_lo);
+    } else {
+        if (to_device) k_repack<double, 1><<<grid, block, 0, s>>>((double*)split, g, (double*)dense, zl_lo);
+        else k_repack<double, 0><<<grid, block, 0, s>>>((double*)split, g, (double*)dense, zl_lo);
+    }
     return launch_ok();
 }
 

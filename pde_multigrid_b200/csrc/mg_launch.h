@@ -2,13 +2,15 @@
  * mg_launch.h -- internal C interface between the C host drivers (mg*_host.c) and the CUDA
  * translation units (mg*_kernels.cu).  Not part of the public ABI (that is include/mg_b200.h).
  *
- * Device layout (all levels, all fields): pitched, x fastest.
- *     element (x,y,zl) of a 3D slab lives at  base[x + y*pitch + zl*plane],  plane = pitch*n
- *     pitch = n rounded up to 128 bytes, base 256-byte aligned -> every row starts 128-B aligned,
- *     every row stride is a multiple of 16 B (TMA-addressable; the reference's dense rows of
- *     (2^k+1)*8 B are not).
+ * 3D device layout (all levels, all fields): colour-split, x fastest.  A field is two arrays, one per
+ * red-black colour c = (x+y+z)&1, each compacted along x:
+ *     element (x,y,zl) lives at  base[c*cstride + zl*plane + y*hp + (x>>1)]
+ *     hp = (n+1)/2 rounded up to 128 bytes, plane = hp*n, cstride = plane*nzl, base 256-byte aligned.
+ * A half-sweep of one colour then touches only that colour's half of v and f (unit stride) and reads the
+ * other colour's half of v: 12 B/point in fp64 instead of 24 B/point with interleaved colours.
  * A slab holds local planes zl = 0..nzl-1 which are the global planes z = z0 .. z0+nzl-1; on one
  * GPU z0 = 0 and nzl = n.  Multi-GPU slabs carry ghost planes at both ends.
+ * 2D fields are pitched (element (x,y) at base[x + y*pitch]); the 1D hierarchy is one arena.
  *
  * Real-valued parameters travel as double; for MG_F32 they hold float values exactly (computed
  * in float on the host, widened) and the kernels narrow them back without rounding.
@@ -23,11 +25,12 @@ extern "C" {
 #endif
 
 typedef struct {
-    int n;           /* global points per axis (cubic: sizeX = sizeY = sizeZ, N3/Grid3D.cpp:10-11) */
-    int pitch;       /* elements per row */
-    long long plane; /* elements per z-plane */
-    int z0;          /* global z of local plane 0 */
-    int nzl;         /* local planes stored */
+    int n;             /* global points per axis (cubic: sizeX = sizeY = sizeZ, N3/Grid3D.cpp:10-11) */
+    int hp;            /* elements per half-row (one colour of one row) */
+    long long plane;   /* elements per z-plane of ONE colour array = hp*n */
+    long long cstride; /* elements between the two colour arrays = plane*nzl */
+    int z0;            /* global z of local plane 0 */
+    int nzl;           /* local planes stored */
 } mg_geom3d;
 
 /* coefficient block of one 3D level, all values exactly representable in the level's dtype */
@@ -36,6 +39,9 @@ typedef struct {
     double cx, cy, cz;    /* hy2*hz2, hx2*hz2, hx2*hy2 */
     double den;           /* 2*(cx + cy + cz), N3/MultiGrid3D.cpp:532 */
     double rden;          /* RN(1/den) */
+    double ihx2, ihy2, ihz2; /* 1/h^2 per axis (exact when h^2 is a power of two) */
+    int fast_den;         /* den = 6*2^e: quotient by the 3-op exact sequence of mg_exact.cuh */
+    int fast_h;           /* every h^2 is a power of two: x/h^2 == x*(1/h^2) exactly */
 } mg_coef3d;
 
 /* every launcher returns the number of kernels it launched (>= 0) or -1 on a launch error */
@@ -71,10 +77,8 @@ int mgk3d_set(cudaStream_t s, int dtype, void* a, mg_geom3d g, double value, int
 int mgk3d_init_f(cudaStream_t s, int dtype, void* f, mg_geom3d g, const double* sx, const double* sy,
                  const double* sz, int zl_lo, int zl_hi);
 
-/* rows x width elements, row strides dpitch / spitch (elements): dense <-> pitched repacking at the
-   ABI boundary (all dimensions: a 3D slab is n*nzl rows) */
-int mgk_copy_rows(cudaStream_t s, int dtype, void* dst, long long dpitch, const void* src, long long spitch, int width,
-                  long long rows);
+/* dense (reference layout, x fastest, zl_hi-zl_lo planes starting at `dense`) <-> colour-split field */
+int mgk3d_repack(cudaStream_t s, int dtype, void* split, mg_geom3d g, void* dense, int to_device, int zl_lo, int zl_hi);
 
 /* ---- 2D (pitched: element (x,y) at base[x + y*pitch]) ---- */
 typedef struct {
