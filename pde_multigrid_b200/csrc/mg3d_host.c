@@ -22,6 +22,9 @@ typedef struct {
     double h[3];    /* h_x, h_y, h_z (values of the level's dtype) */
     int own_lo;     /* local plane range [own_lo, own_hi) owned by this rank */
     int own_hi;
+    int has_tma;    /* tensor maps of the two colour arrays of v are valid */
+    unsigned char tmap_v[2][128] __attribute__((aligned(64)));  /* smoother boxes */
+    unsigned char tmap_rr[2][128] __attribute__((aligned(64))); /* residual+restrict boxes */
 } mg_level3d;
 
 struct mg3d_s {
@@ -162,7 +165,20 @@ int mg3d_create(mg3d_t** out, const int sz[3], const double range[6], int dtype,
         mg3d_destroy(mg);
         return code;
     }
-    /* pad bytes of the pitched layout are never read by a kernel, but keep them defined */
+    /* TMA tensor maps of v for the levels large enough to fill the z-marching tiles */
+    for (int l = 0; l < mg->nlevels; l++) {
+        mg_level3d* L = &mg->lv[l];
+        if ((L->g.n - 1) / 2 < MGK3D_TMA_IT || getenv("MG_B200_NO_TMA")) continue;
+        for (int col = 0; col < 2; col++) {
+            st = mg_tma_make_colour_map(L->tmap_v[col], dtype, (char*)L->v + (size_t)col * L->g.cstride * mg_esize(dtype), &L->g,
+                                        MGK3D_TMA_BOX_I(mg_esize(dtype)), MGK3D_TMA_BOX_Y);
+            if (!st) st = mg_tma_make_colour_map(L->tmap_rr[col], dtype, (char*)L->v + (size_t)col * L->g.cstride * mg_esize(dtype), &L->g,
+                                                 MGK3D_RR_BOX_I(mg_esize(dtype)), MGK3D_RR_BOX_Y);
+            if (st) { mg3d_destroy(mg); return st; }
+        }
+        L->has_tma = 1;
+    }
+    /* pad elements of the layout are never used by a kernel, but keep them defined */
     MG_CUDA(cudaMemsetAsync(mg->arena, 0, total, mg->stream));
     st = mg3d_init_problem(mg);
     if (st) { mg3d_destroy(mg); return st; }
@@ -325,9 +341,14 @@ static int relax_level(mg3d_t* mg, int level, int ncycles)
     const int hi = L->own_hi < L->g.nzl - 1 ? L->own_hi : L->g.nzl - 1;
     if (ncycles <= 0) return MG_OK;
     PROF_BEGIN(mg, level, MG_OP_RELAX);
+    const int use_tma = L->has_tma && mg->smoother != MG_SMOOTHER_COLOUR;
     for (int k = 0; k < ncycles; k++)
-        for (int colour = 0; colour < 2; colour++)
-            MG_LAUNCH(mg->launches, mgk3d_relax_colour(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, colour, lo, hi));
+        for (int colour = 0; colour < 2; colour++) {
+            if (use_tma)
+                MG_LAUNCH(mg->launches, mgk3d_relax_colour_tma(mg->stream, mg->dtype, L->tmap_v[colour ^ 1], L->v, L->f, L->g, L->c, colour, lo, hi));
+            else
+                MG_LAUNCH(mg->launches, mgk3d_relax_colour(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, colour, lo, hi));
+        }
     PROF_END(mg);
     return MG_OK;
 }
@@ -382,15 +403,26 @@ int mg3d_restrict(mg3d_t* mg, int fine_level, int field)
     return MG_OK;
 }
 
+static int residual_restrict_level(mg3d_t* mg, int fine_level)
+{
+    mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
+    PROF_BEGIN(mg, fine_level, MG_OP_RESIDUAL_RESTRICT);
+    if (F->has_tma && mg->smoother != MG_SMOOTHER_COLOUR)
+        MG_LAUNCH(mg->launches, mgk3d_residual_restrict_tma(mg->stream, mg->dtype, F->tmap_rr[0], F->tmap_rr[1], F->f, F->g, F->c,
+                                                            mg->mode == MG_CORRECTED, C->f, C->v, C->g, C->own_lo, C->own_hi));
+    else
+        MG_LAUNCH(mg->launches, mgk3d_residual_restrict(mg->stream, mg->dtype, F->v, F->f, F->g, F->c, mg->mode == MG_CORRECTED,
+                                                        C->f, C->v, C->g, C->own_lo, C->own_hi));
+    PROF_END(mg);
+    return MG_OK;
+}
+
 int mg3d_residual_restrict(mg3d_t* mg, int fine_level)
 {
     int st = check_level(mg, fine_level);
     if (st) return st;
     if (fine_level == mg->nlevels - 1) return mg_fail(MG_ERR_ARG, "level %d is the coarsest", fine_level);
-    mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
-    MG_LAUNCH(mg->launches, mgk3d_residual_restrict(mg->stream, mg->dtype, F->v, F->f, F->g, F->c, mg->mode == MG_CORRECTED,
-                                                    C->f, C->v, C->g, C->own_lo, C->own_hi));
-    return MG_OK;
+    return residual_restrict_level(mg, fine_level);
 }
 
 static int interpolate_level(mg3d_t* mg, int fine_level, int add)
@@ -437,11 +469,8 @@ static int vcycle_rec(mg3d_t* mg, int level, int v1, int v2)
     int st = relax_level(mg, level, v1);
     if (st) return st;
     if (level != mg->nlevels - 1) {
-        mg_level3d *F = &mg->lv[level], *C = &mg->lv[level + 1];
-        PROF_BEGIN(mg, level, MG_OP_RESIDUAL_RESTRICT);
-        MG_LAUNCH(mg->launches, mgk3d_residual_restrict(mg->stream, mg->dtype, F->v, F->f, F->g, F->c, mg->mode == MG_CORRECTED,
-                                                        C->f, C->v, C->g, C->own_lo, C->own_hi));
-        PROF_END(mg);
+        st = residual_restrict_level(mg, level);
+        if (st) return st;
         st = vcycle_rec(mg, level + 1, v1, v2);
         if (st) return st;
         st = interpolate_level(mg, level, 1);

@@ -48,6 +48,8 @@ static inline int mg_num_levels_for(int n)
     while (m > 1) { m >>= 1; k++; }
     return k;
 }
+/* 128-byte CUtensorMap over one colour array of a colour-split 3D field (mg_tma_host.c) */
+int mg_tma_make_colour_map(void* out128, int dtype, void* base, const mg_geom3d* g, int box_i, int box_y);
 int mg_require_device(void); /* MG_OK, or MG_ERR_CUDA with a message: there is no CPU fallback */
 
 #ifdef __cplusplus

@@ -49,6 +49,14 @@ typedef struct {
 /* one colour of one RB Gauss-Seidel sweep, in place, on local planes [zl_lo, zl_hi) */
 int mgk3d_relax_colour(cudaStream_t s, int dtype, void* v, const void* f, mg_geom3d g, mg_coef3d c, int colour,
                        int zl_lo, int zl_hi);
+/* same half-sweep with TMA-staged z-marching shared-memory tiles (mg3d_smooth_tma.cu); tmap_other is the
+   128-byte CUtensorMap of the OTHER colour's v array built with box (MGK3D_TMA_BOX_I(esize), MGK3D_TMA_BOX_Y, 1) */
+#define MGK3D_TMA_IT 128
+#define MGK3D_TMA_YT 8
+#define MGK3D_TMA_BOX_I(esize) (MGK3D_TMA_IT + 2 * (16 / (int)(esize)))
+#define MGK3D_TMA_BOX_Y (MGK3D_TMA_YT + 2)
+int mgk3d_relax_colour_tma(cudaStream_t s, int dtype, const void* tmap_other, void* v, const void* f, mg_geom3d g,
+                           mg_coef3d c, int colour, int zl_lo, int zl_hi);
 /* r = CalculateResidual, full array incl. zero boundary, local planes [zl_lo, zl_hi) */
 int mgk3d_residual(cudaStream_t s, int dtype, const void* v, const void* f, void* r, mg_geom3d g, mg_coef3d c,
                    int corrected, int zl_lo, int zl_hi);
@@ -64,6 +72,15 @@ int mgk3d_restrict(cudaStream_t s, int dtype, const void* fine, mg_geom3d gf, vo
    residual only ever exists in shared memory */
 int mgk3d_residual_restrict(cudaStream_t s, int dtype, const void* v, const void* f, mg_geom3d gf, mg_coef3d c,
                             int corrected, void* coarse_f, void* coarse_v, mg_geom3d gc, int czl_lo, int czl_hi);
+/* the same with TMA-staged z-marching tiles (mg3d_rr_tma.cu): tensor maps of the two colour arrays of the
+   FINE v, built with box (MGK3D_RR_BOX_I(esize), MGK3D_RR_BOX_Y, 1) */
+#define MGK3D_RR_CXT 32
+#define MGK3D_RR_CYT 8
+#define MGK3D_RR_BOX_Y (2 * MGK3D_RR_CYT + 3)
+#define MGK3D_RR_BOX_I(esize) ((MGK3D_RR_CXT + 2 * (16 / (int)(esize))) / (16 / (int)(esize)) * (16 / (int)(esize)))
+int mgk3d_residual_restrict_tma(cudaStream_t s, int dtype, const void* tmap_v_c0, const void* tmap_v_c1, const void* f,
+                                mg_geom3d gf, mg_coef3d c, int corrected, void* coarse_f, void* coarse_v, mg_geom3d gc,
+                                int czl_lo, int czl_hi);
 /* fine interior = Interpolate(coarse) (add == 0) or fine interior += Interpolate(coarse) (add != 0) */
 int mgk3d_interpolate(cudaStream_t s, int dtype, void* fine, mg_geom3d gf, const void* coarse, mg_geom3d gc, int add,
                       int zl_lo, int zl_hi);

@@ -104,7 +104,7 @@ def test_restrict_interpolate_correct_set_host_ops(mg, n, dtype):
 
 @pytest.mark.parametrize("corrected", [False, True])
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("n", [5, 9, 17, 33, 65, 129])
+@pytest.mark.parametrize("n", [5, 9, 17, 33, 65, 129, 257])
 def test_fused_residual_restrict_and_interpolate_correct(mg, n, dtype, corrected):
     eng, orcs, v0, f0 = _pair(mg, n, dtype, corrected, RANGES[1])
     rng = np.random.default_rng(99)
@@ -197,3 +197,52 @@ def test_argument_errors(mg):
     with pytest.raises(mg.MGError):
         eng.Interpolate(np.zeros((9,) * 3, np.float32), np.zeros((4,) * 3, np.float32))
     eng.close()
+
+
+# ---- large levels: the TMA-staged z-marching smoother (n >= 257) --------------------------------
+
+@pytest.mark.parametrize("rng_range", RANGES)
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_relax_tma_path_vs_oracle(mg, dtype, rng_range):
+    n = 257
+    eng, orcs, _, _ = _pair(mg, n, dtype, False, rng_range)
+    eng.Relax(0, 2)
+    got = eng.get_v(0)
+    o = orcs[0]  # the C restatement (the compiled reference is ~10x slower at this size)
+    o.relax(0, 2)
+    assert_bits_equal(got, o.v(0), "Relax n=257 (TMA smoother)")
+    eng.close()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_vcycle_257_vs_oracle(mg, dtype):
+    n = 257
+    eng = mg.MultiGrid3D(n, dtype=dtype, residual_mode=mg.MG_CORRECTED)
+    o = oracles(3, dtype, True, n)[0]
+    eng.VCycle(0, 2, 2)
+    o.vcycle(0, 2, 2)
+    for l in range(eng.numGrids):
+        assert_bits_equal(eng.get_v(l), o.v(l), "v level %d after V(2,2) at 257^3" % l)
+    l2, linf = eng.residual_norm(0)
+    ol2, olinf = o.residual_norms(0)
+    assert abs(l2 - ol2) <= 1e-10 * ol2 and linf == olinf
+    eng.close()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [257, 513])
+def test_smoother_variants_are_bit_identical(mg, n, dtype):
+    """MG_SMOOTHER_COLOUR (plain kernel) and the default (TMA-staged) must agree bit for bit, from random data."""
+    rng = np.random.default_rng(2024)
+    v0 = random_field(rng, (n,) * 3, dtype)
+    f0 = random_field(rng, (n,) * 3, dtype)
+    outs = []
+    for smoother in (mg.MG_SMOOTHER_COLOUR, mg.MG_SMOOTHER_AUTO):
+        eng = mg.MultiGrid3D(n, RANGES[1], dtype=dtype, residual_mode=mg.MG_CORRECTED)
+        eng.set_smoother(smoother, 1)
+        eng.set_v(0, v0)
+        eng.set_f(0, f0)
+        eng.VCycle(0, 2, 1)
+        outs.append(eng.get_v(0))
+        eng.close()
+    assert_bits_equal(outs[0], outs[1], "smoother variants")
