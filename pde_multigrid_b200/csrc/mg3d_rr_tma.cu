@@ -10,7 +10,7 @@
 //     mbarrier) into a 4-slot ring while plane z is being processed; halo / out-of-domain elements are
 //     zero-filled by the hardware;
 //   * the residual of fine plane z is evaluated from the ring (7 conflict-free LDS per point) into a
-//     4-slot ring of residual planes stored parity-split in x, so that the 27 reads of the restriction
+//     3-slot ring of residual planes stored parity-split in x, so that the 27 reads of the restriction
 //     are unit-stride as well; f is prefetched one plane ahead into registers;
 //   * after every odd fine plane 2k+1 the coarse plane k is produced from residual planes 2k-1, 2k, 2k+1
 //     with the reference's exact grouping of the 27 weights, and written together with coarse v = 0.
@@ -31,7 +31,8 @@ constexpr int VROWS = MGK3D_RR_BOX_Y;   // fine rows of a v tile: 2*CYT + 3
 constexpr int RROWS = 2 * CYT + 1;      // fine rows of a residual plane tile
 constexpr int RCOLS = CXT + 2;          // per-parity columns of a residual row (33 used, even pitch)
 constexpr int HPR = CXT + 1;            // half-indices per residual row and colour (33)
-constexpr int RING = 4;
+constexpr int RING = 4;   // v planes: z-1, z, z+1 live + one in flight
+constexpr int RRING = 3;  // residual planes: 2k-1, 2k, 2k+1
 constexpr int NT = 256;
 constexpr int NPT = (2 * RROWS * HPR + NT - 1) / NT;  // residual points per thread and plane (5)
 
@@ -41,7 +42,7 @@ template <typename T> struct VBox {
 };
 
 template <typename T, bool FAST>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid_constant__ CUtensorMap map_c1,
                         const T* __restrict__ f, mg_geom3d gf, Coef3<T> c, int corrected, T* __restrict__ cf,
                         T* __restrict__ cv, mg_geom3d gc, int czl_lo, int czl_hi, int zchunk)
@@ -55,7 +56,7 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
     constexpr int RSLOT = RROWS * 2 * RCOLS;                       // residual plane: [row][x parity][col]
     T* vring = reinterpret_cast<T*>(smem_raw);
     T* rring = vring + (size_t)RING * VSLOT;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(rring + (size_t)RING * RSLOT);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rring + (size_t)RRING * RSLOT);
 
     const int tid = threadIdx.x;
     const int cx0 = blockIdx.x * CXT, cy0 = blockIdx.y * CYT;
@@ -87,25 +88,43 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
     if (tid == 0)
         for (int p = pbase; p <= min(pbase + RING - 1, zf1 + 1); p++) issue(p);
 
-    // the thread's residual points: slot s = tid + j*NT -> (colour cs, row ly, half-index hl); fixed over planes
-    int pc[NPT], ply[NPT], phl[NPT];
+    // The thread's residual points: slot s = tid + j*NT -> (colour, row ly, half-index hl), fixed over planes.
+    // Everything that does not depend on z is folded into a few per-point constants here so that the
+    // z loop is loads, arithmetic and one store per point (the first version of this kernel spent
+    // ~128 instructions per fine point, mostly on index arithmetic, and was issue-bound: profiles/).
+    int own_off[NPT], oth_off[NPT], r_even[NPT], flags[NPT];  // flags: 1 parity of (colour+y), 2 valid for q=0, 4 valid for q=1
+    const T* fptr[NPT];
 #pragma unroll
     for (int j = 0; j < NPT; j++) {
+        // a warp covers half-indices 0..31 of ONE (colour, row): every shared-memory access of the residual
+        // stage is unit-stride and conflict-free; the 33rd half-index of the 34 (colour, row) pairs is a
+        // small tail handled by 34 threads of the last pass
         const int s = tid + j * NT;
-        pc[j] = s / (RROWS * HPR);
-        const int rem = s - pc[j] * (RROWS * HPR);
-        ply[j] = rem / HPR;
-        phl[j] = rem - ply[j] * HPR;
-        if (s >= 2 * RROWS * HPR) pc[j] = -1;
+        const bool main_part = s < 2 * RROWS * 32;
+        const bool active = s < 2 * RROWS * HPR;
+        const int cr = main_part ? (s >> 5) : (active ? s - 2 * RROWS * 32 : 0);
+        const int hl = main_part ? (s & 31) : (active ? 32 : 0);
+        const int col = cr / RROWS;
+        const int ly = cr - col * RROWS;
+        const int y = fy0 + ly, hi = cx0 - 1 + hl;
+        const int cc = (ly + 1) * W + hl + A - 1;
+        own_off[j] = col * VSUB_STRIDE + cc;
+        oth_off[j] = (col ^ 1) * VSUB_STRIDE + cc;
+        r_even[j] = (ly * 2) * RCOLS + hl;  // q = 1: even lx = 2*hl -> parity array 0; q = 0: odd lx -> array 1 at hl-1
+        const bool yv = active && y >= 1 && y <= n - 2;
+        const int x0 = 2 * hi;  // q = 0; q = 1 -> x0 + 1
+        flags[j] = ((col + y) & 1) | ((yv && hl >= 1 && x0 >= 1 && x0 <= n - 2) ? 2 : 0) | ((yv && x0 + 1 >= 1 && x0 + 1 <= n - 2) ? 4 : 0) |
+                   (active ? 8 : 0) | ((active && hl >= 1) ? 16 : 0);
+        const bool fok = active && y >= 0 && y < n && hi >= 0 && hi < gf.hp;
+        fptr[j] = fok ? f + (long long)col * gf.cstride + (long long)y * gf.hp + hi : nullptr;
     }
+    const int nzl = gf.nzl;
     auto load_f = [&](int z, T (&dst)[NPT]) {
         const int zl = z - gf.z0;
+        const bool zok = zl >= 0 && zl < nzl;
+        const long long po = (long long)zl * gf.plane;
 #pragma unroll
-        for (int j = 0; j < NPT; j++) {
-            const int y = fy0 + ply[j], hi = cx0 - 1 + phl[j];
-            const bool ok = pc[j] >= 0 && zl >= 0 && zl < gf.nzl && y >= 0 && y < n && hi >= 0 && hi < gf.hp;
-            dst[j] = ok ? __ldg(f + (long long)pc[j] * gf.cstride + (long long)zl * gf.plane + (long long)y * gf.hp + hi) : T(0);
-        }
+        for (int j = 0; j < NPT; j++) dst[j] = (zok && fptr[j]) ? __ldg(fptr[j] + po) : T(0);
     };
     T fnext[NPT];
     load_f(zf0, fnext);
@@ -122,30 +141,25 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
         }
         mbar_wait(&bars[(k + 1) % RING], ((k + 1) / RING) & 1);
 
-        // ---- residual of fine plane z -> rring[(z - zf0) % RING] ----
+        // ---- residual of fine plane z -> rring[(z - zf0) % RRING] ----
         const T* vD = vring + (size_t)((k - 1) % RING) * VSLOT;
         const T* vC = vring + (size_t)(k % RING) * VSLOT;
         const T* vU = vring + (size_t)((k + 1) % RING) * VSLOT;
-        T* rz = rring + (size_t)((z - zf0) % RING) * RSLOT;
+        T* rz = rring + (size_t)((z - zf0) % RRING) * RSLOT;
         const bool zin = z >= 1 && z <= n - 2;
+        const int zpar = z & 1;
 #pragma unroll
         for (int j = 0; j < NPT; j++) {
-            if (pc[j] < 0) continue;
-            const int col = pc[j], ly = ply[j], hl = phl[j];
-            const int y = fy0 + ly;
-            const int q = (col + y + z) & 1;             // x parity of this colour in this row
-            const int x = 2 * (cx0 - 1 + hl) + q;
-            if (q == 0 && hl == 0) continue;             // x = 2*cx0-2 lies left of the residual tile
+            const int q = (flags[j] ^ zpar) & 1;  // x parity of this colour in this row of this plane
+            const bool store = q ? (flags[j] & 8) : (flags[j] & 16);
+            const bool valid = zin && (flags[j] & (q ? 4 : 2));
             T val = T(0);
-            if (zin && y >= 1 && y <= n - 2 && x >= 1 && x <= n - 2) {
-                const int cc = (ly + 1) * W + hl + A - 1;
-                const T* own = vC + col * VSUB_STRIDE;
-                const int ob = (col ^ 1) * VSUB_STRIDE;
-                val = residual_point<T, FAST>(vC[ob + cc - 1 + q], vC[ob + cc + q], vC[ob + cc - W], vC[ob + cc + W], vD[ob + cc],
-                                              vU[ob + cc], own[cc], fcur[j], c, corrected);
+            if (valid) {
+                const int o = oth_off[j];
+                val = residual_point<T, FAST>(vC[o - 1 + q], vC[o + q], vC[o - W], vC[o + W], vD[o], vU[o], vC[own_off[j]], fcur[j], c,
+                                              corrected);
             }
-            // lx = x - (2*cx0-1) = 2*hl + q - 1: even lx (q = 1) -> parity array 0 at hl, odd lx (q = 0) -> array 1 at hl-1
-            rz[(ly * 2 + (q ^ 1)) * RCOLS + hl - (q ^ 1)] = val;
+            if (store) rz[r_even[j] + (q ? 0 : RCOLS - 1)] = val;
         }
         __syncthreads();  // residual plane z complete; v slot of plane z-1 free
         if (tid == 0 && z + RING - 1 <= zf1 + 1) issue(z + RING - 1);
@@ -158,20 +172,20 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
             if (cx < gc.n && cy < gc.n) {
                 T out = T(0);  // boundary: injection of the zero boundary residual (N3/MultiGrid3D.cpp:113-119, :705)
                 if (!(cx == 0 || cx == gc.n - 1 || cy == 0 || cy == gc.n - 1 || cz == 0 || cz == gc.n - 1)) {
-                    const T* rm = rring + (size_t)((z - 2 - zf0) % RING) * RSLOT;
-                    const T* rc = rring + (size_t)((z - 1 - zf0) % RING) * RSLOT;
-                    const T* rp = rz;
+                    const T* rm = rring + (size_t)((z - 2 - zf0) % RRING) * RSLOT + ((2 * ty + 1) * 2) * RCOLS + tx;
+                    const T* rc = rring + (size_t)((z - 1 - zf0) % RRING) * RSLOT + ((2 * ty + 1) * 2) * RCOLS + tx;
+                    const T* rp = rz + ((2 * ty + 1) * 2) * RCOLS + tx;
                     // centre lx = 2*tx+1 (odd: parity array 1 at tx); dx = -1/+1 -> even lx: array 0 at tx / tx+1
                     out = restrict_point<T>([&](int dx, int dy, int dz) {
                         const T* pl = dz < 0 ? rm : (dz == 0 ? rc : rp);
-                        const int row = 2 * ty + 1 + dy;
-                        return dx == 0 ? pl[(row * 2 + 1) * RCOLS + tx] : pl[(row * 2) * RCOLS + tx + (dx > 0)];
+                        return dx == 0 ? pl[dy * 2 * RCOLS + RCOLS] : pl[dy * 2 * RCOLS + (dx > 0)];
                     });
                 }
                 const long long ci = off3(gc, cx, cy, czl);
                 cf[ci] = out;
                 cv[ci] = T(0);  // setToValue(coarse->h_v, 0, true), N3/MultiGrid3D.cpp:634
             }
+            __syncthreads();  // the 3-slot residual ring: plane z-2 is overwritten by the next iteration
         }
     }
 }
@@ -180,7 +194,7 @@ template <typename T>
 size_t smem_bytes_t()
 {
     constexpr size_t vsub = ((size_t)VROWS * VBox<T>::W * sizeof(T) + 127) / 128 * 128;
-    return RING * 2 * vsub + (size_t)RING * RROWS * 2 * RCOLS * sizeof(T) + RING * sizeof(uint64_t);
+    return RING * 2 * vsub + (size_t)RRING * RROWS * 2 * RCOLS * sizeof(T) + RING * sizeof(uint64_t);
 }
 
 template <typename T, bool FAST>
