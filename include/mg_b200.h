@@ -76,6 +76,13 @@ int mg3d_create(mg3d_t** out, const int finest_size_xyz[3], const double range[6
 int mg3d_create_dist(mg3d_t** out, const int finest_size_xyz[3], const double range[6], int dtype, int residual_mode,
                      int rank, int nranks, const void* nccl_unique_id);
 int mg_comm_unique_id(void* out128);
+/* slab plan of a level with n points per axis (pure arithmetic, no GPU needed): out5 = {distributed?, global z of
+   the first stored plane, stored planes, first owned local plane, one past the last owned local plane} */
+int mg3d_plan_level(int n, int nranks, int rank, int out5[5]);
+/* global planes [z_begin, z_begin + z_count) this rank owns on `level` (the whole level when it is not distributed);
+   set_field / get_field / residual / vcycle_host move exactly these planes */
+int mg3d_owned_range(const mg3d_t* mg, int level, int* z_begin, int* z_count);
+long long mg3d_halo_bytes(const mg3d_t* mg); /* bytes this rank has sent in halo exchanges and gathers so far */
 int mg3d_destroy(mg3d_t* mg); /* ~MultiGrid3D */
 int mg3d_num_levels(const mg3d_t* mg);         /* MultiGrid3D::numGrids */
 int mg3d_level_size(const mg3d_t* mg, int level); /* grids3D[level]->sizeX */
@@ -89,7 +96,7 @@ long long mg3d_kernel_launches(const mg3d_t* mg); /* kernels launched by this ha
 int mg3d_profile(mg3d_t* mg, int enable);
 int mg3d_profile_read(mg3d_t* mg, int level, int op, double* ms_total, long long* kernel_launches, long long* calls);
 
-/* grids3D[level]->h_v / h_f  <->  host dense array of n_l^3 values */
+/* grids3D[level]->h_v / h_f  <->  host dense array of n_l^3 values (multi-GPU: the owned planes, n_l*n_l*z_count) */
 int mg3d_set_field(mg3d_t* mg, int level, int field, const void* host_dense);
 int mg3d_get_field(mg3d_t* mg, int level, int field, void* host_dense);
 /* re-run Grid3D::InitV/InitF on every level (device side) and zero the interior of v */

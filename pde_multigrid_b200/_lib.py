@@ -36,7 +36,8 @@ def lib():
         L.mg_version.restype = ctypes.c_char_p
         for dim in ("1d", "2d", "3d"):
             for name, rt in (("level_h", ctypes.c_double), ("stream", ctypes.c_void_p),
-                             ("kernel_launches", ctypes.c_longlong)):
+                             ("kernel_launches", ctypes.c_longlong),
+                             ("halo_bytes", ctypes.c_longlong)):
                 f = getattr(L, "mg%s_%s" % (dim, name), None)
                 if f is not None:
                     f.restype = rt

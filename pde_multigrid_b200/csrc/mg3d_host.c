@@ -1,18 +1,33 @@
 /*
- * mg3d_host.c -- C host driver of the 3D Poisson multigrid: hierarchy, V-cycle, FMG, field I/O.
+ * mg3d_host.c -- C host driver of the 3D Poisson multigrid: hierarchy, V-cycle, FMG, field I/O, and the
+ * multi-GPU z-slab decomposition.
  *
  * Mirrors the control flow of the reference class MultiGrid3D
  * (NOCUDA_TESI/POISSON_3D(TESI)/MultiGrid3D.cpp: InitGrids :19-47, VCycle :623-647,
- * FullMultiGridVCycle :569-585) over the sm_100a kernels of mg3d_kernels.cu.  Host code is C; all
- * device work goes through the launchers declared in mg_launch.h.  No CPU compute path exists here:
- * the host only computes per-level scalars (h, h^2 products, sin tables for InitF).
+ * FullMultiGridVCycle :569-585) over the sm_100a kernels of mg3d_*.cu.  Host code is C; all device work
+ * goes through the launchers declared in mg_launch.h.  No CPU compute path exists here: the host only
+ * computes per-level scalars (h, h^2 products, sin tables for InitF).
+ *
+ * Multi-GPU (the reference has none; thesis p.75 names it as future work): one process per GPU, the
+ * grid is cut into z-slabs.  Rank g of P owns the global planes [g*m, (g+1)*m), m = (n-1)/P, the last
+ * rank also the Dirichlet plane n-1.  A slab stores 2 ghost planes below (the fused residual+restrict
+ * needs v two planes under its first coarse plane) and 1 above.  A level is slab-distributed while
+ * m >= 8 and n >= 65; coarser levels are agglomerated: every rank holds them whole (one all-gather of the
+ * restricted right-hand side on the way down, nothing on the way up) and smooths them redundantly.
+ * RB Gauss-Seidel only couples opposite colours, so exchanging the just-updated colour's boundary
+ * plane after every half-sweep reproduces the sequential red-then-black order exactly: the P-GPU result
+ * is bit-identical to the 1-GPU result.
  */
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include "mg_comm.h"
 #include "mg_host_common.h"
 #include "mg_profile.h"
+
+#define MG_GHOST_LO 2
+#define MG_GHOST_HI 1
 
 typedef struct {
     mg_geom3d g;
@@ -20,6 +35,7 @@ typedef struct {
     void* v;
     void* f;
     double h[3];    /* h_x, h_y, h_z (values of the level's dtype) */
+    int dist;       /* 1: slab-distributed over the ranks; 0: the whole level lives on this rank */
     int own_lo;     /* local plane range [own_lo, own_hi) owned by this rank */
     int own_hi;
     int has_tma;    /* tensor maps of the two colour arrays of v are valid */
@@ -33,14 +49,16 @@ struct mg3d_s {
     int smoother, sweeps_per_pass;
     double range[6];
     cudaStream_t stream;
+    mg_comm* comm;
     mg_level3d* lv;
     void* arena;
     double* d_scratch; /* 2*MGK_NORM_BLOCKS partials + 2 outputs */
     double* d_tables;  /* 3*n0 doubles: sin tables of InitF */
     double* h_out2;    /* pinned */
-    void* staging;     /* dense device staging buffer for large host<->device field copies */
+    void* staging;     /* dense device staging buffer for host<->device field copies */
     size_t staging_bytes;
     long long launches;
+    long long halo_bytes; /* bytes sent by this rank in halo exchanges / gathers */
     mg_prof prof;
 };
 
@@ -94,6 +112,27 @@ static void set_geom(mg_geom3d* g, int n, int dtype, int z0, int nzl)
     g->nzl = nzl;
 }
 
+/* Slab plan of one level (pure arithmetic, also exported for tests): is the level distributed, and which
+   global planes does `rank` store and own?  out = {dist, z0, nzl, own_lo, own_hi} in local indices. */
+int mg3d_plan_level(int n, int nranks, int rank, int out5[5])
+{
+    if (!out5 || n < 3 || nranks < 1 || rank < 0 || rank >= nranks) return mg_fail(MG_ERR_ARG, "bad plan arguments");
+    const int m = (n - 1) / nranks;
+    const int dist = nranks > 1 && (n - 1) % nranks == 0 && m >= 8 && n >= 65;
+    if (!dist) {
+        out5[0] = 0; out5[1] = 0; out5[2] = n; out5[3] = 0; out5[4] = n;
+        return MG_OK;
+    }
+    const int a = rank * m, b = (rank + 1) * m + (rank == nranks - 1 ? 1 : 0);
+    const int glo = rank > 0 ? MG_GHOST_LO : 0, ghi = rank < nranks - 1 ? MG_GHOST_HI : 0;
+    out5[0] = 1;
+    out5[1] = a - glo;
+    out5[2] = (b - a) + glo + ghi;
+    out5[3] = glo;
+    out5[4] = glo + (b - a);
+    return MG_OK;
+}
+
 static size_t field_bytes(const mg_level3d* L, int dtype)
 {
     return mg_align256(2 * (size_t)L->g.cstride * mg_esize(dtype));
@@ -108,7 +147,87 @@ static int check_level(const mg3d_t* mg, int level)
 
 static void* field_ptr(mg_level3d* L, int field) { return field == MG_FIELD_V ? L->v : L->f; }
 
-int mg3d_create(mg3d_t** out, const int sz[3], const double range[6], int dtype, int residual_mode)
+/* device address of local plane zl of colour `col` of a field */
+static char* plane_ptr(const mg3d_t* mg, const mg_level3d* L, void* field, int col, int zl)
+{
+    return (char*)field + ((size_t)col * (size_t)L->g.cstride + (size_t)zl * (size_t)L->g.plane) * mg_esize(mg->dtype);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Halo exchange of a distributed level (grouped ncclSend/ncclRecv on the handle's stream).
+ *   up:   my top `depth_up` owned planes        -> the lower ghosts of rank+1
+ *   down: my bottom owned plane (if `down` != 0) -> the upper ghost of rank-1
+ * colour_mask: bit 0 = colour-0 array, bit 1 = colour-1 array.
+ * ---------------------------------------------------------------------------------------------- */
+static int exchange(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int down)
+{
+    mg_level3d* L = &mg->lv[level];
+    if (!L->dist) return MG_OK;
+    const size_t pe = (size_t)L->g.plane; /* elements per colour plane */
+    const int r = mg->rank, P = mg->nranks;
+    int st;
+    PROF_BEGIN(mg, level, MG_OP_OTHER);
+    if ((st = mg_comm_group_start(mg->comm))) return st;
+    for (int col = 0; col < 2; col++) {
+        if (!(colour_mask & (1 << col))) continue;
+        if (r + 1 < P) {
+            if (depth_up > 0) {
+                st = mg_comm_send(mg->comm, plane_ptr(mg, L, field, col, L->own_hi - depth_up), pe * depth_up, mg->dtype, r + 1, mg->stream);
+                mg->halo_bytes += (long long)(pe * depth_up * mg_esize(mg->dtype));
+            }
+            if (!st && down) st = mg_comm_recv(mg->comm, plane_ptr(mg, L, field, col, L->own_hi), pe, mg->dtype, r + 1, mg->stream);
+        }
+        if (!st && r > 0) {
+            if (down) {
+                st = mg_comm_send(mg->comm, plane_ptr(mg, L, field, col, L->own_lo), pe, mg->dtype, r - 1, mg->stream);
+                mg->halo_bytes += (long long)(pe * mg_esize(mg->dtype));
+            }
+            if (!st && depth_up > 0)
+                st = mg_comm_recv(mg->comm, plane_ptr(mg, L, field, col, L->own_lo - depth_up), pe * depth_up, mg->dtype, r - 1, mg->stream);
+        }
+        if (st) break;
+    }
+    int st2 = mg_comm_group_end(mg->comm);
+    PROF_END(mg);
+    return st ? st : st2;
+}
+
+/* first agglomerated level below a distributed one: every rank computed the coarse planes under its own
+   slab into its full-size array; gather them so that every rank holds the whole level.  The top plane
+   n-1 (not covered by the equal shares) comes from the last rank when `top_from_last` is set, else the
+   caller fills it. */
+static int gather_level(mg3d_t* mg, int level, void* field, int top_from_last)
+{
+    mg_level3d* L = &mg->lv[level];
+    const int P = mg->nranks, m = (L->g.n - 1) / P;
+    const size_t pe = (size_t)L->g.plane;
+    int st = MG_OK;
+    PROF_BEGIN(mg, level, MG_OP_OTHER);
+    for (int col = 0; col < 2 && !st; col++) {
+        st = mg_comm_allgather_inplace(mg->comm, plane_ptr(mg, L, field, col, 0), pe * m, mg->dtype, mg->stream);
+        mg->halo_bytes += (long long)(pe * m * mg_esize(mg->dtype));
+    }
+    if (!st && top_from_last) {
+        st = mg_comm_group_start(mg->comm);
+        for (int col = 0; col < 2 && !st; col++) {
+            char* top = plane_ptr(mg, L, field, col, L->g.n - 1);
+            if (mg->rank == P - 1) {
+                for (int peer = 0; peer < P - 1 && !st; peer++) st = mg_comm_send(mg->comm, top, pe, mg->dtype, peer, mg->stream);
+            } else {
+                st = mg_comm_recv(mg->comm, top, pe, mg->dtype, P - 1, mg->stream);
+            }
+        }
+        int st2 = mg_comm_group_end(mg->comm);
+        if (!st) st = st2;
+    }
+    PROF_END(mg);
+    return st;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+
+static int create_common(mg3d_t** out, const int sz[3], const double range[6], int dtype, int residual_mode, int rank,
+                         int nranks, const void* uid)
 {
     if (!out || !sz || !range) return mg_fail(MG_ERR_ARG, "null argument");
     *out = NULL;
@@ -119,6 +238,12 @@ int mg3d_create(mg3d_t** out, const int sz[3], const double range[6], int dtype,
     if (!(range[1] > range[0]) || !(range[3] > range[2]) || !(range[5] > range[4])) return mg_fail(MG_ERR_ARG, "range must satisfy b > a on every axis");
     if (dtype != MG_F32 && dtype != MG_F64) return mg_fail(MG_ERR_ARG, "dtype must be MG_F32 or MG_F64");
     if (residual_mode != MG_REF_COMPAT && residual_mode != MG_CORRECTED) return mg_fail(MG_ERR_ARG, "bad residual_mode");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return mg_fail(MG_ERR_ARG, "bad rank %d of %d", rank, nranks);
+    if (nranks > 1) {
+        if ((nranks & (nranks - 1)) != 0) return mg_fail(MG_ERR_ARG, "the number of GPUs must be a power of two (got %d)", nranks);
+        if ((n - 1) / nranks < 8 || n < 65) return mg_fail(MG_ERR_ARG, "grid %d^3 is too small for %d z-slabs (needs >= 8 planes per GPU and n >= 65)", n, nranks);
+        if (!uid) return mg_fail(MG_ERR_ARG, "multi-GPU handles need the NCCL unique id");
+    }
     int st = mg_require_device();
     if (st) return st;
 
@@ -126,8 +251,8 @@ int mg3d_create(mg3d_t** out, const int sz[3], const double range[6], int dtype,
     if (!mg) return mg_fail(MG_ERR_NOMEM, "host allocation failed");
     mg->dtype = dtype;
     mg->mode = residual_mode;
-    mg->rank = 0;
-    mg->nranks = 1;
+    mg->rank = rank;
+    mg->nranks = nranks;
     mg->smoother = MG_SMOOTHER_AUTO;
     mg->sweeps_per_pass = 1;
     memcpy(mg->range, range, sizeof mg->range);
@@ -139,9 +264,12 @@ int mg3d_create(mg3d_t** out, const int sz[3], const double range[6], int dtype,
     int nl = n;
     for (int l = 0; l < mg->nlevels; l++) {
         mg_level3d* L = &mg->lv[l];
-        set_geom(&L->g, nl, dtype, 0, nl);
-        L->own_lo = 0;
-        L->own_hi = nl;
+        int plan[5];
+        mg3d_plan_level(nl, nranks, rank, plan);
+        L->dist = plan[0];
+        set_geom(&L->g, nl, dtype, plan[1], plan[2]);
+        L->own_lo = plan[3];
+        L->own_hi = plan[4];
         level_coefs(dtype, nl, range, L->h, &L->c);
         total += 2 * field_bytes(L, dtype);
         nl = (nl - 1) / 2 + 1; /* N3/MultiGrid3D.cpp:40-42 */
@@ -165,31 +293,52 @@ int mg3d_create(mg3d_t** out, const int sz[3], const double range[6], int dtype,
         mg3d_destroy(mg);
         return code;
     }
+    if (nranks > 1) {
+        st = mg_comm_create(&mg->comm, rank, nranks, uid);
+        if (st) { mg3d_destroy(mg); return st; }
+    }
     /* TMA tensor maps of v for the levels large enough to fill the z-marching tiles */
     for (int l = 0; l < mg->nlevels; l++) {
         mg_level3d* L = &mg->lv[l];
         if ((L->g.n - 1) / 2 < MGK3D_TMA_IT || getenv("MG_B200_NO_TMA")) continue;
         for (int col = 0; col < 2; col++) {
-            st = mg_tma_make_colour_map(L->tmap_v[col], dtype, (char*)L->v + (size_t)col * L->g.cstride * mg_esize(dtype), &L->g,
+            st = mg_tma_make_colour_map(L->tmap_v[col], dtype, plane_ptr(mg, L, L->v, col, 0), &L->g,
                                         MGK3D_TMA_BOX_I(mg_esize(dtype)), MGK3D_TMA_BOX_Y);
-            if (!st) st = mg_tma_make_colour_map(L->tmap_rr[col], dtype, (char*)L->v + (size_t)col * L->g.cstride * mg_esize(dtype), &L->g,
+            if (!st) st = mg_tma_make_colour_map(L->tmap_rr[col], dtype, plane_ptr(mg, L, L->v, col, 0), &L->g,
                                                  MGK3D_RR_BOX_I(mg_esize(dtype)), MGK3D_RR_BOX_Y);
             if (st) { mg3d_destroy(mg); return st; }
         }
         L->has_tma = 1;
     }
     /* pad elements of the layout are never used by a kernel, but keep them defined */
-    MG_CUDA(cudaMemsetAsync(mg->arena, 0, total, mg->stream));
+    if (cudaMemsetAsync(mg->arena, 0, total, mg->stream) != cudaSuccess) {
+        int code = mg_fail(MG_ERR_CUDA, "arena clear failed: %s", cudaGetErrorString(cudaGetLastError()));
+        mg3d_destroy(mg);
+        return code;
+    }
     st = mg3d_init_problem(mg);
     if (st) { mg3d_destroy(mg); return st; }
     *out = mg;
     return MG_OK;
 }
 
+int mg3d_create(mg3d_t** out, const int sz[3], const double range[6], int dtype, int residual_mode)
+{
+    return create_common(out, sz, range, dtype, residual_mode, 0, 1, NULL);
+}
+
+int mg3d_create_dist(mg3d_t** out, const int sz[3], const double range[6], int dtype, int residual_mode, int rank,
+                     int nranks, const void* nccl_unique_id)
+{
+    return create_common(out, sz, range, dtype, residual_mode, rank, nranks, nccl_unique_id);
+}
+
 int mg3d_destroy(mg3d_t* mg)
 {
     if (!mg) return MG_OK;
-    if (mg->stream) { cudaStreamSynchronize(mg->stream); cudaStreamDestroy(mg->stream); }
+    if (mg->stream) cudaStreamSynchronize(mg->stream);
+    if (mg->comm) mg_comm_destroy(mg->comm);
+    if (mg->stream) cudaStreamDestroy(mg->stream);
     if (mg->arena) cudaFree(mg->arena);
     if (mg->d_scratch) cudaFree(mg->d_scratch);
     if (mg->d_tables) cudaFree(mg->d_tables);
@@ -206,6 +355,17 @@ int mg3d_level_size(const mg3d_t* mg, int level) { return (mg && level >= 0 && l
 double mg3d_level_h(const mg3d_t* mg, int level) { return (mg && level >= 0 && level < mg->nlevels) ? mg->lv[level].h[0] : 0.0; }
 void* mg3d_stream(mg3d_t* mg) { return mg ? (void*)mg->stream : NULL; }
 long long mg3d_kernel_launches(const mg3d_t* mg) { return mg ? mg->launches : 0; }
+long long mg3d_halo_bytes(const mg3d_t* mg) { return mg ? mg->halo_bytes : 0; }
+
+int mg3d_owned_range(const mg3d_t* mg, int level, int* z_begin, int* z_count)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    const mg_level3d* L = &mg->lv[level];
+    if (z_begin) *z_begin = L->g.z0 + L->own_lo;
+    if (z_count) *z_count = L->own_hi - L->own_lo;
+    return MG_OK;
+}
 
 int mg3d_set_smoother(mg3d_t* mg, int smoother, int sweeps_per_pass)
 {
@@ -244,7 +404,8 @@ int mg3d_sync(mg3d_t* mg)
 }
 
 /* dense host array (x fastest, idx = x + y*n + z*n*n) <-> colour-split device field: one linear copy
-   between the host array and a dense device staging buffer, plus a repack kernel. */
+   between the host array and a dense device staging buffer, plus a repack kernel.  Local planes
+   [zl_lo, zl_hi) of the field correspond to the start of the host array. */
 static int staging_reserve(mg3d_t* mg, size_t bytes)
 {
     if (mg->staging_bytes >= bytes) return MG_OK;
@@ -254,34 +415,36 @@ static int staging_reserve(mg3d_t* mg, size_t bytes)
     return MG_OK;
 }
 
-static int copy_in(mg3d_t* mg, void* dev, const mg_geom3d* g, const void* host)
+static int copy_in(mg3d_t* mg, void* dev, const mg_geom3d* g, const void* host, int zl_lo, int zl_hi)
 {
-    size_t dense = (size_t)g->n * g->n * (size_t)g->nzl * mg_esize(mg->dtype);
+    size_t dense = (size_t)g->n * g->n * (size_t)(zl_hi - zl_lo) * mg_esize(mg->dtype);
     int st = staging_reserve(mg, dense);
     if (st) return st;
     MG_CUDA(cudaMemcpyAsync(mg->staging, host, dense, cudaMemcpyHostToDevice, mg->stream));
-    MG_LAUNCH(mg->launches, mgk3d_repack(mg->stream, mg->dtype, dev, *g, mg->staging, 1, 0, g->nzl));
+    MG_LAUNCH(mg->launches, mgk3d_repack(mg->stream, mg->dtype, dev, *g, mg->staging, 1, zl_lo, zl_hi));
     return MG_OK;
 }
 
-static int copy_out(mg3d_t* mg, void* host, const void* dev, const mg_geom3d* g)
+static int copy_out(mg3d_t* mg, void* host, const void* dev, const mg_geom3d* g, int zl_lo, int zl_hi)
 {
-    size_t dense = (size_t)g->n * g->n * (size_t)g->nzl * mg_esize(mg->dtype);
+    size_t dense = (size_t)g->n * g->n * (size_t)(zl_hi - zl_lo) * mg_esize(mg->dtype);
     int st = staging_reserve(mg, dense);
     if (st) return st;
-    MG_LAUNCH(mg->launches, mgk3d_repack(mg->stream, mg->dtype, (void*)dev, *g, mg->staging, 0, 0, g->nzl));
+    MG_LAUNCH(mg->launches, mgk3d_repack(mg->stream, mg->dtype, (void*)dev, *g, mg->staging, 0, zl_lo, zl_hi));
     MG_CUDA(cudaMemcpyAsync(host, mg->staging, dense, cudaMemcpyDeviceToHost, mg->stream));
     MG_CUDA(cudaStreamSynchronize(mg->stream));
     return MG_OK;
 }
 
+/* host_dense holds the planes this rank owns (mg3d_owned_range): the whole grid on one GPU */
 int mg3d_set_field(mg3d_t* mg, int level, int field, const void* host_dense)
 {
     int st = check_level(mg, level);
     if (st) return st;
     if (!host_dense || (field != MG_FIELD_V && field != MG_FIELD_F)) return mg_fail(MG_ERR_ARG, "bad field/pointer");
-    if (mg->nranks != 1) return mg_fail(MG_ERR_STATE, "set_field takes the whole grid: single-GPU handles only");
-    st = copy_in(mg, field_ptr(&mg->lv[level], field), &mg->lv[level].g, host_dense);
+    mg_level3d* L = &mg->lv[level];
+    st = copy_in(mg, field_ptr(L, field), &L->g, host_dense, L->own_lo, L->own_hi);
+    if (!st) st = exchange(mg, level, field_ptr(L, field), 3, MG_GHOST_LO, 1);
     if (st) return st;
     MG_CUDA(cudaStreamSynchronize(mg->stream)); /* host buffer may be reused by the caller */
     return MG_OK;
@@ -292,11 +455,11 @@ int mg3d_get_field(mg3d_t* mg, int level, int field, void* host_dense)
     int st = check_level(mg, level);
     if (st) return st;
     if (!host_dense || (field != MG_FIELD_V && field != MG_FIELD_F)) return mg_fail(MG_ERR_ARG, "bad field/pointer");
-    if (mg->nranks != 1) return mg_fail(MG_ERR_STATE, "get_field returns the whole grid: single-GPU handles only");
-    return copy_out(mg, host_dense, field_ptr(&mg->lv[level], field), &mg->lv[level].g);
+    mg_level3d* L = &mg->lv[level];
+    return copy_out(mg, host_dense, field_ptr(L, field), &L->g, L->own_lo, L->own_hi);
 }
 
-/* Grid3D::InitV / InitF on every level (N3/Grid3D.cpp:61-96) */
+/* Grid3D::InitV / InitF on every level (N3/Grid3D.cpp:61-96); ghost planes are initialised like owned ones */
 int mg3d_init_problem(mg3d_t* mg)
 {
     if (!mg) return mg_fail(MG_ERR_ARG, "null handle");
@@ -333,23 +496,33 @@ int mg3d_init_problem(mg3d_t* mg)
     return MG_OK;
 }
 
-/* Relax: ncycles x (red half-sweep, black half-sweep), N3/MultiGrid3D.cpp:489-567 */
+/* interior planes this rank updates, in local indices */
+static void interior_range(const mg_level3d* L, int* lo, int* hi)
+{
+    const int first = 1 - L->g.z0, last = L->g.n - 2 - L->g.z0; /* local indices of global planes 1 and n-2 */
+    *lo = L->own_lo > first ? L->own_lo : first;
+    *hi = (L->own_hi - 1 < last ? L->own_hi - 1 : last) + 1;
+}
+
+/* Relax: ncycles x (red half-sweep, black half-sweep), N3/MultiGrid3D.cpp:489-567.  On a distributed
+   level the boundary planes of the colour just updated go to the neighbours after every half-sweep. */
 static int relax_level(mg3d_t* mg, int level, int ncycles)
 {
     mg_level3d* L = &mg->lv[level];
-    const int lo = L->own_lo > 1 ? L->own_lo : 1;
-    const int hi = L->own_hi < L->g.nzl - 1 ? L->own_hi : L->g.nzl - 1;
+    int lo, hi, st;
+    interior_range(L, &lo, &hi);
     if (ncycles <= 0) return MG_OK;
-    PROF_BEGIN(mg, level, MG_OP_RELAX);
     const int use_tma = L->has_tma && mg->smoother != MG_SMOOTHER_COLOUR;
     for (int k = 0; k < ncycles; k++)
         for (int colour = 0; colour < 2; colour++) {
+            PROF_BEGIN(mg, level, MG_OP_RELAX);
             if (use_tma)
                 MG_LAUNCH(mg->launches, mgk3d_relax_colour_tma(mg->stream, mg->dtype, L->tmap_v[colour ^ 1], L->v, L->f, L->g, L->c, colour, lo, hi));
             else
                 MG_LAUNCH(mg->launches, mgk3d_relax_colour(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, colour, lo, hi));
+            PROF_END(mg);
+            if ((st = exchange(mg, level, L->v, 1 << colour, 1, 1))) return st;
         }
-    PROF_END(mg);
     return MG_OK;
 }
 
@@ -361,6 +534,7 @@ int mg3d_relax(mg3d_t* mg, int level, int ncycles)
     return relax_level(mg, level, ncycles);
 }
 
+/* CalculateResidual -> host array of the planes this rank owns */
 int mg3d_residual(mg3d_t* mg, int level, void* host_out)
 {
     int st = check_level(mg, level);
@@ -369,10 +543,10 @@ int mg3d_residual(mg3d_t* mg, int level, void* host_out)
     mg_level3d* L = &mg->lv[level];
     void* r = NULL;
     MG_CUDA(cudaMalloc(&r, field_bytes(L, mg->dtype)));
-    int k = mgk3d_residual(mg->stream, mg->dtype, L->v, L->f, r, L->g, L->c, mg->mode == MG_CORRECTED, 0, L->g.nzl);
+    int k = mgk3d_residual(mg->stream, mg->dtype, L->v, L->f, r, L->g, L->c, mg->mode == MG_CORRECTED, L->own_lo, L->own_hi);
     if (k < 0) { cudaFree(r); return mg_fail(MG_ERR_CUDA, "residual launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
     mg->launches += k;
-    st = copy_out(mg, host_out, r, &L->g);
+    st = copy_out(mg, host_out, r, &L->g, L->own_lo, L->own_hi);
     cudaFree(r);
     return st;
 }
@@ -385,10 +559,35 @@ int mg3d_residual_norm(mg3d_t* mg, int level, double* l2, double* linf)
     double* out2 = mg->d_scratch + 2 * MGK_NORM_BLOCKS;
     MG_LAUNCH(mg->launches, mgk3d_residual_norm(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, mg->mode == MG_CORRECTED,
                                                 L->own_lo, L->own_hi, mg->d_scratch, out2));
+    if (L->dist && (st = mg_comm_allreduce_sum_max(mg->comm, out2, mg->stream))) return st;
     MG_CUDA(cudaMemcpyAsync(mg->h_out2, out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, mg->stream));
     MG_CUDA(cudaStreamSynchronize(mg->stream));
     if (l2) *l2 = sqrt(mg->h_out2[0]);
     if (linf) *linf = mg->h_out2[1];
+    return MG_OK;
+}
+
+/* coarse local planes this rank computes when restricting from fine level `fine_level` */
+static void coarse_share(const mg3d_t* mg, int fine_level, int* czl_lo, int* czl_hi)
+{
+    const mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
+    if (C->dist || !F->dist) {
+        *czl_lo = C->own_lo;
+        *czl_hi = C->own_hi;
+    } else { /* first agglomerated level: the planes under my fine slab (C is stored whole: z0 = 0) */
+        const int a = F->g.z0 + F->own_lo, b = F->g.z0 + F->own_hi;
+        *czl_lo = a / 2;
+        *czl_hi = (b - 1) / 2 + 1; /* the last rank's b = n makes this n_c: it also produces the top plane */
+        if (mg->rank < mg->nranks - 1) *czl_hi = b / 2;
+    }
+}
+
+/* what follows a restriction onto level+1: refresh ghosts (distributed) or gather (first agglomerated level) */
+static int after_restrict(mg3d_t* mg, int fine_level, void* coarse_field)
+{
+    const mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
+    if (C->dist) return exchange(mg, fine_level + 1, coarse_field, 3, MG_GHOST_LO, 1);
+    if (F->dist) return gather_level(mg, fine_level + 1, coarse_field, 1);
     return MG_OK;
 }
 
@@ -399,22 +598,32 @@ int mg3d_restrict(mg3d_t* mg, int fine_level, int field)
     if (fine_level == mg->nlevels - 1) return mg_fail(MG_ERR_ARG, "level %d is the coarsest", fine_level);
     if (field != MG_FIELD_V && field != MG_FIELD_F) return mg_fail(MG_ERR_ARG, "bad field");
     mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
-    MG_LAUNCH(mg->launches, mgk3d_restrict(mg->stream, mg->dtype, field_ptr(F, field), F->g, field_ptr(C, field), C->g, C->own_lo, C->own_hi));
-    return MG_OK;
+    int lo, hi;
+    coarse_share(mg, fine_level, &lo, &hi);
+    PROF_BEGIN(mg, fine_level, MG_OP_OTHER);
+    MG_LAUNCH(mg->launches, mgk3d_restrict(mg->stream, mg->dtype, field_ptr(F, field), F->g, field_ptr(C, field), C->g, lo, hi));
+    PROF_END(mg);
+    return after_restrict(mg, fine_level, field_ptr(C, field));
 }
 
 static int residual_restrict_level(mg3d_t* mg, int fine_level)
 {
     mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
+    int lo, hi, st;
+    coarse_share(mg, fine_level, &lo, &hi);
+    /* the fused kernel reads v two planes below the slab: only plane a-2 is stale after the smoother's exchanges */
+    if (F->dist && (st = exchange(mg, fine_level, F->v, 3, MG_GHOST_LO, 0))) return st;
     PROF_BEGIN(mg, fine_level, MG_OP_RESIDUAL_RESTRICT);
     if (F->has_tma && mg->smoother != MG_SMOOTHER_COLOUR)
         MG_LAUNCH(mg->launches, mgk3d_residual_restrict_tma(mg->stream, mg->dtype, F->tmap_rr[0], F->tmap_rr[1], F->f, F->g, F->c,
-                                                            mg->mode == MG_CORRECTED, C->f, C->v, C->g, C->own_lo, C->own_hi));
+                                                            mg->mode == MG_CORRECTED, C->f, C->v, C->g, lo, hi));
     else
         MG_LAUNCH(mg->launches, mgk3d_residual_restrict(mg->stream, mg->dtype, F->v, F->f, F->g, F->c, mg->mode == MG_CORRECTED,
-                                                        C->f, C->v, C->g, C->own_lo, C->own_hi));
+                                                        C->f, C->v, C->g, lo, hi));
+    if (F->dist) /* coarse v = 0 everywhere this rank stores it (ghost planes, or the whole agglomerated level) */
+        MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, C->v, C->g, 0.0, 1, 0, C->g.nzl));
     PROF_END(mg);
-    return MG_OK;
+    return after_restrict(mg, fine_level, C->f);
 }
 
 int mg3d_residual_restrict(mg3d_t* mg, int fine_level)
@@ -428,12 +637,12 @@ int mg3d_residual_restrict(mg3d_t* mg, int fine_level)
 static int interpolate_level(mg3d_t* mg, int fine_level, int add)
 {
     mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
-    const int lo = F->own_lo > 1 ? F->own_lo : 1;
-    const int hi = F->own_hi < F->g.nzl - 1 ? F->own_hi : F->g.nzl - 1;
+    int lo, hi;
+    interior_range(F, &lo, &hi);
     PROF_BEGIN(mg, fine_level, MG_OP_INTERPOLATE);
     MG_LAUNCH(mg->launches, mgk3d_interpolate(mg->stream, mg->dtype, F->v, F->g, C->v, C->g, add, lo, hi));
     PROF_END(mg);
-    return MG_OK;
+    return exchange(mg, fine_level, F->v, 3, 1, 1);
 }
 
 int mg3d_interpolate(mg3d_t* mg, int fine_level)
@@ -458,7 +667,8 @@ int mg3d_set_to_value(mg3d_t* mg, int level, int field, double value, int modify
     if (st) return st;
     if (field != MG_FIELD_V && field != MG_FIELD_F) return mg_fail(MG_ERR_ARG, "bad field");
     mg_level3d* L = &mg->lv[level];
-    MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, field_ptr(L, field), L->g, value, modify_boundaries, L->own_lo, L->own_hi));
+    /* ghost planes take the same constant: no exchange needed */
+    MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, field_ptr(L, field), L->g, value, modify_boundaries, 0, L->g.nzl));
     return MG_OK;
 }
 
@@ -469,12 +679,9 @@ static int vcycle_rec(mg3d_t* mg, int level, int v1, int v2)
     int st = relax_level(mg, level, v1);
     if (st) return st;
     if (level != mg->nlevels - 1) {
-        st = residual_restrict_level(mg, level);
-        if (st) return st;
-        st = vcycle_rec(mg, level + 1, v1, v2);
-        if (st) return st;
-        st = interpolate_level(mg, level, 1);
-        if (st) return st;
+        if ((st = residual_restrict_level(mg, level))) return st;
+        if ((st = vcycle_rec(mg, level + 1, v1, v2))) return st;
+        if ((st = interpolate_level(mg, level, 1))) return st;
     }
     return relax_level(mg, level, v2);
 }
@@ -493,21 +700,20 @@ static int fmg_rec(mg3d_t* mg, int level, int v0, int v1, int v2)
     int st;
     if (level != mg->nlevels - 1) {
         mg_level3d *F = &mg->lv[level], *C = &mg->lv[level + 1];
+        int lo, hi;
+        coarse_share(mg, level, &lo, &hi);
         PROF_BEGIN(mg, level, MG_OP_OTHER);
-        MG_LAUNCH(mg->launches, mgk3d_restrict(mg->stream, mg->dtype, F->f, F->g, C->f, C->g, C->own_lo, C->own_hi));
+        MG_LAUNCH(mg->launches, mgk3d_restrict(mg->stream, mg->dtype, F->f, F->g, C->f, C->g, lo, hi));
         PROF_END(mg);
-        st = fmg_rec(mg, level + 1, v0, v1, v2);
-        if (st) return st;
-        st = interpolate_level(mg, level, 0);
-        if (st) return st;
+        if ((st = after_restrict(mg, level, C->f))) return st;
+        if ((st = fmg_rec(mg, level + 1, v0, v1, v2))) return st;
+        if ((st = interpolate_level(mg, level, 0))) return st;
     } else {
         mg_level3d* L = &mg->lv[level];
-        MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, L->v, L->g, 0.0, 0, L->own_lo, L->own_hi));
+        MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, L->v, L->g, 0.0, 0, 0, L->g.nzl));
     }
-    for (int i = 0; i < v0; i++) {
-        st = vcycle_rec(mg, level, v1, v2);
-        if (st) return st;
-    }
+    for (int i = 0; i < v0; i++)
+        if ((st = vcycle_rec(mg, level, v1, v2))) return st;
     return MG_OK;
 }
 
@@ -548,12 +754,12 @@ int mg3d_restrict_host(mg3d_t* mg, const void* fine, const int fs[3], void* coar
     void *df = NULL, *dc = NULL;
     if ((st = temp_alloc(mg, &gf, &df))) return st;
     if ((st = temp_alloc(mg, &gc, &dc))) { cudaFree(df); return st; }
-    st = copy_in(mg, df, &gf, fine);
+    st = copy_in(mg, df, &gf, fine, 0, fn);
     if (!st) {
         int k = mgk3d_restrict(mg->stream, mg->dtype, df, gf, dc, gc, 0, cn);
         if (k < 0) st = mg_fail(MG_ERR_CUDA, "restrict launch failed"); else mg->launches += k;
     }
-    if (!st) st = copy_out(mg, coarse, dc, &gc);
+    if (!st) st = copy_out(mg, coarse, dc, &gc, 0, cn);
     cudaFree(df); cudaFree(dc);
     return st;
 }
@@ -570,13 +776,13 @@ int mg3d_interpolate_host(mg3d_t* mg, void* fine, const int fs[3], const void* c
     void *df = NULL, *dc = NULL;
     if ((st = temp_alloc(mg, &gf, &df))) return st;
     if ((st = temp_alloc(mg, &gc, &dc))) { cudaFree(df); return st; }
-    st = copy_in(mg, df, &gf, fine); /* boundary of fine is kept */
-    if (!st) st = copy_in(mg, dc, &gc, coarse);
+    st = copy_in(mg, df, &gf, fine, 0, fn); /* boundary of fine is kept */
+    if (!st) st = copy_in(mg, dc, &gc, coarse, 0, cn);
     if (!st) {
         int k = mgk3d_interpolate(mg->stream, mg->dtype, df, gf, dc, gc, 0, 1, fn - 1);
         if (k < 0) st = mg_fail(MG_ERR_CUDA, "interpolate launch failed"); else mg->launches += k;
     }
-    if (!st) st = copy_out(mg, fine, df, &gf);
+    if (!st) st = copy_out(mg, fine, df, &gf, 0, fn);
     cudaFree(df); cudaFree(dc);
     return st;
 }
@@ -592,13 +798,13 @@ int mg3d_apply_correction_host(mg3d_t* mg, void* fine, const int fs[3], const vo
     void *df = NULL, *de = NULL;
     if ((st = temp_alloc(mg, &g, &df))) return st;
     if ((st = temp_alloc(mg, &g, &de))) { cudaFree(df); return st; }
-    st = copy_in(mg, df, &g, fine);
-    if (!st) st = copy_in(mg, de, &g, error);
+    st = copy_in(mg, df, &g, fine, 0, fn);
+    if (!st) st = copy_in(mg, de, &g, error, 0, fn);
     if (!st) {
         int k = mgk3d_apply_correction(mg->stream, mg->dtype, df, de, g, 1, fn - 1);
         if (k < 0) st = mg_fail(MG_ERR_CUDA, "apply_correction launch failed"); else mg->launches += k;
     }
-    if (!st) st = copy_out(mg, fine, df, &g);
+    if (!st) st = copy_out(mg, fine, df, &g, 0, fn);
     cudaFree(df); cudaFree(de);
     return st;
 }
@@ -612,27 +818,27 @@ int mg3d_set_to_value_host(mg3d_t* mg, void* grid, const int s[3], double value,
     temp_geom(n, mg->dtype, &g);
     void* d = NULL;
     if ((st = temp_alloc(mg, &g, &d))) return st;
-    st = copy_in(mg, d, &g, grid);
+    st = copy_in(mg, d, &g, grid, 0, n);
     if (!st) {
         int k = mgk3d_set(mg->stream, mg->dtype, d, g, value, modify_boundaries, 0, n);
         if (k < 0) st = mg_fail(MG_ERR_CUDA, "set launch failed"); else mg->launches += k;
     }
-    if (!st) st = copy_out(mg, grid, d, &g);
+    if (!st) st = copy_out(mg, grid, d, &g, 0, n);
     cudaFree(d);
     return st;
 }
 
+/* end to end with HOST buffers: v,f hold the planes this rank owns (the whole grid on one GPU) */
 int mg3d_vcycle_host(mg3d_t* mg, void* v_host, const void* f_host, int v1, int v2, int cycles)
 {
     if (!mg || !v_host || !f_host) return mg_fail(MG_ERR_ARG, "null argument");
-    if (mg->nranks != 1) return mg_fail(MG_ERR_STATE, "vcycle_host: single-GPU handles only");
     if (v1 < 0 || v2 < 0 || cycles < 0) return mg_fail(MG_ERR_ARG, "negative count");
     mg_level3d* L = &mg->lv[0];
-    int st = copy_in(mg, L->v, &L->g, v_host);
-    if (!st) st = copy_in(mg, L->f, &L->g, f_host);
+    int st = copy_in(mg, L->v, &L->g, v_host, L->own_lo, L->own_hi);
+    if (!st) st = exchange(mg, 0, L->v, 3, MG_GHOST_LO, 1);
+    if (!st) st = copy_in(mg, L->f, &L->g, f_host, L->own_lo, L->own_hi);
+    if (!st) st = exchange(mg, 0, L->f, 3, MG_GHOST_LO, 1);
     for (int i = 0; i < cycles && !st; i++) st = vcycle_rec(mg, 0, v1, v2);
-    if (!st) st = copy_out(mg, v_host, L->v, &L->g);
+    if (!st) st = copy_out(mg, v_host, L->v, &L->g, L->own_lo, L->own_hi);
     return st;
 }
-
-/* multi-GPU entry points: implemented in mg3d_dist.c */

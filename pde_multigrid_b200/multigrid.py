@@ -62,6 +62,7 @@ class _MultiGridBase:
         return self._fn("level_h")(self._h, ctypes.c_int(level))
 
     def shape(self, level):
+        """Shape of the host array of a level as this rank sees it (multi-GPU 3D: the owned z-planes)."""
         return (self.level_size(level),) * self.dim
 
     @property
@@ -210,8 +211,31 @@ class MultiGrid3D(_MultiGridBase):
                                            int(rank), int(nranks), nccl_unique_id))
         self._h = h
 
+        self.rank, self.nranks = int(rank), int(nranks)
+
     def set_smoother(self, smoother, sweeps_per_pass=1):
         self._call("set_smoother", ctypes.c_int(smoother), ctypes.c_int(sweeps_per_pass))
+
+    def owned_range(self, level):
+        """(z_begin, z_count) of the global planes this rank owns on `level`."""
+        zb, zc = ctypes.c_int(), ctypes.c_int()
+        self._call("owned_range", ctypes.c_int(level), ctypes.byref(zb), ctypes.byref(zc))
+        return zb.value, zc.value
+
+    def shape(self, level):
+        n = self.level_size(level)
+        return (self.owned_range(level)[1], n, n)
+
+    @property
+    def halo_bytes(self):
+        return self._fn("halo_bytes")(self._h)
+
+    @staticmethod
+    def plan_level(n, nranks, rank):
+        """Slab plan (no GPU needed): dict(dist, z0, nzl, own_lo, own_hi)."""
+        out = (ctypes.c_int * 5)()
+        check(_lib.lib().mg3d_plan_level(ctypes.c_int(n), ctypes.c_int(nranks), ctypes.c_int(rank), out))
+        return dict(zip(("dist", "z0", "nzl", "own_lo", "own_hi"), list(out)))
 
 
 class MultiGrid2D(_MultiGridBase):
