@@ -43,6 +43,18 @@ typedef struct {
     unsigned char tmap_rr[2][128] __attribute__((aligned(64))); /* residual+restrict boxes */
 } mg_level3d;
 
+/* direct NVLink halo path (mg_halo_p2p.cu): the neighbours' arenas and flag words mapped with CUDA IPC */
+typedef struct {
+    int enabled;
+    char* peer_arena[2];          /* [0] rank-1, [1] rank+1 */
+    unsigned int* flags;          /* local words, one per 128-B line: [0] raised by rank-1, [32] by rank+1, [64] push counter, [96] wait error */
+    unsigned int* peer_flags[2];
+    unsigned int sent[2], expect[2];
+    size_t* nb_off[2];            /* neighbour's byte offset of field fi of level l inside its arena: [2*l + fi] */
+    mg_geom3d* nb_geom[2];        /* neighbour's slab geometry per level */
+    int* nb_own[2];               /* neighbour's own_lo, own_hi per level: [2*l], [2*l+1] */
+} mg_p2p;
+
 struct mg3d_s {
     int dtype, mode, nlevels;
     int rank, nranks;
@@ -50,6 +62,7 @@ struct mg3d_s {
     double range[6];
     cudaStream_t stream;
     mg_comm* comm;
+    mg_p2p p2p;
     mg_level3d* lv;
     void* arena;
     double* d_scratch; /* 2*MGK_NORM_BLOCKS partials + 2 outputs */
@@ -159,10 +172,54 @@ static char* plane_ptr(const mg3d_t* mg, const mg_level3d* L, void* field, int c
  *   down: my bottom owned plane (if `down` != 0) -> the upper ghost of rank-1
  * colour_mask: bit 0 = colour-0 array, bit 1 = colour-1 array.
  * ---------------------------------------------------------------------------------------------- */
+static int exchange_p2p(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int down)
+{
+    mg_level3d* L = &mg->lv[level];
+    mg_p2p* q = &mg->p2p;
+    const size_t es = mg_esize(mg->dtype), pb = (size_t)L->g.plane * es; /* bytes per colour plane */
+    const int r = mg->rank, P = mg->nranks, fi = field == L->v ? 0 : 1;
+    const void* src[4] = {0, 0, 0, 0};
+    void* dst[4] = {0, 0, 0, 0};
+    unsigned long long bytes[4] = {0, 0, 0, 0};
+    unsigned int* raise[2] = {0, 0};
+    unsigned int values[2] = {0, 0};
+    int nseg = 0;
+    const int send_up = r + 1 < P && depth_up > 0, send_down = r > 0 && down;
+    for (int col = 0; col < 2; col++) {
+        if (!(colour_mask & (1 << col))) continue;
+        if (send_up) { /* my top planes -> the lower ghosts of rank+1 */
+            const mg_geom3d* ng = &q->nb_geom[1][level];
+            src[nseg] = plane_ptr(mg, L, field, col, L->own_hi - depth_up);
+            dst[nseg] = q->peer_arena[1] + q->nb_off[1][2 * level + fi] +
+                        ((size_t)col * (size_t)ng->cstride + (size_t)(q->nb_own[1][2 * level] - depth_up) * (size_t)ng->plane) * es;
+            bytes[nseg++] = pb * depth_up;
+            mg->halo_bytes += (long long)(pb * depth_up);
+        }
+        if (send_down) { /* my bottom plane -> the upper ghost of rank-1 */
+            const mg_geom3d* ng = &q->nb_geom[0][level];
+            src[nseg] = plane_ptr(mg, L, field, col, L->own_lo);
+            dst[nseg] = q->peer_arena[0] + q->nb_off[0][2 * level + fi] +
+                        ((size_t)col * (size_t)ng->cstride + (size_t)q->nb_own[0][2 * level + 1] * (size_t)ng->plane) * es;
+            bytes[nseg++] = pb;
+            mg->halo_bytes += (long long)pb;
+        }
+    }
+    if (send_up) { raise[1] = q->peer_flags[1] + 0; values[1] = ++q->sent[1]; }    /* its "from below" word */
+    if (send_down) { raise[0] = q->peer_flags[0] + 32; values[0] = ++q->sent[0]; } /* its "from above" word */
+    PROF_BEGIN(mg, level, MG_OP_OTHER);
+    MG_LAUNCH(mg->launches, mgk_halo_push(mg->stream, src, dst, bytes, raise, values, q->flags + 64));
+    const int recv_below = r > 0 && depth_up > 0, recv_above = r + 1 < P && down;
+    const unsigned int v0 = recv_below ? ++q->expect[0] : 0, v1 = recv_above ? ++q->expect[1] : 0;
+    MG_LAUNCH(mg->launches, mgk_halo_wait(mg->stream, recv_below ? q->flags + 0 : NULL, v0, recv_above ? q->flags + 32 : NULL, v1, q->flags + 96));
+    PROF_END(mg);
+    return MG_OK;
+}
+
 static int exchange(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int down)
 {
     mg_level3d* L = &mg->lv[level];
     if (!L->dist) return MG_OK;
+    if (mg->p2p.enabled) return exchange_p2p(mg, level, field, colour_mask, depth_up, down);
     const size_t pe = (size_t)L->g.plane; /* elements per colour plane */
     const int r = mg->rank, P = mg->nranks;
     int st;
@@ -222,6 +279,108 @@ static int gather_level(mg3d_t* mg, int level, void* field, int top_from_last)
     }
     PROF_END(mg);
     return st;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * CUDA IPC mapping of the z-neighbours' arenas and flag words (enables exchange_p2p).  Handles travel
+ * through an NCCL all-gather.  If IPC / peer access is not available the NCCL send/recv path stays.
+ * ---------------------------------------------------------------------------------------------- */
+static int p2p_setup(mg3d_t* mg, size_t arena_bytes)
+{
+    (void)arena_bytes;
+    mg_p2p* q = &mg->p2p;
+    const int r = mg->rank, P = mg->nranks;
+    /* what the neighbours' arenas look like: replay the allocation arithmetic for rank-1 and rank+1 */
+    for (int k = 0; k < 2; k++) {
+        const int nr = k == 0 ? r - 1 : r + 1;
+        if (nr < 0 || nr >= P) continue;
+        q->nb_off[k] = (size_t*)calloc(2 * (size_t)mg->nlevels, sizeof(size_t));
+        q->nb_geom[k] = (mg_geom3d*)calloc((size_t)mg->nlevels, sizeof(mg_geom3d));
+        q->nb_own[k] = (int*)calloc(2 * (size_t)mg->nlevels, sizeof(int));
+        if (!q->nb_off[k] || !q->nb_geom[k] || !q->nb_own[k]) return mg_fail(MG_ERR_NOMEM, "host allocation failed");
+        size_t off = 0;
+        for (int l = 0; l < mg->nlevels; l++) {
+            int plan[5];
+            mg3d_plan_level(mg->lv[l].g.n, P, nr, plan);
+            set_geom(&q->nb_geom[k][l], mg->lv[l].g.n, mg->dtype, plan[1], plan[2]);
+            q->nb_own[k][2 * l] = plan[3];
+            q->nb_own[k][2 * l + 1] = plan[4];
+            const size_t fb = mg_align256(2 * (size_t)q->nb_geom[k][l].cstride * mg_esize(mg->dtype));
+            q->nb_off[k][2 * l] = off; off += fb;
+            q->nb_off[k][2 * l + 1] = off; off += fb;
+        }
+    }
+    MG_CUDA(cudaMalloc((void**)&q->flags, 128 * sizeof(unsigned int)));
+    MG_CUDA(cudaMemsetAsync(q->flags, 0, 128 * sizeof(unsigned int), mg->stream));
+    /* all-gather {arena handle, flags handle} (64 B each) */
+    cudaIpcMemHandle_t mine[2];
+    int ok = 1; /* a rank without IPC still takes part in the collectives below, then everybody keeps NCCL */
+    memset(mine, 0, sizeof mine);
+    if (cudaIpcGetMemHandle(&mine[0], mg->arena) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], q->flags) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+    }
+    const size_t hb = sizeof mine; /* 128 */
+    unsigned char* d_all = NULL;
+    MG_CUDA(cudaMalloc((void**)&d_all, hb * P));
+    MG_CUDA(cudaMemcpyAsync(d_all + hb * r, mine, hb, cudaMemcpyHostToDevice, mg->stream));
+    int st = mg_comm_allgather_inplace(mg->comm, d_all, hb / 4, MG_F32, mg->stream);
+    if (st) { cudaFree(d_all); return st; }
+    cudaIpcMemHandle_t* all = (cudaIpcMemHandle_t*)malloc(hb * P);
+    if (!all) { cudaFree(d_all); return mg_fail(MG_ERR_NOMEM, "host allocation failed"); }
+    cudaError_t e = cudaMemcpyAsync(all, d_all, hb * P, cudaMemcpyDeviceToHost, mg->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(mg->stream);
+    cudaFree(d_all);
+    if (e != cudaSuccess) ok = 0;
+    for (int k = 0; k < 2 && ok; k++) {
+        const int nr = k == 0 ? r - 1 : r + 1;
+        if (nr < 0 || nr >= P) continue;
+        void *pa = NULL, *pf = NULL;
+        if (cudaIpcOpenMemHandle(&pa, all[2 * nr], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&pf, all[2 * nr + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+            break;
+        }
+        q->peer_arena[k] = (char*)pa;
+        q->peer_flags[k] = (unsigned int*)pf;
+    }
+    free(all);
+    /* every rank must agree on the transport: all-reduce the success bit */
+    double* d2 = mg->d_scratch + 2 * MGK_NORM_BLOCKS;
+    double h2[2] = {ok ? 0.0 : 1.0, 0.0};
+    MG_CUDA(cudaMemcpyAsync(d2, h2, sizeof h2, cudaMemcpyHostToDevice, mg->stream));
+    if ((st = mg_comm_allreduce_sum_max(mg->comm, d2, mg->stream))) return st;
+    MG_CUDA(cudaMemcpyAsync(h2, d2, sizeof h2, cudaMemcpyDeviceToHost, mg->stream));
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
+    q->enabled = h2[0] == 0.0;
+    return MG_OK;
+}
+
+static void p2p_teardown(mg3d_t* mg)
+{
+    mg_p2p* q = &mg->p2p;
+    for (int k = 0; k < 2; k++) {
+        if (q->peer_arena[k]) cudaIpcCloseMemHandle(q->peer_arena[k]);
+        if (q->peer_flags[k]) cudaIpcCloseMemHandle(q->peer_flags[k]);
+        free(q->nb_off[k]); free(q->nb_geom[k]); free(q->nb_own[k]);
+    }
+    if (mg->comm && q->flags) { /* nobody unmaps or frees while a neighbour may still be pushing */
+        double* d2 = mg->d_scratch + 2 * MGK_NORM_BLOCKS;
+        if (mg_comm_allreduce_sum_max(mg->comm, d2, mg->stream) == MG_OK) cudaStreamSynchronize(mg->stream);
+    }
+    if (q->flags) cudaFree(q->flags);
+    memset(q, 0, sizeof *q);
+}
+
+static int halo_error_check(mg3d_t* mg)
+{
+    if (!mg->p2p.enabled) return MG_OK;
+    unsigned int err = 0;
+    MG_CUDA(cudaMemcpyAsync(&err, mg->p2p.flags + 96, sizeof err, cudaMemcpyDeviceToHost, mg->stream));
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
+    if (err) return mg_fail(MG_ERR_COMM, "halo exchange timed out waiting for a neighbour's flag (rank %d)", mg->rank);
+    return MG_OK;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -295,6 +454,7 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
     }
     if (nranks > 1) {
         st = mg_comm_create(&mg->comm, rank, nranks, uid);
+        if (!st && !(getenv("MG_B200_HALO") && !strcmp(getenv("MG_B200_HALO"), "nccl"))) st = p2p_setup(mg, total);
         if (st) { mg3d_destroy(mg); return st; }
     }
     /* TMA tensor maps of v for the levels large enough to fill the z-marching tiles */
@@ -337,6 +497,7 @@ int mg3d_destroy(mg3d_t* mg)
 {
     if (!mg) return MG_OK;
     if (mg->stream) cudaStreamSynchronize(mg->stream);
+    p2p_teardown(mg);
     if (mg->comm) mg_comm_destroy(mg->comm);
     if (mg->stream) cudaStreamDestroy(mg->stream);
     if (mg->arena) cudaFree(mg->arena);
@@ -400,7 +561,7 @@ int mg3d_sync(mg3d_t* mg)
 {
     if (!mg) return mg_fail(MG_ERR_ARG, "null handle");
     MG_CUDA(cudaStreamSynchronize(mg->stream));
-    return MG_OK;
+    return halo_error_check(mg);
 }
 
 /* dense host array (x fastest, idx = x + y*n + z*n*n) <-> colour-split device field: one linear copy
@@ -493,6 +654,15 @@ int mg3d_init_problem(mg3d_t* mg)
         if (e != cudaSuccess) { free(tab); return mg_fail(MG_ERR_CUDA, "init failed: %s", cudaGetErrorString(e)); }
     }
     free(tab);
+    /* The init kernels wrote the ghost planes locally.  With the direct-store halo transport a neighbour that
+       is already past this point could push into them before those kernels ran here: a bidirectional
+       exchange per distributed level is the handshake that orders the two (and it is cheap). */
+    for (int l = 0; l < mg->nlevels; l++) {
+        mg_level3d* L = &mg->lv[l];
+        int st = exchange(mg, l, L->v, 3, MG_GHOST_LO, 1);
+        if (!st) st = exchange(mg, l, L->f, 3, MG_GHOST_LO, 1);
+        if (st) return st;
+    }
     return MG_OK;
 }
 
@@ -564,7 +734,7 @@ int mg3d_residual_norm(mg3d_t* mg, int level, double* l2, double* linf)
     MG_CUDA(cudaStreamSynchronize(mg->stream));
     if (l2) *l2 = sqrt(mg->h_out2[0]);
     if (linf) *linf = mg->h_out2[1];
-    return MG_OK;
+    return halo_error_check(mg);
 }
 
 /* coarse local planes this rank computes when restricting from fine level `fine_level` */
@@ -667,9 +837,9 @@ int mg3d_set_to_value(mg3d_t* mg, int level, int field, double value, int modify
     if (st) return st;
     if (field != MG_FIELD_V && field != MG_FIELD_F) return mg_fail(MG_ERR_ARG, "bad field");
     mg_level3d* L = &mg->lv[level];
-    /* ghost planes take the same constant: no exchange needed */
+    /* ghost planes take the same constant; the exchange is the neighbour handshake (see mg3d_init_problem) */
     MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, field_ptr(L, field), L->g, value, modify_boundaries, 0, L->g.nzl));
-    return MG_OK;
+    return exchange(mg, level, field_ptr(L, field), 3, MG_GHOST_LO, 1);
 }
 
 /* VCycle, N3/MultiGrid3D.cpp:623-647.  CalculateResidual + Restrict + setToValue(coarse v, 0, true)
