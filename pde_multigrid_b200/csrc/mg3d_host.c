@@ -49,11 +49,20 @@ typedef struct {
     char* peer_arena[2];          /* [0] rank-1, [1] rank+1 */
     unsigned int* flags;          /* local words, one per 128-B line: [0] raised by rank-1, [32] by rank+1, [64] push counter, [96] wait error */
     unsigned int* peer_flags[2];
-    unsigned int sent[2], expect[2];
     size_t* nb_off[2];            /* neighbour's byte offset of field fi of level l inside its arena: [2*l + fi] */
     mg_geom3d* nb_geom[2];        /* neighbour's slab geometry per level */
     int* nb_own[2];               /* neighbour's own_lo, own_hi per level: [2*l], [2*l+1] */
 } mg_p2p;
+
+/* CUDA-graph cache of whole V-cycles: the cycle is ~100 dependent launches, most of them tiny (coarse
+   levels, halo kernels); replaying them from a graph removes the per-launch gaps that dominate at 257^3
+   and on the 8-GPU slabs.  Key = (level, v1, v2, smoother). */
+#define MG_GRAPH_SLOTS 8
+typedef struct {
+    int used, level, v1, v2, smoother, calls;
+    cudaGraphExec_t exec;
+    long long launches, halo_bytes;
+} mg_graph_slot;
 
 struct mg3d_s {
     int dtype, mode, nlevels;
@@ -73,6 +82,8 @@ struct mg3d_s {
     long long launches;
     long long halo_bytes; /* bytes sent by this rank in halo exchanges / gathers */
     mg_prof prof;
+    int use_graphs;
+    mg_graph_slot graphs[MG_GRAPH_SLOTS];
 };
 
 #define PROF_BEGIN(mg, level, op) mg_prof_begin(&(mg)->prof, (mg)->stream, (level), (op), (mg)->launches)
@@ -182,7 +193,6 @@ static int exchange_p2p(mg3d_t* mg, int level, void* field, int colour_mask, int
     void* dst[4] = {0, 0, 0, 0};
     unsigned long long bytes[4] = {0, 0, 0, 0};
     unsigned int* raise[2] = {0, 0};
-    unsigned int values[2] = {0, 0};
     int nseg = 0;
     const int send_up = r + 1 < P && depth_up > 0, send_down = r > 0 && down;
     for (int col = 0; col < 2; col++) {
@@ -204,13 +214,11 @@ static int exchange_p2p(mg3d_t* mg, int level, void* field, int colour_mask, int
             mg->halo_bytes += (long long)pb;
         }
     }
-    if (send_up) { raise[1] = q->peer_flags[1] + 0; values[1] = ++q->sent[1]; }    /* its "from below" word */
-    if (send_down) { raise[0] = q->peer_flags[0] + 32; values[0] = ++q->sent[0]; } /* its "from above" word */
-    PROF_BEGIN(mg, level, MG_OP_OTHER);
-    MG_LAUNCH(mg->launches, mgk_halo_push(mg->stream, src, dst, bytes, raise, values, q->flags + 64));
+    if (send_up) raise[1] = q->peer_flags[1] + 0;    /* its "from below" word */
+    if (send_down) raise[0] = q->peer_flags[0] + 32; /* its "from above" word */
     const int recv_below = r > 0 && depth_up > 0, recv_above = r + 1 < P && down;
-    const unsigned int v0 = recv_below ? ++q->expect[0] : 0, v1 = recv_above ? ++q->expect[1] : 0;
-    MG_LAUNCH(mg->launches, mgk_halo_wait(mg->stream, recv_below ? q->flags + 0 : NULL, v0, recv_above ? q->flags + 32 : NULL, v1, q->flags + 96));
+    PROF_BEGIN(mg, level, MG_OP_OTHER);
+    MG_LAUNCH(mg->launches, mgk_halo_exchange(mg->stream, src, dst, bytes, raise, recv_below, recv_above, q->flags));
     PROF_END(mg);
     return MG_OK;
 }
@@ -310,8 +318,8 @@ static int p2p_setup(mg3d_t* mg, size_t arena_bytes)
             q->nb_off[k][2 * l + 1] = off; off += fb;
         }
     }
-    MG_CUDA(cudaMalloc((void**)&q->flags, 128 * sizeof(unsigned int)));
-    MG_CUDA(cudaMemsetAsync(q->flags, 0, 128 * sizeof(unsigned int), mg->stream));
+    MG_CUDA(cudaMalloc((void**)&q->flags, MG_HALO_FLAG_WORDS * sizeof(unsigned int)));
+    MG_CUDA(cudaMemsetAsync(q->flags, 0, MG_HALO_FLAG_WORDS * sizeof(unsigned int), mg->stream));
     /* all-gather {arena handle, flags handle} (64 B each) */
     cudaIpcMemHandle_t mine[2];
     int ok = 1; /* a rank without IPC still takes part in the collectives below, then everybody keeps NCCL */
@@ -414,6 +422,7 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
     mg->nranks = nranks;
     mg->smoother = MG_SMOOTHER_AUTO;
     mg->sweeps_per_pass = 1;
+    mg->use_graphs = getenv("MG_B200_NO_GRAPH") ? 0 : 1;
     memcpy(mg->range, range, sizeof mg->range);
     mg->nlevels = mg_num_levels_for(n);
     mg->lv = (mg_level3d*)calloc((size_t)mg->nlevels, sizeof(mg_level3d));
@@ -497,6 +506,8 @@ int mg3d_destroy(mg3d_t* mg)
 {
     if (!mg) return MG_OK;
     if (mg->stream) cudaStreamSynchronize(mg->stream);
+    for (int i = 0; i < MG_GRAPH_SLOTS; i++)
+        if (mg->graphs[i].used && mg->graphs[i].exec) cudaGraphExecDestroy(mg->graphs[i].exec);
     p2p_teardown(mg);
     if (mg->comm) mg_comm_destroy(mg->comm);
     if (mg->stream) cudaStreamDestroy(mg->stream);
@@ -856,12 +867,60 @@ static int vcycle_rec(mg3d_t* mg, int level, int v1, int v2)
     return relax_level(mg, level, v2);
 }
 
+/* The second call with the same (level, v1, v2, smoother) captures the cycle into a CUDA graph; later calls
+   replay it.  The first call runs eagerly (kernel attributes are set, lazy module loading is done).  The
+   P2P halo kernels keep their sequence counters in device memory, so their arguments are capture-stable;
+   NCCL collectives are graph-capturable.  Per-operator timers need eager launches: profiling disables it. */
 int mg3d_vcycle(mg3d_t* mg, int level, int v1, int v2)
 {
     int st = check_level(mg, level);
     if (st) return st;
     if (v1 < 0 || v2 < 0) return mg_fail(MG_ERR_ARG, "negative sweep count");
-    return vcycle_rec(mg, level, v1, v2);
+    const long long per_cycle = 2LL * (v1 + v2) * (mg->nlevels - level) * 2;
+    if (!mg->use_graphs || mg->prof.enabled || per_cycle > 4096) return vcycle_rec(mg, level, v1, v2);
+    mg_graph_slot* g = NULL;
+    for (int i = 0; i < MG_GRAPH_SLOTS && !g; i++)
+        if (mg->graphs[i].used && mg->graphs[i].level == level && mg->graphs[i].v1 == v1 && mg->graphs[i].v2 == v2 &&
+            mg->graphs[i].smoother == mg->smoother)
+            g = &mg->graphs[i];
+    if (!g) {
+        for (int i = 0; i < MG_GRAPH_SLOTS && !g; i++)
+            if (!mg->graphs[i].used) g = &mg->graphs[i];
+        if (!g) return vcycle_rec(mg, level, v1, v2); /* cache full: run eagerly */
+        memset(g, 0, sizeof *g);
+        g->used = 1; g->level = level; g->v1 = v1; g->v2 = v2; g->smoother = mg->smoother;
+    }
+    g->calls++;
+    if (g->calls == 1) return vcycle_rec(mg, level, v1, v2);
+    if (!g->exec) {
+        const long long l0 = mg->launches, h0 = mg->halo_bytes;
+        cudaGraph_t graph = NULL;
+        MG_CUDA(cudaStreamBeginCapture(mg->stream, cudaStreamCaptureModeThreadLocal));
+        st = vcycle_rec(mg, level, v1, v2);
+        cudaError_t e = cudaStreamEndCapture(mg->stream, &graph);
+        g->launches = mg->launches - l0;
+        g->halo_bytes = mg->halo_bytes - h0;
+        mg->launches = l0;
+        mg->halo_bytes = h0;
+        if (st || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            mg->use_graphs = 0; /* capture is not possible here: stay eager */
+            return st ? st : vcycle_rec(mg, level, v1, v2);
+        }
+        e = cudaGraphInstantiate(&g->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            g->exec = NULL;
+            cudaGetLastError();
+            mg->use_graphs = 0;
+            return vcycle_rec(mg, level, v1, v2);
+        }
+    }
+    MG_CUDA(cudaGraphLaunch(g->exec, mg->stream));
+    mg->launches += g->launches;
+    mg->halo_bytes += g->halo_bytes;
+    return MG_OK;
 }
 
 /* FullMultiGridVCycle, N3/MultiGrid3D.cpp:569-585 */

@@ -2,9 +2,9 @@
 //
 // The z-slab neighbours map each other's field arena with CUDA IPC.  One "push" kernel copies this
 // rank's boundary planes straight into the ghost planes of rank-1 / rank+1 (plain st.global on peer
-// pointers: NVLink 5 through NVSwitch), fences system-wide and then raises a sequence flag in the
-// neighbour's memory; one "wait" kernel spins (single thread, acquire loads, bounded) until both
-// neighbours' flags have reached the expected sequence number.  Two tiny launches per exchange and no
+// pointers: NVLink 5 through NVSwitch), fences system-wide, raises a sequence flag in the neighbour's
+// memory and finally (last CTA, one thread, acquire loads, bounded) waits until both neighbours' flags
+// have reached this exchange's sequence number.  One tiny launch per exchange and no
 // host round trip or collective-library protocol: ~5 us instead of the ~20-90 us of a grouped
 // ncclSend/ncclRecv (measured on 8 B200: profiles/), which is what the latency-bound coarse distributed
 // levels need.  Write-after-read safety comes from the SPMD schedule: every rank alternates compute and
@@ -15,16 +15,21 @@
 
 namespace {
 
-struct PushArgs {
+// flag block layout (unsigned words, one per 128-byte line): [0] raised by rank-1, [32] raised by rank+1,
+// [64] push-completion counter, [96] wait-timeout error, [128] sent-to-below count, [160] sent-to-above count,
+// [192] expected-from-below count, [224] expected-from-above count.  The sequence counters live in device
+// memory so that the kernel arguments never change: the exchange can be captured into a CUDA graph.
+struct XArgs {
     const void* src[4];
     void* dst[4];
     unsigned long long bytes[4];  // multiples of 16
-    unsigned int* flag[2];        // peer flags to raise (nullptr = none)
-    unsigned int value[2];
-    unsigned int* done_counter;   // local, zero on entry, reset by the last CTA
+    unsigned int* peer_flag[2];   // [0]: word in rank-1's block to raise, [1]: word in rank+1's block (nullptr = no send)
+    int wait_below, wait_above;   // expect a push from rank-1 / rank+1
+    unsigned int* block;          // my flag block
+    long long max_cycles;
 };
 
-__global__ void __launch_bounds__(256) k_halo_push(PushArgs a)
+__global__ void __launch_bounds__(256) k_halo_exchange(XArgs a)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
@@ -38,36 +43,33 @@ __global__ void __launch_bounds__(256) k_halo_push(PushArgs a)
     }
     __threadfence_system();  // my stores are visible to the peer before the flag
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(a.done_counter, 1u);
-        if (prev == gridDim.x - 1) {  // last CTA: everything has been stored and fenced
-            *a.done_counter = 0;
-            __threadfence_system();
-            for (int f = 0; f < 2; f++)
-                if (a.flag[f]) {
-                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag[f]), "r"(a.value[f]) : "memory");
-                }
+    if (threadIdx.x != 0) return;
+    unsigned int* blk = a.block;
+    const unsigned int prev = atomicAdd(blk + 64, 1u);
+    if (prev != gridDim.x - 1) return;
+    // last CTA: every segment has been stored and fenced
+    blk[64] = 0;
+    __threadfence_system();
+    for (int k = 0; k < 2; k++)
+        if (a.peer_flag[k]) {
+            const unsigned int v = ++blk[128 + 32 * k];
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flag[k]), "r"(v) : "memory");
         }
-    }
-}
-
-__global__ void k_halo_wait(const unsigned int* f0, unsigned int v0, const unsigned int* f1, unsigned int v1, unsigned int* error_flag,
-                            long long max_cycles)
-{
+    // then wait for the neighbours' pushes of this same exchange (bounded: never hang the GPU)
     const long long t0 = clock64();
-    const unsigned int* fl[2] = {f0, f1};
-    const unsigned int want[2] = {v0, v1};
+    const int waits[2] = {a.wait_below, a.wait_above};
     for (int k = 0; k < 2; k++) {
-        if (!fl[k]) continue;
+        if (!waits[k]) continue;
+        const unsigned int want = ++blk[192 + 32 * k];
+        const unsigned int* fl = blk + 32 * k;
         while (true) {
             unsigned int cur;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(fl[k]) : "memory");
-            if ((int)(cur - want[k]) >= 0) break;
-            if (clock64() - t0 > max_cycles) {  // never hang the GPU: report and carry on
-                *error_flag = 1;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(fl) : "memory");
+            if ((int)(cur - want) >= 0) break;
+            if (clock64() - t0 > a.max_cycles) {
+                blk[96] = 1;
                 return;
             }
-            __nanosleep(100);
         }
     }
 }
@@ -76,11 +78,13 @@ __global__ void k_halo_wait(const unsigned int* f0, unsigned int v0, const unsig
 
 extern "C" {
 
-/* up to 4 (src, dst, bytes) segments; flags[k] (may be NULL) receives values[k] once all segments are stored */
-int mgk_halo_push(cudaStream_t s, const void* const src[4], void* const dst[4], const unsigned long long bytes[4],
-                  unsigned int* const flags[2], const unsigned int values[2], unsigned int* done_counter)
+/* One launch per halo exchange: push up to 4 (src, dst, bytes) segments into the neighbours' ghost planes,
+   raise their sequence flags, then wait for the neighbours' own pushes.  peer_flag[k] == NULL: nothing is sent
+   in that direction. */
+int mgk_halo_exchange(cudaStream_t s, const void* const src[4], void* const dst[4], const unsigned long long bytes[4],
+                      unsigned int* const peer_flag[2], int wait_below, int wait_above, unsigned int* flag_block)
 {
-    PushArgs a;
+    XArgs a;
     unsigned long long total = 0;
     for (int i = 0; i < 4; i++) {
         a.src[i] = src[i];
@@ -88,23 +92,16 @@ int mgk_halo_push(cudaStream_t s, const void* const src[4], void* const dst[4], 
         a.bytes[i] = bytes[i];
         total += bytes[i];
     }
-    for (int k = 0; k < 2; k++) {
-        a.flag[k] = flags[k];
-        a.value[k] = values[k];
-    }
-    a.done_counter = done_counter;
-    if (!total && !flags[0] && !flags[1]) return 0;
+    a.peer_flag[0] = peer_flag[0];
+    a.peer_flag[1] = peer_flag[1];
+    a.wait_below = wait_below;
+    a.wait_above = wait_above;
+    a.block = flag_block;
+    a.max_cycles = 6000000000LL; /* ~3 s */
+    if (!total && !peer_flag[0] && !peer_flag[1] && !wait_below && !wait_above) return 0;
     unsigned long long want = (total / 16 + 256 * 8 - 1) / (256 * 8);  // ~8 x 16 B per thread
     int grid = (int)(want < 1 ? 1 : (want > 296 ? 296 : want));
-    k_halo_push<<<grid, 256, 0, s>>>(a);
-    return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
-}
-
-int mgk_halo_wait(cudaStream_t s, const unsigned int* f0, unsigned int v0, const unsigned int* f1, unsigned int v1,
-                  unsigned int* error_flag)
-{
-    if (!f0 && !f1) return 0;
-    k_halo_wait<<<1, 1, 0, s>>>(f0, v0, f1, v1, error_flag, 6000000000LL /* ~3 s */);
+    k_halo_exchange<<<grid, 256, 0, s>>>(a);
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 

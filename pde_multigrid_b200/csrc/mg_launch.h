@@ -97,12 +97,11 @@ int mgk3d_init_f(cudaStream_t s, int dtype, void* f, mg_geom3d g, const double* 
 /* dense (reference layout, x fastest, zl_hi-zl_lo planes starting at `dense`) <-> colour-split field */
 int mgk3d_repack(cudaStream_t s, int dtype, void* split, mg_geom3d g, void* dense, int to_device, int zl_lo, int zl_hi);
 
-/* P2P halo exchange (mg_halo_p2p.cu): push up to 4 segments into peer memory and raise the peers' sequence
-   flags; wait until this rank's flags have reached the expected sequence numbers (bounded spin) */
-int mgk_halo_push(cudaStream_t s, const void* const src[4], void* const dst[4], const unsigned long long bytes[4],
-                  unsigned int* const flags[2], const unsigned int values[2], unsigned int* done_counter);
-int mgk_halo_wait(cudaStream_t s, const unsigned int* f0, unsigned int v0, const unsigned int* f1, unsigned int v1,
-                  unsigned int* error_flag);
+/* P2P halo exchange (mg_halo_p2p.cu), one launch: push up to 4 segments into peer memory, raise the peers'
+   sequence flags, wait for the neighbours' pushes (bounded spin); sequence counters live in flag_block */
+#define MG_HALO_FLAG_WORDS 256
+int mgk_halo_exchange(cudaStream_t s, const void* const src[4], void* const dst[4], const unsigned long long bytes[4],
+                      unsigned int* const peer_flag[2], int wait_below, int wait_above, unsigned int* flag_block);
 
 /* ---- 2D (pitched: element (x,y) at base[x + y*pitch]) ---- */
 typedef struct {
