@@ -1,0 +1,226 @@
+"""CPU, world_size 2, gloo: the multi-GPU z-slab SCHEDULE of the 3D driver (pde_multigrid_b200/csrc/mg3d_host.c).
+
+Two processes hold the slabs that mg3d_plan_level (the product's own partition arithmetic, called through the
+C ABI) assigns them; everything outside a slab is NaN.  They run V(2,2) cycles with numpy stand-ins for the
+kernels, restricted to the planes a rank owns, and exchange planes over gloo exactly where the C driver does:
+  * after every half-sweep: the just-updated colour's top plane up / bottom plane down (depth 1),
+  * before the fused residual+restrict: the two top planes up (the kernel reads v two planes below the slab),
+  * after it: coarse f planes (distributed coarse level) or an all-gather (first agglomerated level),
+  * after prolongation+correction: fine v, depth 1 both ways.
+If a ghost depth or an exchange were missing, a NaN would reach an owned plane.  The owned planes must equal the
+same cycles run sequentially on the whole grid, bit for bit (RB Gauss-Seidel is partition-invariant)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+N = 65
+NU = 2
+CYCLES = 2
+
+
+def sizes(n):
+    out = [n]
+    while out[-1] > 3:
+        out.append((out[-1] - 1) // 2 + 1)
+    return out
+
+
+# ---- numpy stand-ins for the kernels (z, y, x axes), acting on planes [lo, hi) only ----------------
+
+def relax_colour(v, f, colour, lo, hi):
+    n = v.shape[1]
+    h2 = (1.0 / (n - 1)) ** 2
+    z, y, x = np.meshgrid(np.arange(lo, hi), np.arange(1, n - 1), np.arange(1, n - 1), indexing="ij")
+    mask = ((x + y + z) % 2) == colour
+    s = (v[lo:hi, 1:-1, :-2] + v[lo:hi, 1:-1, 2:] + v[lo:hi, :-2, 1:-1] + v[lo:hi, 2:, 1:-1] +
+         v[lo - 1:hi - 1, 1:-1, 1:-1] + v[lo + 1:hi + 1, 1:-1, 1:-1] - f[lo:hi, 1:-1, 1:-1] * h2) / 6.0
+    blk = v[lo:hi, 1:-1, 1:-1]
+    blk[mask] = s[mask]
+
+
+def residual_plane(v, f, z):
+    n = v.shape[1]
+    r = np.zeros((n, n))
+    if z < 1 or z > n - 2:
+        return r
+    h2 = (1.0 / (n - 1)) ** 2
+    c = v[z, 1:-1, 1:-1]
+    r[1:-1, 1:-1] = f[z, 1:-1, 1:-1] - (v[z, 1:-1, :-2] - 2 * c + v[z, 1:-1, 2:]) / h2 \
+        - (v[z, :-2, 1:-1] - 2 * c + v[z, 2:, 1:-1]) / h2 - (v[z - 1, 1:-1, 1:-1] - 2 * c + v[z + 1, 1:-1, 1:-1]) / h2
+    return r
+
+
+def residual_restrict(v, f, cf, cv, clo, chi):
+    cn = cf.shape[1]
+    w1 = np.array([0.25, 0.5, 0.25])
+    for cz in range(clo, chi):
+        cv[cz] = 0.0
+        cf[cz] = 0.0
+        if cz == 0 or cz == cn - 1:
+            continue
+        acc = np.zeros((cn - 2, cn - 2))
+        for dz in (-1, 0, 1):
+            r = residual_plane(v, f, 2 * cz + dz)
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    acc += w1[dz + 1] * w1[dy + 1] * w1[dx + 1] * r[2 + dy:2 * cn - 2 + dy:2, 2 + dx:2 * cn - 2 + dx:2]
+        cf[cz, 1:-1, 1:-1] = acc
+
+
+def interpolate_add(v, cv, lo, hi):
+    n = v.shape[1]
+    for z in range(lo, hi):
+        cz = z // 2
+        pz = cv[cz] if z % 2 == 0 else 0.5 * (cv[cz] + cv[cz + 1])
+        py = np.empty((n, pz.shape[1]))
+        py[0::2] = pz
+        py[1::2] = 0.5 * (pz[:-1] + pz[1:])
+        e = np.empty((n, n))
+        e[:, 0::2] = py
+        e[:, 1::2] = 0.5 * (py[:, :-1] + py[:, 1:])
+        v[z, 1:-1, 1:-1] += e[1:-1, 1:-1]
+
+
+# ---- the driver's schedule ---------------------------------------------------------------------------
+
+class Level:
+    def __init__(self, n, plan):
+        self.n = n
+        self.dist = plan["dist"]
+        self.z0, self.nzl = plan["z0"], plan["nzl"]
+        self.a, self.b = plan["z0"] + plan["own_lo"], plan["z0"] + plan["own_hi"]  # owned global planes
+        self.v = np.full((n, n, n), np.nan)
+        self.f = np.full((n, n, n), np.nan)
+
+    def interior(self):
+        return max(self.a, 1), min(self.b, self.n - 1)
+
+
+def exchange(L, arr, rank, world, depth_up, down, colour=None):
+    """colour is ignored (whole planes travel): a superset of what the engine sends."""
+    if not L.dist:
+        return
+    reqs = []
+    if rank + 1 < world:
+        if depth_up:
+            reqs.append(dist.isend(torch.from_numpy(arr[L.b - depth_up:L.b].copy()), rank + 1))
+        if down:
+            up_ghost = torch.empty((1, L.n, L.n), dtype=torch.float64)
+            reqs.append(dist.irecv(up_ghost, rank + 1))
+    if rank > 0:
+        if down:
+            reqs.append(dist.isend(torch.from_numpy(arr[L.a:L.a + 1].copy()), rank - 1))
+        if depth_up:
+            lo_ghost = torch.empty((depth_up, L.n, L.n), dtype=torch.float64)
+            reqs.append(dist.irecv(lo_ghost, rank - 1))
+    for r in reqs:
+        r.wait()
+    if rank + 1 < world and down:
+        arr[L.b:L.b + 1] = up_ghost.numpy()
+    if rank > 0 and depth_up:
+        arr[L.a - depth_up:L.a] = lo_ghost.numpy()
+
+
+def relax(L, rank, world, nu):
+    lo, hi = L.interior()
+    for _ in range(nu):
+        for colour in (0, 1):
+            relax_colour(L.v, L.f, colour, lo, hi)
+            exchange(L, L.v, rank, world, 1, 1, colour)
+
+
+def vcycle(levels, l, rank, world):
+    L = levels[l]
+    relax(L, rank, world, NU)
+    if l + 1 < len(levels):
+        C = levels[l + 1]
+        exchange(L, L.v, rank, world, 2, 0)                       # plane a-2 for the fused residual+restrict
+        if C.dist or not L.dist:
+            clo, chi = C.a, C.b
+        else:                                                     # first agglomerated level: planes under my slab
+            clo, chi = L.a // 2, (L.b // 2 if rank < world - 1 else C.n)
+        residual_restrict(L.v, L.f, C.f, C.v, clo, chi)
+        if L.dist:
+            C.v[max(C.z0, 0):C.z0 + C.nzl] = 0.0                  # coarse v = 0 wherever this rank stores it
+        if C.dist:
+            exchange(C, C.f, rank, world, 2, 1)
+        elif L.dist:                                              # all-gather of the equal shares + top plane from the last rank
+            m = (C.n - 1) // world
+            parts = [torch.empty((m, C.n, C.n), dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(parts, torch.from_numpy(C.f[rank * m:(rank + 1) * m].copy()))
+            for r, p in enumerate(parts):
+                C.f[r * m:(r + 1) * m] = p.numpy()
+            top = torch.from_numpy(C.f[C.n - 1:C.n].copy())
+            dist.broadcast(top, world - 1)
+            C.f[C.n - 1] = top.numpy()[0]
+        vcycle(levels, l + 1, rank, world)
+        lo, hi = L.interior()
+        interpolate_add(L.v, C.v, lo, hi)
+        exchange(L, L.v, rank, world, 1, 1)
+    relax(L, rank, world, NU)
+
+
+def problem(n):
+    x = np.linspace(0.0, 1.0, n)
+    f = -3 * np.pi ** 2 * np.sin(np.pi * x)[:, None, None] * np.sin(np.pi * x)[None, :, None] * np.sin(np.pi * x)[None, None, :]
+    return np.zeros((n, n, n)), f
+
+
+def worker(rank, world, port, plans, out_queue):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    levels = [Level(n, plans[(n, rank)]) for n in sizes(N)]
+    v0, f0 = problem(N)
+    L0 = levels[0]
+    sl = slice(L0.z0, L0.z0 + L0.nzl)
+    L0.v[sl], L0.f[sl] = v0[sl], f0[sl]
+    for _ in range(CYCLES):
+        vcycle(levels, 0, rank, world)
+    out_queue.put((rank, L0.a, L0.b, L0.v[L0.a:L0.b].copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_slab_schedule_world2_gloo(mg):
+    world = 2
+    plans = {(n, r): mg.MultiGrid3D.plan_level(n, world, r) for n in sizes(N) for r in range(world)}
+    assert plans[(65, 0)]["dist"] == 1 and plans[(33, 0)]["dist"] == 0
+    # sequential reference: the same stand-in kernels on the whole grid in one process
+    one = {(n, 0): mg.MultiGrid3D.plan_level(n, 1, 0) for n in sizes(N)}
+    ref_levels = [Level(n, one[(n, 0)]) for n in sizes(N)]
+    ref_levels[0].v, ref_levels[0].f = problem(N)
+    for L in ref_levels[1:]:
+        L.v[...] = 0.0
+        L.f[...] = 0.0
+    for _ in range(CYCLES):
+        vcycle(ref_levels, 0, 0, 1)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=worker, args=(r, world, port, plans, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    covered = 0
+    for rank, a, b, v in got:
+        assert not np.isnan(v).any(), "a NaN reached the owned planes of rank %d: a ghost plane was missing" % rank
+        assert np.array_equal(v, ref_levels[0].v[a:b]), "rank %d differs from the sequential run" % rank
+        covered += b - a
+    assert covered == N
+    r = ref_levels[0]
+    assert np.isfinite(r.v).all() and np.abs(r.v).max() > 0.1  # the cycles did something (solution ~ sin sin sin)
