@@ -12,7 +12,7 @@
  * grid is cut into z-slabs.  Rank g of P owns the global planes [g*m, (g+1)*m), m = (n-1)/P, the last
  * rank also the Dirichlet plane n-1.  A slab stores 2 ghost planes below (the fused residual+restrict
  * needs v two planes under its first coarse plane) and 1 above.  A level is slab-distributed while
- * m >= 8 and n >= 65; coarser levels are agglomerated: every rank holds them whole (one all-gather of the
+ * m >= 8 and n >= 257; coarser levels are agglomerated: every rank holds them whole (one all-gather of the
  * restricted right-hand side on the way down, nothing on the way up) and smooths them redundantly.
  * RB Gauss-Seidel only couples opposite colours, so exchanging the just-updated colour's boundary
  * plane after every half-sweep reproduces the sequential red-then-black order exactly: the P-GPU result
@@ -70,6 +70,9 @@ struct mg3d_s {
     int smoother, sweeps_per_pass;
     double range[6];
     cudaStream_t stream;
+    cudaStream_t cstream;       /* side stream: halo exchange of the boundary planes overlapping the interior sweep */
+    cudaEvent_t ev_fork, ev_join;
+    int overlap;
     mg_comm* comm;
     mg_p2p p2p;
     mg_level3d* lv;
@@ -142,7 +145,12 @@ int mg3d_plan_level(int n, int nranks, int rank, int out5[5])
 {
     if (!out5 || n < 3 || nranks < 1 || rank < 0 || rank >= nranks) return mg_fail(MG_ERR_ARG, "bad plan arguments");
     const int m = (n - 1) / nranks;
-    const int dist = nranks > 1 && (n - 1) % nranks == 0 && m >= 8 && n >= 65;
+    /* distribute while a slab keeps >= 8 planes and the level is big enough for the halo latency to pay off:
+       at 8 GPUs the 129^3 and 65^3 levels cost 0.3 ms per cycle each when distributed (11 latency-bound
+       exchanges) against 0.1 ms when every GPU smooths them whole (profiles/r1_scaling.md) */
+    const char* env = getenv("MG_B200_DIST_MIN_N");
+    const int min_n = env ? atoi(env) : 257;
+    const int dist = nranks > 1 && (n - 1) % nranks == 0 && m >= 8 && n >= min_n;
     if (!dist) {
         out5[0] = 0; out5[1] = 0; out5[2] = n; out5[3] = 0; out5[4] = n;
         return MG_OK;
@@ -183,7 +191,7 @@ static char* plane_ptr(const mg3d_t* mg, const mg_level3d* L, void* field, int c
  *   down: my bottom owned plane (if `down` != 0) -> the upper ghost of rank-1
  * colour_mask: bit 0 = colour-0 array, bit 1 = colour-1 array.
  * ---------------------------------------------------------------------------------------------- */
-static int exchange_p2p(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int down)
+static int exchange_p2p(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int down, cudaStream_t xs)
 {
     mg_level3d* L = &mg->lv[level];
     mg_p2p* q = &mg->p2p;
@@ -217,44 +225,49 @@ static int exchange_p2p(mg3d_t* mg, int level, void* field, int colour_mask, int
     if (send_up) raise[1] = q->peer_flags[1] + 0;    /* its "from below" word */
     if (send_down) raise[0] = q->peer_flags[0] + 32; /* its "from above" word */
     const int recv_below = r > 0 && depth_up > 0, recv_above = r + 1 < P && down;
-    PROF_BEGIN(mg, level, MG_OP_OTHER);
-    MG_LAUNCH(mg->launches, mgk_halo_exchange(mg->stream, src, dst, bytes, raise, recv_below, recv_above, q->flags));
-    PROF_END(mg);
+    if (xs == mg->stream) PROF_BEGIN(mg, level, MG_OP_OTHER);
+    MG_LAUNCH(mg->launches, mgk_halo_exchange(xs, src, dst, bytes, raise, recv_below, recv_above, q->flags));
+    if (xs == mg->stream) PROF_END(mg);
     return MG_OK;
 }
 
-static int exchange(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int down)
+static int exchange_on(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int down, cudaStream_t xs)
 {
     mg_level3d* L = &mg->lv[level];
     if (!L->dist) return MG_OK;
-    if (mg->p2p.enabled) return exchange_p2p(mg, level, field, colour_mask, depth_up, down);
+    if (mg->p2p.enabled) return exchange_p2p(mg, level, field, colour_mask, depth_up, down, xs);
     const size_t pe = (size_t)L->g.plane; /* elements per colour plane */
     const int r = mg->rank, P = mg->nranks;
     int st;
-    PROF_BEGIN(mg, level, MG_OP_OTHER);
+    if (xs == mg->stream) PROF_BEGIN(mg, level, MG_OP_OTHER);
     if ((st = mg_comm_group_start(mg->comm))) return st;
     for (int col = 0; col < 2; col++) {
         if (!(colour_mask & (1 << col))) continue;
         if (r + 1 < P) {
             if (depth_up > 0) {
-                st = mg_comm_send(mg->comm, plane_ptr(mg, L, field, col, L->own_hi - depth_up), pe * depth_up, mg->dtype, r + 1, mg->stream);
+                st = mg_comm_send(mg->comm, plane_ptr(mg, L, field, col, L->own_hi - depth_up), pe * depth_up, mg->dtype, r + 1, xs);
                 mg->halo_bytes += (long long)(pe * depth_up * mg_esize(mg->dtype));
             }
-            if (!st && down) st = mg_comm_recv(mg->comm, plane_ptr(mg, L, field, col, L->own_hi), pe, mg->dtype, r + 1, mg->stream);
+            if (!st && down) st = mg_comm_recv(mg->comm, plane_ptr(mg, L, field, col, L->own_hi), pe, mg->dtype, r + 1, xs);
         }
         if (!st && r > 0) {
             if (down) {
-                st = mg_comm_send(mg->comm, plane_ptr(mg, L, field, col, L->own_lo), pe, mg->dtype, r - 1, mg->stream);
+                st = mg_comm_send(mg->comm, plane_ptr(mg, L, field, col, L->own_lo), pe, mg->dtype, r - 1, xs);
                 mg->halo_bytes += (long long)(pe * mg_esize(mg->dtype));
             }
             if (!st && depth_up > 0)
-                st = mg_comm_recv(mg->comm, plane_ptr(mg, L, field, col, L->own_lo - depth_up), pe * depth_up, mg->dtype, r - 1, mg->stream);
+                st = mg_comm_recv(mg->comm, plane_ptr(mg, L, field, col, L->own_lo - depth_up), pe * depth_up, mg->dtype, r - 1, xs);
         }
         if (st) break;
     }
     int st2 = mg_comm_group_end(mg->comm);
-    PROF_END(mg);
+    if (xs == mg->stream) PROF_END(mg);
     return st ? st : st2;
+}
+
+static int exchange(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int down)
+{
+    return exchange_on(mg, level, field, colour_mask, depth_up, down, mg->stream);
 }
 
 /* first agglomerated level below a distributed one: every rank computed the coarse planes under its own
@@ -408,7 +421,9 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
     if (nranks < 1 || rank < 0 || rank >= nranks) return mg_fail(MG_ERR_ARG, "bad rank %d of %d", rank, nranks);
     if (nranks > 1) {
         if ((nranks & (nranks - 1)) != 0) return mg_fail(MG_ERR_ARG, "the number of GPUs must be a power of two (got %d)", nranks);
-        if ((n - 1) / nranks < 8 || n < 65) return mg_fail(MG_ERR_ARG, "grid %d^3 is too small for %d z-slabs (needs >= 8 planes per GPU and n >= 65)", n, nranks);
+        int plan[5];
+        mg3d_plan_level(n, nranks, rank, plan);
+        if (!plan[0]) return mg_fail(MG_ERR_ARG, "grid %d^3 is too small for %d z-slabs (needs >= 8 planes per GPU and n >= 257, or MG_B200_DIST_MIN_N)", n, nranks);
         if (!uid) return mg_fail(MG_ERR_ARG, "multi-GPU handles need the NCCL unique id");
     }
     int st = mg_require_device();
@@ -462,6 +477,14 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
         return code;
     }
     if (nranks > 1) {
+        if (cudaStreamCreateWithFlags(&mg->cstream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&mg->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&mg->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            int code = mg_fail(MG_ERR_CUDA, "side stream setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+            mg3d_destroy(mg);
+            return code;
+        }
+        mg->overlap = getenv("MG_B200_NO_OVERLAP") ? 0 : 1;
         st = mg_comm_create(&mg->comm, rank, nranks, uid);
         if (!st && !(getenv("MG_B200_HALO") && !strcmp(getenv("MG_B200_HALO"), "nccl"))) st = p2p_setup(mg, total);
         if (st) { mg3d_destroy(mg); return st; }
@@ -510,6 +533,9 @@ int mg3d_destroy(mg3d_t* mg)
         if (mg->graphs[i].used && mg->graphs[i].exec) cudaGraphExecDestroy(mg->graphs[i].exec);
     p2p_teardown(mg);
     if (mg->comm) mg_comm_destroy(mg->comm);
+    if (mg->cstream) { cudaStreamSynchronize(mg->cstream); cudaStreamDestroy(mg->cstream); }
+    if (mg->ev_fork) cudaEventDestroy(mg->ev_fork);
+    if (mg->ev_join) cudaEventDestroy(mg->ev_join);
     if (mg->stream) cudaStreamDestroy(mg->stream);
     if (mg->arena) cudaFree(mg->arena);
     if (mg->d_scratch) cudaFree(mg->d_scratch);
@@ -687,6 +713,16 @@ static void interior_range(const mg_level3d* L, int* lo, int* hi)
 
 /* Relax: ncycles x (red half-sweep, black half-sweep), N3/MultiGrid3D.cpp:489-567.  On a distributed
    level the boundary planes of the colour just updated go to the neighbours after every half-sweep. */
+static int relax_launch(mg3d_t* mg, mg_level3d* L, int colour, int lo, int hi, int use_tma)
+{
+    if (hi <= lo) return MG_OK;
+    if (use_tma)
+        MG_LAUNCH(mg->launches, mgk3d_relax_colour_tma(mg->stream, mg->dtype, L->tmap_v[colour ^ 1], L->v, L->f, L->g, L->c, colour, lo, hi));
+    else
+        MG_LAUNCH(mg->launches, mgk3d_relax_colour(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, colour, lo, hi));
+    return MG_OK;
+}
+
 static int relax_level(mg3d_t* mg, int level, int ncycles)
 {
     mg_level3d* L = &mg->lv[level];
@@ -694,14 +730,26 @@ static int relax_level(mg3d_t* mg, int level, int ncycles)
     interior_range(L, &lo, &hi);
     if (ncycles <= 0) return MG_OK;
     const int use_tma = L->has_tma && mg->smoother != MG_SMOOTHER_COLOUR;
+    /* distributed level: the two boundary planes of the slab are swept first, their halo exchange then runs on
+       the side stream while the interior planes are swept; the next half-sweep waits for both */
+    const int overlap = L->dist && mg->overlap && !mg->prof.enabled && hi - lo >= 4;
     for (int k = 0; k < ncycles; k++)
         for (int colour = 0; colour < 2; colour++) {
+            if (overlap) {
+                if ((st = relax_launch(mg, L, colour, lo, lo + 1, 0))) return st;
+                if ((st = relax_launch(mg, L, colour, hi - 1, hi, 0))) return st;
+                MG_CUDA(cudaEventRecord(mg->ev_fork, mg->stream));
+                MG_CUDA(cudaStreamWaitEvent(mg->cstream, mg->ev_fork, 0));
+                if ((st = exchange_on(mg, level, L->v, 1 << colour, 1, 1, mg->cstream))) return st;
+                MG_CUDA(cudaEventRecord(mg->ev_join, mg->cstream));
+                if ((st = relax_launch(mg, L, colour, lo + 1, hi - 1, use_tma))) return st;
+                MG_CUDA(cudaStreamWaitEvent(mg->stream, mg->ev_join, 0));
+                continue;
+            }
             PROF_BEGIN(mg, level, MG_OP_RELAX);
-            if (use_tma)
-                MG_LAUNCH(mg->launches, mgk3d_relax_colour_tma(mg->stream, mg->dtype, L->tmap_v[colour ^ 1], L->v, L->f, L->g, L->c, colour, lo, hi));
-            else
-                MG_LAUNCH(mg->launches, mgk3d_relax_colour(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, colour, lo, hi));
+            st = relax_launch(mg, L, colour, lo, hi, use_tma);
             PROF_END(mg);
+            if (st) return st;
             if ((st = exchange(mg, level, L->v, 1 << colour, 1, 1))) return st;
         }
     return MG_OK;

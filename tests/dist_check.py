@@ -37,8 +37,14 @@ def main():
     def same(a, b):
         return a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
 
-    sizes = [129, 257] if world <= 4 else [257]
-    for n in sizes:
+    # default plan (levels n >= 257 distributed) at 513^3, and a deep-nesting plan (threshold lowered to 65) at 129/257
+    runs = [(513, None)] + ([(129, "65"), (257, "65")] if world <= 4 else [(257, "65")])
+    sizes = [r[0] for r in runs]
+    for n, min_n in runs:
+        if min_n is None:
+            os.environ.pop("MG_B200_DIST_MIN_N", None)
+        else:
+            os.environ["MG_B200_DIST_MIN_N"] = min_n
         for dtype in (np.float64, np.float32):
             for corrected in (True, False):
                 mode = mg.MG_CORRECTED if corrected else mg.MG_REF_COMPAT

@@ -193,8 +193,9 @@ def free_port():
         return s.getsockname()[1]
 
 
-def test_slab_schedule_world2_gloo(mg):
+def test_slab_schedule_world2_gloo(mg, monkeypatch):
     world = 2
+    monkeypatch.setenv("MG_B200_DIST_MIN_N", "65")  # distribute the small test grid too (default threshold: n >= 257)
     plans = {(n, r): mg.MultiGrid3D.plan_level(n, world, r) for n in sizes(N) for r in range(world)}
     assert plans[(65, 0)]["dist"] == 1 and plans[(33, 0)]["dist"] == 0
     # sequential reference: the same stand-in kernels on the whole grid in one process

@@ -4,7 +4,7 @@ threshold."""
 import pytest
 
 
-@pytest.mark.parametrize("n,P", [(1025, 2), (1025, 4), (1025, 8), (2049, 8), (257, 2), (129, 8), (65, 8)])
+@pytest.mark.parametrize("n,P", [(1025, 2), (1025, 4), (1025, 8), (2049, 8), (513, 2), (257, 8), (129, 8), (65, 8)])
 def test_slabs_tile_and_nest(mg, n, P):
     plan = mg.MultiGrid3D.plan_level
     levels = []
@@ -21,7 +21,7 @@ def test_slabs_tile_and_nest(mg, n, P):
         assert all(p["dist"] == dist for p in plans)
         if not dist:
             assert all(p["z0"] == 0 and p["nzl"] == nl and p["own_lo"] == 0 and p["own_hi"] == nl for p in plans)
-            assert (nl - 1) // P < 8 or nl < 65
+            assert (nl - 1) // P < 8 or nl < 257
         else:
             owned = []
             for r, p in enumerate(plans):
