@@ -39,8 +39,13 @@ typedef struct {
     int own_lo;     /* local plane range [own_lo, own_hi) owned by this rank */
     int own_hi;
     int has_tma;    /* tensor maps of the two colour arrays of v are valid */
-    unsigned char tmap_v[2][128] __attribute__((aligned(64)));  /* smoother boxes */
-    unsigned char tmap_rr[2][128] __attribute__((aligned(64))); /* residual+restrict boxes */
+    /* temporally blocked smoother: it works out of place, v ping-pongs between two buffers */
+    void* vbuf[2];  /* vbuf[cur] == v; vbuf[1] is NULL when the level has no second buffer */
+    int cur;
+    unsigned char tmap_v[2][2][128] __attribute__((aligned(64)));  /* [buffer][colour] smoother boxes */
+    unsigned char tmap_rr[2][2][128] __attribute__((aligned(64))); /* residual+restrict boxes */
+    unsigned char tmap_fu[2][2][128] __attribute__((aligned(64))); /* fused-smoother boxes of v */
+    unsigned char tmap_ff[2][128] __attribute__((aligned(64)));    /* fused-smoother boxes of f: [colour] */
 } mg_level3d;
 
 /* direct NVLink halo path (mg_halo_p2p.cu): the neighbours' arenas and flag words mapped with CUDA IPC */
@@ -169,6 +174,12 @@ static size_t field_bytes(const mg_level3d* L, int dtype)
 {
     return mg_align256(2 * (size_t)L->g.cstride * mg_esize(dtype));
 }
+
+static int level_uses_tma(int n) { return (n - 1) / 2 >= MGK3D_TMA_IT && !getenv("MG_B200_NO_TMA"); }
+
+/* fields a level keeps in the arena: v, f and, where the fused smoother can run (large, not distributed), a second v */
+static int level_fields_for(int n, int dist) { return (level_uses_tma(n) && !dist) ? 3 : 2; }
+static int level_fields(const mg_level3d* L) { return level_fields_for(L->g.n, L->dist); }
 
 static int check_level(const mg3d_t* mg, int level)
 {
@@ -329,6 +340,7 @@ static int p2p_setup(mg3d_t* mg, size_t arena_bytes)
             const size_t fb = mg_align256(2 * (size_t)q->nb_geom[k][l].cstride * mg_esize(mg->dtype));
             q->nb_off[k][2 * l] = off; off += fb;
             q->nb_off[k][2 * l + 1] = off; off += fb;
+            if (level_fields_for(mg->lv[l].g.n, plan[0]) == 3) off += fb;
         }
     }
     MG_CUDA(cudaMalloc((void**)&q->flags, MG_HALO_FLAG_WORDS * sizeof(unsigned int)));
@@ -454,7 +466,7 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
         L->own_lo = plan[3];
         L->own_hi = plan[4];
         level_coefs(dtype, nl, range, L->h, &L->c);
-        total += 2 * field_bytes(L, dtype);
+        total += (size_t)level_fields(L) * field_bytes(L, dtype);
         nl = (nl - 1) / 2 + 1; /* N3/MultiGrid3D.cpp:40-42 */
     }
     cudaError_t e = cudaMalloc(&mg->arena, total);
@@ -467,6 +479,8 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
         mg_level3d* L = &mg->lv[l];
         L->v = p; p += field_bytes(L, dtype);
         L->f = p; p += field_bytes(L, dtype);
+        L->vbuf[0] = L->v;
+        if (level_fields(L) == 3) { L->vbuf[1] = p; p += field_bytes(L, dtype); }
     }
     if (cudaStreamCreateWithFlags(&mg->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc((void**)&mg->d_scratch, (2 * MGK_NORM_BLOCKS + 2) * sizeof(double)) != cudaSuccess ||
@@ -489,17 +503,23 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
         if (!st && !(getenv("MG_B200_HALO") && !strcmp(getenv("MG_B200_HALO"), "nccl"))) st = p2p_setup(mg, total);
         if (st) { mg3d_destroy(mg); return st; }
     }
-    /* TMA tensor maps of v for the levels large enough to fill the z-marching tiles */
+    /* TMA tensor maps for the levels large enough to fill the z-marching tiles */
     for (int l = 0; l < mg->nlevels; l++) {
         mg_level3d* L = &mg->lv[l];
-        if ((L->g.n - 1) / 2 < MGK3D_TMA_IT || getenv("MG_B200_NO_TMA")) continue;
-        for (int col = 0; col < 2; col++) {
-            st = mg_tma_make_colour_map(L->tmap_v[col], dtype, plane_ptr(mg, L, L->v, col, 0), &L->g,
-                                        MGK3D_TMA_BOX_I(mg_esize(dtype)), MGK3D_TMA_BOX_Y);
-            if (!st) st = mg_tma_make_colour_map(L->tmap_rr[col], dtype, plane_ptr(mg, L, L->v, col, 0), &L->g,
-                                                 MGK3D_RR_BOX_I(mg_esize(dtype)), MGK3D_RR_BOX_Y);
-            if (st) { mg3d_destroy(mg); return st; }
+        if (!level_uses_tma(L->g.n)) continue;
+        const int es = (int)mg_esize(dtype);
+        for (int b = 0; b < 2 && !st; b++) {
+            if (!L->vbuf[b]) continue;
+            for (int col = 0; col < 2 && !st; col++) {
+                char* base = plane_ptr(mg, L, L->vbuf[b], col, 0);
+                st = mg_tma_make_colour_map(L->tmap_v[b][col], dtype, base, &L->g, MGK3D_TMA_BOX_I(es), MGK3D_TMA_BOX_Y);
+                if (!st) st = mg_tma_make_colour_map(L->tmap_rr[b][col], dtype, base, &L->g, MGK3D_RR_BOX_I(es), MGK3D_RR_BOX_Y);
+                if (!st) st = mg_tma_make_colour_map(L->tmap_fu[b][col], dtype, base, &L->g, MGK3D_FU_BOX_I(es), MGK3D_FU_BOX_Y);
+            }
         }
+        for (int col = 0; col < 2 && !st; col++)
+            st = mg_tma_make_colour_map(L->tmap_ff[col], dtype, plane_ptr(mg, L, L->f, col, 0), &L->g, MGK3D_FU_BOX_I(es), MGK3D_FU_BOX_Y);
+        if (st) { mg3d_destroy(mg); return st; }
         L->has_tma = 1;
     }
     /* pad elements of the layout are never used by a kernel, but keep them defined */
@@ -717,7 +737,7 @@ static int relax_launch(mg3d_t* mg, mg_level3d* L, int colour, int lo, int hi, i
 {
     if (hi <= lo) return MG_OK;
     if (use_tma)
-        MG_LAUNCH(mg->launches, mgk3d_relax_colour_tma(mg->stream, mg->dtype, L->tmap_v[colour ^ 1], L->v, L->f, L->g, L->c, colour, lo, hi));
+        MG_LAUNCH(mg->launches, mgk3d_relax_colour_tma(mg->stream, mg->dtype, L->tmap_v[L->cur][colour ^ 1], L->v, L->f, L->g, L->c, colour, lo, hi));
     else
         MG_LAUNCH(mg->launches, mgk3d_relax_colour(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, colour, lo, hi));
     return MG_OK;
@@ -730,6 +750,19 @@ static int relax_level(mg3d_t* mg, int level, int ncycles)
     interior_range(L, &lo, &hi);
     if (ncycles <= 0) return MG_OK;
     const int use_tma = L->has_tma && mg->smoother != MG_SMOOTHER_COLOUR;
+    /* temporally blocked smoother: two full sweeps per pass over HBM, out of place (v ping-pongs) */
+    if (mg->smoother == MG_SMOOTHER_FUSED && L->has_tma && L->vbuf[1] && !L->dist) {
+        while (ncycles >= 2) {
+            const void* maps4[4] = {L->tmap_fu[L->cur][0], L->tmap_fu[L->cur][1], L->tmap_ff[0], L->tmap_ff[1]};
+            PROF_BEGIN(mg, level, MG_OP_RELAX);
+            MG_LAUNCH(mg->launches, mgk3d_relax_fused2(mg->stream, mg->dtype, maps4, L->vbuf[L->cur ^ 1], L->g, L->c));
+            PROF_END(mg);
+            L->cur ^= 1;
+            L->v = L->vbuf[L->cur];
+            ncycles -= 2;
+        }
+        if (ncycles <= 0) return MG_OK;
+    }
     /* distributed level: the two boundary planes of the slab are swept first, their halo exchange then runs on
        the side stream while the interior planes are swept; the next half-sweep waits for both */
     const int overlap = L->dist && mg->overlap && !mg->prof.enabled && hi - lo >= 4;
@@ -844,7 +877,7 @@ static int residual_restrict_level(mg3d_t* mg, int fine_level)
     if (F->dist && (st = exchange(mg, fine_level, F->v, 3, MG_GHOST_LO, 0))) return st;
     PROF_BEGIN(mg, fine_level, MG_OP_RESIDUAL_RESTRICT);
     if (F->has_tma && mg->smoother != MG_SMOOTHER_COLOUR)
-        MG_LAUNCH(mg->launches, mgk3d_residual_restrict_tma(mg->stream, mg->dtype, F->tmap_rr[0], F->tmap_rr[1], F->f, F->g, F->c,
+        MG_LAUNCH(mg->launches, mgk3d_residual_restrict_tma(mg->stream, mg->dtype, F->tmap_rr[F->cur][0], F->tmap_rr[F->cur][1], F->f, F->g, F->c,
                                                             mg->mode == MG_CORRECTED, C->f, C->v, C->g, lo, hi));
     else
         MG_LAUNCH(mg->launches, mgk3d_residual_restrict(mg->stream, mg->dtype, F->v, F->f, F->g, F->c, mg->mode == MG_CORRECTED,
@@ -943,9 +976,16 @@ int mg3d_vcycle(mg3d_t* mg, int level, int v1, int v2)
     if (!g->exec) {
         const long long l0 = mg->launches, h0 = mg->halo_bytes;
         cudaGraph_t graph = NULL;
+        int cur0[MG_PROF_MAX_LEVELS];
+        for (int l = 0; l < mg->nlevels; l++) cur0[l] = mg->lv[l].cur;
         MG_CUDA(cudaStreamBeginCapture(mg->stream, cudaStreamCaptureModeThreadLocal));
         st = vcycle_rec(mg, level, v1, v2);
         cudaError_t e = cudaStreamEndCapture(mg->stream, &graph);
+        for (int l = 0; l < mg->nlevels; l++) { /* nothing ran during the capture: undo the host-side buffer flips */
+            if (mg->lv[l].cur != cur0[l] && e == cudaSuccess) e = cudaErrorNotSupported; /* a replay must end on the buffers it started from */
+            mg->lv[l].cur = cur0[l];
+            mg->lv[l].v = mg->lv[l].vbuf[cur0[l]];
+        }
         g->launches = mg->launches - l0;
         g->halo_bytes = mg->halo_bytes - h0;
         mg->launches = l0;

@@ -57,6 +57,14 @@ int mgk3d_relax_colour(cudaStream_t s, int dtype, void* v, const void* f, mg_geo
 #define MGK3D_TMA_BOX_Y (MGK3D_TMA_YT + 2)
 int mgk3d_relax_colour_tma(cudaStream_t s, int dtype, const void* tmap_other, void* v, const void* f, mg_geom3d g,
                            mg_coef3d c, int colour, int zl_lo, int zl_hi);
+/* temporally blocked smoother (mg3d_smooth_fused.cu): TWO full RB sweeps in one pass over HBM, out of place.
+   maps4 = tensor maps of {v_in colour 0, v_in colour 1, f colour 0, f colour 1} with box
+   (MGK3D_FU_BOX_I(esize), MGK3D_FU_BOX_Y, 1); every plane of v_out is written */
+#define MGK3D_FU_TI 32
+#define MGK3D_FU_TY 16
+#define MGK3D_FU_BOX_I(esize) (MGK3D_FU_TI + 2 * (16 / (int)(esize)))
+#define MGK3D_FU_BOX_Y (MGK3D_FU_TY + 8)
+int mgk3d_relax_fused2(cudaStream_t s, int dtype, const void* const maps4[4], void* v_out, mg_geom3d g, mg_coef3d c);
 /* r = CalculateResidual, full array incl. zero boundary, local planes [zl_lo, zl_hi) */
 int mgk3d_residual(cudaStream_t s, int dtype, const void* v, const void* f, void* r, mg_geom3d g, mg_coef3d c,
                    int corrected, int zl_lo, int zl_hi);
