@@ -218,9 +218,13 @@ static int relax_level(mg2d_t* mg, int level, int ncycles)
     mg_level2d* L = &mg->lv[level];
     if (ncycles <= 0) return MG_OK;
     PROF_BEGIN(mg, level, MG_OP_RELAX);
-    for (int k = 0; k < ncycles; k++)
-        for (int colour = 0; colour < 2; colour++)
-            MG_LAUNCH(mg->launches, mgk2d_relax_colour(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, colour));
+    if (L->g.n <= MGK2D_SMALL_N) { /* the whole level fits in one CTA: every sweep in a single launch */
+        MG_LAUNCH(mg->launches, mgk2d_relax_small(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, ncycles));
+    } else {
+        for (int k = 0; k < ncycles; k++)
+            for (int colour = 0; colour < 2; colour++)
+                MG_LAUNCH(mg->launches, mgk2d_relax_colour(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, colour));
+    }
     PROF_END(mg);
     return MG_OK;
 }

@@ -124,6 +124,9 @@ typedef struct {
 } mg_coef2d;
 
 int mgk2d_relax_colour(cudaStream_t s, int dtype, void* v, const void* f, mg_geom2d g, mg_coef2d c, int colour);
+/* levels with n <= MGK2D_SMALL_N: all `ncycles` RB sweeps in ONE launch of one CTA, v in shared memory */
+#define MGK2D_SMALL_N 65
+int mgk2d_relax_small(cudaStream_t s, int dtype, void* v, const void* f, mg_geom2d g, mg_coef2d c, int ncycles);
 int mgk2d_residual(cudaStream_t s, int dtype, const void* v, const void* f, void* r, mg_geom2d g, mg_coef2d c);
 int mgk2d_residual_norm(cudaStream_t s, int dtype, const void* v, const void* f, mg_geom2d g, mg_coef2d c,
                         double* scratch, double* out2);
