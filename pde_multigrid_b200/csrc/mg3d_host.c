@@ -938,7 +938,24 @@ int mg3d_set_to_value(mg3d_t* mg, int level, int field, double value, int modify
    are one kernel; Interpolate + ApplyCorrection are one kernel: no residual / error grid exists. */
 static int vcycle_rec(mg3d_t* mg, int level, int v1, int v2)
 {
-    int st = relax_level(mg, level, v1);
+    int st;
+    mg_level3d* L0 = &mg->lv[level];
+    if (L0->g.n <= MGK3D_TAIL_N && !L0->dist && mg->nlevels - level <= MGK3D_TAIL_MAX_LEVELS && !getenv("MG_B200_NO_TAIL")) {
+        /* the coarse tail: the whole recursion from here down in one launch of one CTA */
+        mg_geom3d g[MGK3D_TAIL_MAX_LEVELS];
+        mg_coef3d c[MGK3D_TAIL_MAX_LEVELS];
+        void *v[MGK3D_TAIL_MAX_LEVELS], *f[MGK3D_TAIL_MAX_LEVELS];
+        const int nlev = mg->nlevels - level;
+        for (int l = 0; l < nlev; l++) {
+            g[l] = mg->lv[level + l].g; c[l] = mg->lv[level + l].c;
+            v[l] = mg->lv[level + l].v; f[l] = mg->lv[level + l].f;
+        }
+        PROF_BEGIN(mg, level, MG_OP_RELAX);
+        MG_LAUNCH(mg->launches, mgk3d_vcycle_tail(mg->stream, mg->dtype, nlev, g, c, v, f, v1, v2, mg->mode == MG_CORRECTED));
+        PROF_END(mg);
+        return MG_OK;
+    }
+    st = relax_level(mg, level, v1);
     if (st) return st;
     if (level != mg->nlevels - 1) {
         if ((st = residual_restrict_level(mg, level))) return st;

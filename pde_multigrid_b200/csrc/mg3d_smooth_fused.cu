@@ -30,7 +30,8 @@ constexpr int TY = MGK3D_FU_TY;  // rows per tile
 constexpr int HALO = 4;          // grid points of halo: four half-sweeps
 constexpr int BH = TY + 2 * HALO;
 constexpr int NS = 8;            // ring slots: planes p+2, p+1 (in flight), p ... p-5
-constexpr int NT = 1024;
+constexpr int NT = 1024;           // 32 warps, SPT = 1 slot per thread and stage (measured: 512x2 15.0 ms, 1024x1 14.0 ms, 256x4 17.6 ms per pass at 1025^3)
+constexpr int SPT = ((TY + 6) * (TI + 4) + NT - 1) / NT;  // slots per thread and stage (4)
 
 template <typename T> struct FBox {
     static constexpr int A = 16 / sizeof(T);   // half-indices loaded left of the tile (16-byte aligned TMA start)
@@ -92,75 +93,100 @@ k_relax_fused2(const __grid_constant__ FusedMaps maps, T* __restrict__ v_out, mg
     // half-indices, at most one slot per thread.  Everything that does not depend on the plane is decoded once:
     // the shared-memory offset of the slot and three flag bits (bit 0: parity of colour+y; bit 1 / bit 2: the point
     // with x parity 0 / 1 exists, is interior and lies inside the stage's region).
-    int cc[4];
-    unsigned fl[4];
+    int cc[4][SPT];
+    unsigned fl[4][SPT];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int e = 3 - k, rows = TY + 2 * e, col = k & 1;
-        cc[k] = 0;
-        fl[k] = 0;
-        if (tid < rows * (TI + 4)) {
-            const int rr = tid / (TI + 4), ii = tid - rr * (TI + 4) - 2;  // ii = half-index - i0 in [-2, TI+2)
-            const int r = HALO - e + rr, y = y0 - HALO + r;
-            cc[k] = r * W + ii + A;
-            const bool yok = y >= 1 && y <= n - 2;
-            unsigned f = (unsigned)((col + y + g.z0) & 1);
 #pragma unroll
-            for (int par = 0; par < 2; par++) {
-                const int x = X0 + 2 * ii + par;
-                if (yok && x >= 1 && x <= n - 2 && x >= X0 - e && x < X0 + 2 * TI + e) f |= 2u << par;
+        for (int s = 0; s < SPT; s++) {
+            const int idx = tid + s * NT;
+            cc[k][s] = 0;
+            fl[k][s] = 0;
+            if (idx < rows * (TI + 4)) {
+                const int rr = idx / (TI + 4), ii = idx - rr * (TI + 4) - 2;  // ii = half-index - i0 in [-2, TI+2)
+                const int r = HALO - e + rr, y = y0 - HALO + r;
+                cc[k][s] = r * W + ii + A;
+                const bool yok = y >= 1 && y <= n - 2;
+                unsigned f = (unsigned)((col + y + g.z0) & 1);
+#pragma unroll
+                for (int par = 0; par < 2; par++) {
+                    const int x = X0 + 2 * ii + par;
+                    if (yok && x >= 1 && x <= n - 2 && x >= X0 - e && x < X0 + 2 * TI + e) f |= 2u << par;
+                }
+                fl[k][s] = f;
             }
-            fl[k] = f;
         }
     }
-    // operands of stage k on plane q (nothing is loaded when the slot is inactive on this plane)
-    struct Ops { T O, E, N, S, D, U, f; bool on; int par; };
-    auto fetch = [&](int k, int q) {
-        Ops o;
-        const int e = 3 - k, col = k & 1;
-        o.par = (int)((fl[k] ^ (unsigned)q) & 1u);
-        o.on = (fl[k] & (2u << o.par)) && q >= 1 && q <= n - 2 && q >= zs - e && q < ze + e;
-        o.O = o.E = o.N = o.S = o.D = o.U = o.f = T(0);
-        if (o.on) {
-            const T* oth = slot_of(q) + (col ^ 1) * SUBS + cc[k];
-            o.O = oth[o.par - 1]; o.E = oth[o.par]; o.N = oth[-W]; o.S = oth[W];
-            o.D = slot_of(q - 1)[(col ^ 1) * SUBS + cc[k]];
-            o.U = slot_of(q + 1)[(col ^ 1) * SUBS + cc[k]];
-            o.f = slot_of(q)[(2 + col) * SUBS + cc[k]];
+    // the thread's elements of the output tile (2 colours x TY rows x TI half-indices), decoded once
+    constexpr int OPT = 2 * TY * TI / NT;
+    static_assert(OPT * NT == 2 * TY * TI, "output tile must divide evenly");
+    int st_src[OPT];
+    long long st_dst[OPT];
+    bool st_ok[OPT];
+#pragma unroll
+    for (int s = 0; s < OPT; s++) {
+        const int idx = tid + s * NT;
+        const int col = idx / (TY * TI), rem = idx - col * (TY * TI);
+        const int rr = rem / TI, ii = rem - rr * TI;
+        st_src[s] = col * SUBS + (HALO + rr) * W + ii + A;
+        st_dst[s] = (long long)col * g.cstride + (long long)(y0 + rr) * g.hp + (i0 + ii);
+        st_ok[s] = y0 + rr < n && i0 + ii <= (n - 1) / 2;
+    }
+
+    // One stage: colour `col` of plane p-d for the thread's SPT slots: all loads first, then SPT independent
+    // arithmetic chains, then the stores.  sb[] holds the ring offsets of planes p..p-6.
+    auto stage = [&](int k, int d, int col, bool plane_on, const int (&sb)[7], unsigned zpar) {
+        if (!plane_on) return;
+        T O[SPT], E[SPT], N[SPT], S[SPT], D[SPT], U[SPT], F[SPT];
+        bool on[SPT];
+#pragma unroll
+        for (int s = 0; s < SPT; s++) {
+            const int par = (int)((fl[k][s] ^ zpar ^ (unsigned)d) & 1u);
+            on[s] = (fl[k][s] & (2u << par)) != 0;
+            O[s] = E[s] = N[s] = S[s] = D[s] = U[s] = F[s] = T(0);
+            if (on[s]) {
+                const T* oth = ring + sb[d] + (col ^ 1) * SUBS + cc[k][s];
+                O[s] = oth[par - 1]; E[s] = oth[par]; N[s] = oth[-W]; S[s] = oth[W];
+                D[s] = ring[sb[d + 1] + (col ^ 1) * SUBS + cc[k][s]];
+                U[s] = ring[sb[d - 1] + (col ^ 1) * SUBS + cc[k][s]];
+                F[s] = ring[sb[d] + (2 + col) * SUBS + cc[k][s]];
+            }
         }
-        return o;
-    };
-    auto commit = [&](int k, int q, const Ops& o) {
-        if (o.on) slot_of(q)[(k & 1) * SUBS + cc[k]] = relax_point<T, FAST>(o.O, o.E, o.N, o.S, o.D, o.U, o.f, c);
+#pragma unroll
+        for (int s = 0; s < SPT; s++)
+            if (on[s]) ring[sb[d] + col * SUBS + cc[k][s]] = relax_point<T, FAST>(O[s], E[s], N[s], S[s], D[s], U[s], F[s], c);
     };
 
+    // STATUS (round 1, 1025^3 fp64): 14.0 ms per pass against 8.4 ms for the four colour launches it replaces.  It
+    // moves the bytes it should (ncu: 24.6 GB read + 8.7 GB written per pass, 33 GB against 51.6 GB) but it is
+    // latency-bound: the 8-slot ring fills the SM's shared memory (221 KB), so there is one CTA per SM and only
+    // the planes p+1, p+2 can be in flight; a TMA plane (4 boxes of 24 rows x 288 B) issued at the end of iteration p
+    // has to land within one iteration.  Neither fewer instructions (hoisted ring offsets) nor more ILP (4 slots per
+    // thread) changed the time.  Next steps: per-colour rings with different phases to free slots for a deeper
+    // prefetch, or 2-CTA clusters sharing halos through DSMEM.  Kept opt-in (MG_SMOOTHER_FUSED); bit-identical.
     for (int p = pb; p <= plast + 1; p++) {
         if (p <= plast) mbar_wait(&bars[(p - pb) & (NS - 1)], ((p - pb) / NS) & 1);
-        {   // phase A: red of sweep 1 on plane p-1, red of sweep 2 on plane p-4 (both sets of loads issued first)
-            const Ops a = fetch(0, p - 1), b = fetch(2, p - 4);
-            commit(0, p - 1, a);
-            commit(2, p - 4, b);
-        }
+        int sb[7];  // element offset of the slot of plane p-j
+#pragma unroll
+        for (int j = 0; j < 7; j++) sb[j] = ((p - j - pb) & (NS - 1)) * SLOT;
+        const unsigned zpar = (unsigned)p & 1u;
+        auto plane_on = [&](int q, int e) { return q >= 1 && q <= n - 2 && q >= zs - e && q < ze + e; };
+        // phase A: red of sweep 1 on plane p-1, red of sweep 2 on plane p-4
+        stage(0, 1, 0, plane_on(p - 1, 3), sb, zpar);
+        stage(2, 4, 0, plane_on(p - 4, 1), sb, zpar);
         __syncthreads();
-        {   // phase B: black of sweep 1 on plane p-2, black of sweep 2 on plane p-5 (reads red of plane p-6)
-            const Ops a = fetch(1, p - 2), b = fetch(3, p - 5);
-            commit(1, p - 2, a);
-            commit(3, p - 5, b);
-        }
+        // phase B: black of sweep 1 on plane p-2, black of sweep 2 on plane p-5 (reads red of plane p-6)
+        stage(1, 2, 1, plane_on(p - 2, 2), sb, zpar);
+        stage(3, 5, 1, plane_on(p - 5, 0), sb, zpar);
         __syncthreads();
         if (tid == 0 && p + 2 <= plast) issue(p + 2);  // into the slot of plane p-6, which nobody reads any more
         // plane p-5 is final: write the tile (both colours) to the output field
         const int ps = p - 5;
         if (ps >= zs && ps < ze) {
-            const T* src = slot_of(ps);
-            for (int idx = tid; idx < 2 * TY * TI; idx += NT) {
-                const int col = idx / (TY * TI), rem = idx - col * (TY * TI);
-                const int rr = rem / TI, ii = rem - rr * TI;
-                const int y = y0 + rr, i = i0 + ii;
-                if (y < n && i <= (n - 1) / 2)
-                    __stcs(v_out + (long long)col * g.cstride + (long long)ps * g.plane + (long long)y * g.hp + i,
-                           src[col * SUBS + (HALO + rr) * W + ii + A]);
-            }
+#pragma unroll
+            for (int s = 0; s < OPT; s++)
+                if (st_ok[s]) __stcs(v_out + st_dst[s] + (long long)ps * g.plane, ring[sb[5] + st_src[s]]);
         }
     }
 }

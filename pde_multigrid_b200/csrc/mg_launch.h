@@ -65,6 +65,12 @@ int mgk3d_relax_colour_tma(cudaStream_t s, int dtype, const void* tmap_other, vo
 #define MGK3D_FU_BOX_I(esize) (MGK3D_FU_TI + 2 * (16 / (int)(esize)))
 #define MGK3D_FU_BOX_Y (MGK3D_FU_TY + 8)
 int mgk3d_relax_fused2(cudaStream_t s, int dtype, const void* const maps4[4], void* v_out, mg_geom3d g, mg_coef3d c);
+/* the coarse tail of a V-cycle in one launch (mg3d_tail.cu): V(v1,v2) on the sub-hierarchy g[0..nlev-1], g[0].n <=
+   MGK3D_TAIL_N, every level resident in one CTA's shared memory */
+#define MGK3D_TAIL_N 17
+#define MGK3D_TAIL_MAX_LEVELS 4
+int mgk3d_vcycle_tail(cudaStream_t s, int dtype, int nlev, const mg_geom3d* g, const mg_coef3d* c, void* const* v,
+                      void* const* f, int v1, int v2, int corrected);
 /* r = CalculateResidual, full array incl. zero boundary, local planes [zl_lo, zl_hi) */
 int mgk3d_residual(cudaStream_t s, int dtype, const void* v, const void* f, void* r, mg_geom3d g, mg_coef3d c,
                    int corrected, int zl_lo, int zl_hi);
