@@ -42,7 +42,7 @@ template <typename T> struct VBox {
 };
 
 template <typename T, bool FAST>
-__global__ void __launch_bounds__(NT, 3)
+__global__ void __launch_bounds__(NT, 2)
 k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid_constant__ CUtensorMap map_c1,
                         const T* __restrict__ f, mg_geom3d gf, Coef3<T> c, int corrected, T* __restrict__ cf,
                         T* __restrict__ cv, mg_geom3d gc, int czl_lo, int czl_hi, int zchunk)
