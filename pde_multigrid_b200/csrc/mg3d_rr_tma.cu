@@ -34,7 +34,6 @@ constexpr int HPR = CXT + 1;            // half-indices per residual row and col
 constexpr int RING = 4;   // v planes: z-1, z, z+1 live + one in flight
 constexpr int RRING = 3;  // residual planes: 2k-1, 2k, 2k+1
 constexpr int NT = 256;
-constexpr int NPT = (2 * RROWS * HPR + NT - 1) / NT;  // residual points per thread and plane (5)
 
 template <typename T> struct VBox {
     static constexpr int A = 16 / sizeof(T);                      // TMA inner-coordinate alignment in elements
@@ -88,78 +87,137 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
     if (tid == 0)
         for (int p = pbase; p <= min(pbase + RING - 1, zf1 + 1); p++) issue(p);
 
-    // The thread's residual points: slot s = tid + j*NT -> (colour, row ly, half-index hl), fixed over planes.
-    // Everything that does not depend on z is folded into a few per-point constants here so that the
-    // z loop is loads, arithmetic and one store per point (the first version of this kernel spent
-    // ~128 instructions per fine point, mostly on index arithmetic, and was issue-bound: profiles/).
-    int own_off[NPT], oth_off[NPT], r_even[NPT], flags[NPT];  // flags: 1 parity of (colour+y), 2 valid for q=0, 4 valid for q=1
-    const T* fptr[NPT];
-#pragma unroll
-    for (int j = 0; j < NPT; j++) {
-        // a warp covers half-indices 0..31 of ONE (colour, row): every shared-memory access of the residual
-        // stage is unit-stride and conflict-free; the 33rd half-index of the 34 (colour, row) pairs is a
-        // small tail handled by 34 threads of the last pass
-        const int s = tid + j * NT;
-        const bool main_part = s < 2 * RROWS * 32;
-        const bool active = s < 2 * RROWS * HPR;
-        const int cr = main_part ? (s >> 5) : (active ? s - 2 * RROWS * 32 : 0);
-        const int hl = main_part ? (s & 31) : (active ? 32 : 0);
-        const int col = cr / RROWS;
-        const int ly = cr - col * RROWS;
-        const int y = fy0 + ly, hi = cx0 - 1 + hl;
-        const int cc = (ly + 1) * W + hl + A - 1;
-        own_off[j] = col * VSUB_STRIDE + cc;
-        oth_off[j] = (col ^ 1) * VSUB_STRIDE + cc;
-        r_even[j] = (ly * 2) * RCOLS + hl;  // q = 1: even lx = 2*hl -> parity array 0; q = 0: odd lx -> array 1 at hl-1
-        const bool yv = active && y >= 1 && y <= n - 2;
-        const int x0 = 2 * hi;  // q = 0; q = 1 -> x0 + 1
-        flags[j] = ((col + y) & 1) | ((yv && hl >= 1 && x0 >= 1 && x0 <= n - 2) ? 2 : 0) | ((yv && x0 + 1 >= 1 && x0 + 1 <= n - 2) ? 4 : 0) |
-                   (active ? 8 : 0) | ((active && hl >= 1) ? 16 : 0);
-        const bool fok = active && y >= 0 && y < n && hi >= 0 && hi < gf.hp;
-        fptr[j] = fok ? f + (long long)col * gf.cstride + (long long)y * gf.hp + hi : nullptr;
-    }
-    const int nzl = gf.nzl;
-    auto load_f = [&](int z, T (&dst)[NPT]) {
-        const int zl = z - gf.z0;
-        const bool zok = zl >= 0 && zl < nzl;
-        const long long po = (long long)zl * gf.plane;
-#pragma unroll
-        for (int j = 0; j < NPT; j++) dst[j] = (zok && fptr[j]) ? __ldg(fptr[j] + po) : T(0);
+    // Thread -> residual points, fixed over the planes.  Warp w, lane l.  Four regular passes: colour
+    // (p >> 1), row ly = w + 8*(p & 1), half-index hl = l -- every index of these is ONE per-thread base plus
+    // a compile-time constant, so the z loop is loads, arithmetic and one store per point.  (The first
+    // versions kept per-point offset/flag arrays; under the register cap the compiler re-derived them from
+    // threadIdx every plane: 72 instructions per residual point, 4.8e9 warp instructions per launch at
+    // 1025^3, issue-bound at 0.53 of the HBM roofline -- profiles/r1_residual_restrict_tma_ncu_full.txt.)
+    // The fifth pass is the irregular rest: row 16 of both colours (warps 0, 1) and the 33rd half-index
+    // of the 34 (colour, row) pairs (warps 2, 3), with per-thread precomputed indices.
+    static_assert(CXT == 32 && CYT == 8 && NT == 256, "thread mapping of the residual stage");
+    const int w = tid >> 5, lane = tid & 31;
+    const int hp = gf.hp;
+    const int T0 = w * W + lane;           // + (8*jj + 1)*W + A - 1 -> element of a v colour sub-tile
+    const int T1 = w * 2 * RCOLS + lane;   // + jj*16*RCOLS          -> element of a residual plane
+    const int T2 = ((2 * w + 1) * 2) * RCOLS + lane;  // restriction stage: centre row of coarse point (lane, w)
+    // Per-thread predicates live in one opaque bit mask (otherwise ptxas re-derives each of them from
+    // blockIdx/threadIdx in every plane).  x parity q of a colour-c point in row y of plane z: (c + y + z) & 1.
+    enum : unsigned {
+        F_A0 = 1u << 0, F_A1 = 1u << 1,  // rows w:     residual defined for the q = 0 / q = 1 point
+        F_B0 = 1u << 2, F_B1 = 1u << 3,  // rows w + 8
+        F_FA = 1u << 4, F_FB = 1u << 5,  // f needed in rows w / w + 8
+        F_L1 = 1u << 6,                  // lane >= 1: the q = 0 point belongs to the residual tile
+        F_PW = 1u << 7,                  // y parity of rows w, w + 8 (fy0 is odd)
+        F_TACT = 1u << 8, F_TST0 = 1u << 9, F_T0 = 1u << 10, F_T1 = 1u << 11, F_TF = 1u << 12, F_TP = 1u << 13,  // fifth pass
+        F_CIN = 1u << 14, F_CBND = 1u << 15, F_CP = 1u << 16  // coarse point: inside the grid, on its boundary, (cx+cy)&1
     };
-    T fnext[NPT];
+    unsigned fl = 0;
+    int t_own, t_oth, t_r;
+    const T *fp, *tfp;  // f of this thread's first point / fifth-pass point in plane zf0 (advanced by one plane per iteration)
+    long long c_base;
+    {
+        const int x0 = 2 * (cx0 - 1 + lane);  // x of a q = 0 point; q = 1: x0 + 1
+        const bool xv0 = lane >= 1 && x0 >= 1 && x0 <= n - 2;
+        const bool xv1 = x0 + 1 >= 1 && x0 + 1 <= n - 2;
+        const int ya = fy0 + w, yb = ya + 8;
+        const bool yva = ya >= 1 && ya <= n - 2, yvb = yb >= 1 && yb <= n - 2;
+        fl |= (yva && xv0 ? F_A0 : 0) | (yva && xv1 ? F_A1 : 0) | (yvb && xv0 ? F_B0 : 0) | (yvb && xv1 ? F_B1 : 0);
+        fl |= (yva && (xv0 || xv1) ? F_FA : 0) | (yvb && (xv0 || xv1) ? F_FB : 0);  // f is only read where a residual is evaluated
+        fl |= (lane >= 1 ? F_L1 : 0) | (((w + 1) & 1) ? F_PW : 0);
+        const long long zoff = (long long)(zf0 - gf.z0) * gf.plane;
+        fp = f + (zoff + (long long)ya * hp + (cx0 - 1 + lane));
+
+        // fifth pass: row 16 of both colours (warps 0, 1) and the 33rd half-index of the 34 (colour, row)
+        // pairs (warps 2, 3)
+        int col, ly, hl;
+        bool act;
+        if (w < 2) { col = w; ly = RROWS - 1; hl = lane; act = true; }
+        else {
+            const int u = (w - 2) * 32 + lane;
+            act = w < 4 && u < 2 * RROWS;
+            col = (act && u >= RROWS) ? 1 : 0;
+            ly = act ? u - col * RROWS : 0;
+            hl = 32;
+        }
+        const int y = fy0 + ly, hi = cx0 - 1 + hl, cc = (ly + 1) * W + hl + A - 1;
+        t_own = col * VSUB_STRIDE + cc;
+        t_oth = (col ^ 1) * VSUB_STRIDE + cc;
+        t_r = ly * 2 * RCOLS + hl;
+        const bool tyv = act && y >= 1 && y <= n - 2;
+        const bool tx0 = hl >= 1 && 2 * hi >= 1 && 2 * hi <= n - 2, tx1 = 2 * hi + 1 >= 1 && 2 * hi + 1 <= n - 2;
+        fl |= (act ? F_TACT : 0) | (act && hl >= 1 ? F_TST0 : 0) | (tyv && tx0 ? F_T0 : 0) | (tyv && tx1 ? F_T1 : 0) |
+              (tyv && (tx0 || tx1) ? F_TF : 0) | (((col + y) & 1) ? F_TP : 0);
+        tfp = f + (zoff + (long long)col * gf.cstride + (long long)y * hp + hi);
+
+        // the thread's coarse point (restriction stage): cx = cx0 + lane, cy = cy0 + w
+        const int cx = cx0 + lane, cy = cy0 + w;
+        fl |= (cx < gc.n && cy < gc.n ? F_CIN : 0) | ((cx == 0 || cx == gc.n - 1 || cy == 0 || cy == gc.n - 1) ? F_CBND : 0) |
+              (((cx + cy) & 1) ? F_CP : 0);
+        c_base = (long long)cy * gc.hp + (cx >> 1);
+    }
+    asm volatile("" : "+r"(fl));
+    const long long f_b = 8ll * hp, f_c1 = gf.cstride;  // f offsets of rows w + 8 / of colour 1, in elements
+
+    const int nzl = gf.nzl;
+    // f of plane z (fp/tfp point into that plane) -> dst; addresses of points without a residual are never formed
+    auto load_f = [&](int z, T (&dst)[5]) {
+        const int zl = z - gf.z0;
+        const unsigned m = (zl >= 0 && zl < nzl) ? fl : 0u;
+        dst[0] = (m & F_FA) ? __ldg(fp) : T(0);
+        dst[1] = (m & F_FB) ? __ldg(fp + f_b) : T(0);
+        dst[2] = (m & F_FA) ? __ldg(fp + f_c1) : T(0);
+        dst[3] = (m & F_FB) ? __ldg(fp + f_c1 + f_b) : T(0);
+        dst[4] = (m & F_TF) ? __ldg(tfp) : T(0);
+    };
+    T fnext[5];
     load_f(zf0, fnext);
 
+    unsigned rs = 0;  // residual-ring slot of plane z: (z - zf0) % RRING
     for (int z = zf0; z <= zf1; z++) {
-        const int k = z - pbase;  // ring index of v plane z
-        T fcur[NPT];
+        const unsigned k = (unsigned)(z - pbase);  // ring index of v plane z (>= 1)
+        T fcur[5];
 #pragma unroll
-        for (int j = 0; j < NPT; j++) fcur[j] = fnext[j];
+        for (int j = 0; j < 5; j++) fcur[j] = fnext[j];
+        fp += gf.plane;
+        tfp += gf.plane;
         if (z < zf1) load_f(z + 1, fnext);
         if (z == zf0) {
-            mbar_wait(&bars[(k - 1) % RING], ((k - 1) / RING) & 1);
-            mbar_wait(&bars[k % RING], (k / RING) & 1);
+            mbar_wait(&bars[(k - 1) & (RING - 1)], ((k - 1) / RING) & 1);
+            mbar_wait(&bars[k & (RING - 1)], (k / RING) & 1);
         }
-        mbar_wait(&bars[(k + 1) % RING], ((k + 1) / RING) & 1);
+        mbar_wait(&bars[(k + 1) & (RING - 1)], ((k + 1) / RING) & 1);
 
-        // ---- residual of fine plane z -> rring[(z - zf0) % RRING] ----
-        const T* vD = vring + (size_t)((k - 1) % RING) * VSLOT;
-        const T* vC = vring + (size_t)(k % RING) * VSLOT;
-        const T* vU = vring + (size_t)((k + 1) % RING) * VSLOT;
-        T* rz = rring + (size_t)((z - zf0) % RRING) * RSLOT;
-        const bool zin = z >= 1 && z <= n - 2;
-        const int zpar = z & 1;
+        // ---- residual of fine plane z -> rring[rs] ----
+        const T* vD = vring + ((k - 1) & (RING - 1)) * VSLOT + T0;
+        const T* vC = vring + (k & (RING - 1)) * VSLOT + T0;
+        const T* vU = vring + ((k + 1) & (RING - 1)) * VSLOT + T0;
+        T* rz = rring + rs * RSLOT;
+        const unsigned vm = (z >= 1 && z <= n - 2) ? fl : 0u;  // residual is zero on the boundary planes
+        const int q0 = ((fl / F_PW) ^ z) & 1;  // x parity of the colour-0 points of this thread's rows in this plane
 #pragma unroll
-        for (int j = 0; j < NPT; j++) {
-            const int q = (flags[j] ^ zpar) & 1;  // x parity of this colour in this row of this plane
-            const bool store = q ? (flags[j] & 8) : (flags[j] & 16);
-            const bool valid = zin && (flags[j] & (q ? 4 : 2));
+        for (int p = 0; p < 4; p++) {
+            const int col = p >> 1, jj = p & 1;  // compile-time after unrolling
+            const int cp = (8 * jj + 1) * W + A - 1;
+            const int q = q0 ^ col;
+            const T* own = vC + col * VSUB_STRIDE + cp;
+            const T* oc = vC + (col ^ 1) * VSUB_STRIDE + cp;
+            const T* od = vD + (col ^ 1) * VSUB_STRIDE + cp;
+            const T* ou = vU + (col ^ 1) * VSUB_STRIDE + cp;
             T val = T(0);
-            if (valid) {
-                const int o = oth_off[j];
-                val = residual_point<T, FAST>(vC[o - 1 + q], vC[o + q], vC[o - W], vC[o + W], vD[o], vU[o], vC[own_off[j]], fcur[j], c,
-                                              corrected);
+            if (vm & (jj ? (q ? F_B1 : F_B0) : (q ? F_A1 : F_A0)))
+                val = residual_point<T, FAST>(oc[q - 1], oc[q], oc[-W], oc[W], od[0], ou[0], own[0], fcur[p], c, corrected);
+            if (q || (fl & F_L1)) rz[T1 + jj * 16 * RCOLS + (q ? 0 : RCOLS - 1)] = val;
+        }
+        if (w < 4) {  // warp-uniform: warps 4..7 have no fifth-pass point
+            const int q = ((fl / F_TP) ^ z) & 1;
+            T val = T(0);
+            if (vm & (q ? F_T1 : F_T0)) {
+                const T *c0 = vC - T0, *d0 = vD - T0, *u0 = vU - T0;
+                const int o = t_oth;
+                val = residual_point<T, FAST>(c0[o - 1 + q], c0[o + q], c0[o - W], c0[o + W], d0[o], u0[o], c0[t_own], fcur[4], c, corrected);
             }
-            if (store) rz[r_even[j] + (q ? 0 : RCOLS - 1)] = val;
+            if (fl & (q ? F_TACT : F_TST0)) rz[t_r + (q ? 0 : RCOLS - 1)] = val;
         }
         __syncthreads();  // residual plane z complete; v slot of plane z-1 free
         if (tid == 0 && z + RING - 1 <= zf1 + 1) issue(z + RING - 1);
@@ -167,26 +225,25 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
         // ---- after an odd fine plane z = 2*cz+1: restrict planes z-2, z-1, z -> coarse plane cz ----
         if ((z & 1) && z > zf0) {
             const int cz = (z - 1) >> 1, czl = cz - gc.z0;
-            const int tx = tid & (CXT - 1), ty = tid / CXT;
-            const int cx = cx0 + tx, cy = cy0 + ty;
-            if (cx < gc.n && cy < gc.n) {
+            if (fl & F_CIN) {
                 T out = T(0);  // boundary: injection of the zero boundary residual (N3/MultiGrid3D.cpp:113-119, :705)
-                if (!(cx == 0 || cx == gc.n - 1 || cy == 0 || cy == gc.n - 1 || cz == 0 || cz == gc.n - 1)) {
-                    const T* rm = rring + (size_t)((z - 2 - zf0) % RRING) * RSLOT + ((2 * ty + 1) * 2) * RCOLS + tx;
-                    const T* rc = rring + (size_t)((z - 1 - zf0) % RRING) * RSLOT + ((2 * ty + 1) * 2) * RCOLS + tx;
-                    const T* rp = rz + ((2 * ty + 1) * 2) * RCOLS + tx;
-                    // centre lx = 2*tx+1 (odd: parity array 1 at tx); dx = -1/+1 -> even lx: array 0 at tx / tx+1
+                if (!((fl & F_CBND) || cz == 0 || cz == gc.n - 1)) {
+                    const T* rm = rring + (rs == 2 ? 0u : rs + 1) * RSLOT + T2;  // plane z-2
+                    const T* rc = rring + (rs == 0 ? 2u : rs - 1) * RSLOT + T2;  // plane z-1
+                    const T* rp = rz + T2;
+                    // centre lx = 2*lane+1 (odd: parity array 1 at lane); dx = -1/+1 -> even lx: array 0 at lane / lane+1
                     out = restrict_point<T>([&](int dx, int dy, int dz) {
                         const T* pl = dz < 0 ? rm : (dz == 0 ? rc : rp);
                         return dx == 0 ? pl[dy * 2 * RCOLS + RCOLS] : pl[dy * 2 * RCOLS + (dx > 0)];
                     });
                 }
-                const long long ci = off3(gc, cx, cy, czl);
+                const long long ci = ((((fl / F_CP) ^ cz) & 1) ? gc.cstride : 0ll) + (long long)czl * gc.plane + c_base;
                 cf[ci] = out;
                 cv[ci] = T(0);  // setToValue(coarse->h_v, 0, true), N3/MultiGrid3D.cpp:634
             }
             __syncthreads();  // the 3-slot residual ring: plane z-2 is overwritten by the next iteration
         }
+        rs = rs == RRING - 1 ? 0 : rs + 1;
     }
 }
 
