@@ -50,6 +50,8 @@ extern "C" {
 #define MG_SMOOTHER_AUTO 0
 #define MG_SMOOTHER_COLOUR 1 /* one colour per launch, in place */
 #define MG_SMOOTHER_FUSED 2  /* red+black (and several sweeps) per HBM pass, z-marching smem tiles */
+#define MG_SMOOTHER_JACOBI 3 /* weighted Jacobi (3D only): v += omega*(GS(v_old) - v_old), all points from old values.
+                                Not in the reference (it only has red-black Gauss-Seidel): no parity contract with it */
 
 /* operator classes of the per-operator device timers (mg?d_profile_read) */
 #define MG_OP_RELAX 0             /* Relax */
@@ -88,6 +90,9 @@ int mg3d_num_levels(const mg3d_t* mg);         /* MultiGrid3D::numGrids */
 int mg3d_level_size(const mg3d_t* mg, int level); /* grids3D[level]->sizeX */
 double mg3d_level_h(const mg3d_t* mg, int level); /* grids3D[level]->h_x */
 int mg3d_set_smoother(mg3d_t* mg, int smoother, int sweeps_per_pass);
+/* relaxation weight of MG_SMOOTHER_JACOBI, 0 < omega <= 1 (default 6/7, the optimal smoothing weight of the 7-point
+   Laplacian); rounded to the handle's dtype */
+int mg3d_set_jacobi_weight(mg3d_t* mg, double omega);
 int mg3d_sync(mg3d_t* mg);
 void* mg3d_stream(mg3d_t* mg); /* cudaStream_t the handle enqueues on (for event timing) */
 long long mg3d_kernel_launches(const mg3d_t* mg); /* kernels launched by this handle so far */

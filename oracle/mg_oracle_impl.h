@@ -88,6 +88,42 @@ void FN(orc3d_relax)(REAL* v, const REAL* f, int n, const double* range, int ncy
                     }
 }
 
+/* Weighted Jacobi.  NOT in the reference (its only smoother is the red-black Gauss-Seidel above; SURVEY.md 8f
+   rank 4): this function is the definition the engine's MG_SMOOTHER_JACOBI is tested against -- parity with the
+   reference is unpinned by construction.  One sweep: every interior point, from the OLD values of its six
+   neighbours,  v_new = v_old + omega * (gs - v_old)  with gs the expression of N3/MultiGrid3D.cpp:532. */
+void FN(orc3d_relax_jacobi)(REAL* v, const REAL* f, int n, const double* range, double omega_d, int ncycles)
+{
+    REAL h_x, h_y, h_z;
+    FN(orc3d_h)(n, range, &h_x, &h_y, &h_z);
+    REAL h_x2 = h_x * h_x, h_y2 = h_y * h_y, h_z2 = h_z * h_z;
+    const REAL omega = (REAL)omega_d;
+    size_t tot = (size_t)n * n * n;
+    REAL* nv = (REAL*)malloc(tot * sizeof(REAL));
+    for (int k = 0; k < ncycles; k++) {
+        for (size_t i = 0; i < tot; i++) nv[i] = v[i];
+        for (int pz = 1; pz < n - 1; pz++)
+            for (int py = 1; py < n - 1; py++)
+                for (int px = 1; px < n - 1; px++) {
+                    REAL O = v[IDX3(px - 1, py, pz)];
+                    REAL E = v[IDX3(px + 1, py, pz)];
+                    REAL N = v[IDX3(px, py - 1, pz)];
+                    REAL S = v[IDX3(px, py + 1, pz)];
+                    REAL D = v[IDX3(px, py, pz - 1)];
+                    REAL U = v[IDX3(px, py, pz + 1)];
+                    size_t idx = IDX3(px, py, pz);
+                    REAL gs = (O * (h_y2 * h_z2) + E * (h_y2 * h_z2) + N * (h_x2 * h_z2) + S * (h_x2 * h_z2) +
+                               D * (h_x2 * h_y2) + U * (h_x2 * h_y2) - f[idx] * h_x2 * h_y2 * h_z2) /
+                              (2 * (h_y2 * h_z2 + h_x2 * h_z2 + h_x2 * h_y2));
+                    REAL d = gs - v[idx];
+                    REAL u = omega * d;
+                    nv[idx] = v[idx] + u;
+                }
+        for (size_t i = 0; i < tot; i++) v[i] = nv[i];
+    }
+    free(nv);
+}
+
 /* MultiGrid3D::CalculateResidual, N3/MultiGrid3D.cpp:678-730; corrected != 0 flips the two
    wrong signs of :723 */
 void FN(orc3d_residual)(const REAL* v, const REAL* f, REAL* r, int n, const double* range, int corrected)
@@ -219,6 +255,28 @@ void FN(orc3d_vcycle)(REAL** v, REAL** f, int n0, int nlevels, const double* ran
         free(tmp);
     }
     FN(orc3d_relax)(v[level], f[level], n, range, v2);
+}
+
+/* the same V-cycle with the weighted-Jacobi smoother in place of Relax (no reference counterpart, see above) */
+void FN(orc3d_vcycle_jacobi)(REAL** v, REAL** f, int n0, int nlevels, const double* range, int level, int v1, int v2,
+                             int corrected, double omega)
+{
+    int n = n0;
+    for (int l = 0; l < level; l++) n = (n - 1) / 2 + 1;
+    FN(orc3d_relax_jacobi)(v[level], f[level], n, range, omega, v1);
+    if (level != nlevels - 1) {
+        size_t tot = (size_t)n * n * n;
+        REAL* tmp = (REAL*)malloc(tot * sizeof(REAL));
+        FN(orc3d_residual)(v[level], f[level], tmp, n, range, corrected);
+        FN(orc3d_restrict)(tmp, n, f[level + 1]);
+        int cn = (n - 1) / 2 + 1;
+        FN(orc3d_set)(v[level + 1], cn, 0.0, 1);
+        FN(orc3d_vcycle_jacobi)(v, f, n0, nlevels, range, level + 1, v1, v2, corrected, omega);
+        FN(orc3d_interpolate)(tmp, n, v[level + 1]);
+        FN(orc3d_apply_correction)(v[level], tmp, n);
+        free(tmp);
+    }
+    FN(orc3d_relax_jacobi)(v[level], f[level], n, range, omega, v2);
 }
 
 /* MultiGrid3D::FullMultiGridVCycle, N3/MultiGrid3D.cpp:569-585 */

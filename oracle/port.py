@@ -116,6 +116,16 @@ class PortMG:
     def relax(self, l, ncycles):
         self._call("relax", self._p(self._v[l]), self._p(self._f[l]), self.sizes[l], *self._extra(), int(ncycles))
 
+    def relax_jacobi(self, l, ncycles, omega=6.0 / 7.0):
+        """Weighted Jacobi (3D only; not in the reference -- the port is its definition)."""
+        assert self.dim == 3
+        self._call("relax_jacobi", self._p(self._v[l]), self._p(self._f[l]), self.sizes[l], self.range, float(omega), int(ncycles))
+
+    def vcycle_jacobi(self, l, v1, v2, omega=6.0 / 7.0):
+        assert self.dim == 3
+        self._call("vcycle_jacobi", self._pp(self._v), self._pp(self._f), self.sizes[0], self.num_levels, self.range, int(l),
+                   int(v1), int(v2), self.corrected, float(omega))
+
     def residual(self, l=0):
         out = np.empty(self.shape(l), dtype=self.np_dtype)
         if self.dim == 2:

@@ -42,6 +42,7 @@ typedef struct {
     /* temporally blocked smoother: it works out of place, v ping-pongs between two buffers */
     void* vbuf[2];  /* vbuf[cur] == v; vbuf[1] is NULL when the level has no second buffer */
     int cur;
+    void* jscratch; /* weighted Jacobi: one colour array of scratch, allocated on first use */
     unsigned char tmap_v[2][2][128] __attribute__((aligned(64)));  /* [buffer][colour] smoother boxes */
     unsigned char tmap_rr[2][2][128] __attribute__((aligned(64))); /* residual+restrict boxes */
     unsigned char tmap_fu[2][2][128] __attribute__((aligned(64))); /* fused-smoother boxes of v */
@@ -92,6 +93,7 @@ struct mg3d_s {
     mg_prof prof;
     int use_graphs;
     mg_graph_slot graphs[MG_GRAPH_SLOTS];
+    double omega;   /* weight of MG_SMOOTHER_JACOBI */
 };
 
 #define PROF_BEGIN(mg, level, op) mg_prof_begin(&(mg)->prof, (mg)->stream, (level), (op), (mg)->launches)
@@ -246,7 +248,8 @@ static int exchange_on(mg3d_t* mg, int level, void* field, int colour_mask, int 
 {
     mg_level3d* L = &mg->lv[level];
     if (!L->dist) return MG_OK;
-    if (mg->p2p.enabled) return exchange_p2p(mg, level, field, colour_mask, depth_up, down, xs);
+    /* the direct NVLink path addresses the neighbour's v and f inside its arena; anything else (the Jacobi scratch) goes through NCCL */
+    if (mg->p2p.enabled && (field == L->v || field == L->f)) return exchange_p2p(mg, level, field, colour_mask, depth_up, down, xs);
     const size_t pe = (size_t)L->g.plane; /* elements per colour plane */
     const int r = mg->rank, P = mg->nranks;
     int st;
@@ -450,6 +453,7 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
     mg->smoother = MG_SMOOTHER_AUTO;
     mg->sweeps_per_pass = 1;
     mg->use_graphs = getenv("MG_B200_NO_GRAPH") ? 0 : 1;
+    mg->omega = 6.0 / 7.0;
     memcpy(mg->range, range, sizeof mg->range);
     mg->nlevels = mg_num_levels_for(n);
     mg->lv = (mg_level3d*)calloc((size_t)mg->nlevels, sizeof(mg_level3d));
@@ -563,6 +567,8 @@ int mg3d_destroy(mg3d_t* mg)
     if (mg->h_out2) cudaFreeHost(mg->h_out2);
     if (mg->staging) cudaFree(mg->staging);
     mg_prof_free(&mg->prof);
+    for (int l = 0; mg->lv && l < mg->nlevels; l++)
+        if (mg->lv[l].jscratch) cudaFree(mg->lv[l].jscratch);
     free(mg->lv);
     free(mg);
     return MG_OK;
@@ -588,10 +594,23 @@ int mg3d_owned_range(const mg3d_t* mg, int level, int* z_begin, int* z_count)
 int mg3d_set_smoother(mg3d_t* mg, int smoother, int sweeps_per_pass)
 {
     if (!mg) return mg_fail(MG_ERR_ARG, "null handle");
-    if (smoother < MG_SMOOTHER_AUTO || smoother > MG_SMOOTHER_FUSED) return mg_fail(MG_ERR_ARG, "bad smoother %d", smoother);
+    if (smoother < MG_SMOOTHER_AUTO || smoother > MG_SMOOTHER_JACOBI) return mg_fail(MG_ERR_ARG, "bad smoother %d", smoother);
     if (sweeps_per_pass < 1 || sweeps_per_pass > 4) return mg_fail(MG_ERR_ARG, "sweeps_per_pass must be 1..4");
     mg->smoother = smoother;
     mg->sweeps_per_pass = sweeps_per_pass;
+    return MG_OK;
+}
+
+int mg3d_set_jacobi_weight(mg3d_t* mg, double omega)
+{
+    if (!mg) return mg_fail(MG_ERR_ARG, "null handle");
+    if (!(omega > 0.0 && omega <= 1.0)) return mg_fail(MG_ERR_ARG, "Jacobi weight %g outside (0,1]", omega);
+    mg->omega = mg->dtype == MG_F32 ? (double)(float)omega : omega;
+    for (int i = 0; i < MG_GRAPH_SLOTS; i++) /* captured cycles carry the old weight as a kernel argument */
+        if (mg->graphs[i].used && mg->graphs[i].smoother == MG_SMOOTHER_JACOBI) {
+            if (mg->graphs[i].exec) cudaGraphExecDestroy(mg->graphs[i].exec);
+            memset(&mg->graphs[i], 0, sizeof mg->graphs[i]);
+        }
     return MG_OK;
 }
 
@@ -743,12 +762,45 @@ static int relax_launch(mg3d_t* mg, mg_level3d* L, int colour, int lo, int hi, i
     return MG_OK;
 }
 
+/* Weighted Jacobi, ncycles sweeps.  On the colour-split layout a sweep is two launches: the new colour-0 values go
+   to a scratch array (colour 1 still needs the old ones), colour 1 is then updated in place (a point reads only
+   its own old value of that array).  The scratch array IS the colour-0 array of the next sweep, so the roles of
+   scratch and v alternate; an odd number of sweeps ends with one copy back.  4*B*N_l bytes per sweep (RB-GS: 3). */
+static int relax_jacobi_level(mg3d_t* mg, int level, int ncycles)
+{
+    mg_level3d* L = &mg->lv[level];
+    const size_t cbytes = (size_t)L->g.cstride * mg_esize(mg->dtype);
+    int st;
+    if (!L->jscratch) {
+        MG_CUDA(cudaMalloc(&L->jscratch, cbytes));
+        MG_CUDA(cudaMemsetAsync(L->jscratch, 0, cbytes, mg->stream));
+    }
+    char *red = (char*)L->v, *black = red + cbytes, *cur = red;
+    const char *f_red = (const char*)L->f, *f_black = f_red + cbytes;
+    for (int k = 0; k < ncycles; k++) {
+        char* nxt = cur == red ? (char*)L->jscratch : red;
+        PROF_BEGIN(mg, level, MG_OP_RELAX);
+        MG_LAUNCH(mg->launches, mgk3d_jacobi_colour(mg->stream, mg->dtype, nxt, cur, black, f_red, L->g, L->c, mg->omega, 0, L->own_lo, L->own_hi));
+        MG_LAUNCH(mg->launches, mgk3d_jacobi_colour(mg->stream, mg->dtype, black, black, cur, f_black, L->g, L->c, mg->omega, 1, L->own_lo, L->own_hi));
+        PROF_END(mg);
+        cur = nxt;
+        if (L->dist) {
+            /* `cur` as a field pointer with colour mask 1 addresses exactly that colour-0 array */
+            if ((st = exchange(mg, level, cur == red ? L->v : (void*)cur, 1, 1, 1))) return st;
+            if ((st = exchange(mg, level, L->v, 2, 1, 1))) return st;
+        }
+    }
+    if (cur != red) MG_CUDA(cudaMemcpyAsync(red, cur, cbytes, cudaMemcpyDeviceToDevice, mg->stream));
+    return MG_OK;
+}
+
 static int relax_level(mg3d_t* mg, int level, int ncycles)
 {
     mg_level3d* L = &mg->lv[level];
     int lo, hi, st;
     interior_range(L, &lo, &hi);
     if (ncycles <= 0) return MG_OK;
+    if (mg->smoother == MG_SMOOTHER_JACOBI) return relax_jacobi_level(mg, level, ncycles);
     const int use_tma = L->has_tma && mg->smoother != MG_SMOOTHER_COLOUR;
     /* temporally blocked smoother: two full sweeps per pass over HBM, out of place (v ping-pongs) */
     if (mg->smoother == MG_SMOOTHER_FUSED && L->has_tma && L->vbuf[1] && !L->dist) {
@@ -769,8 +821,7 @@ static int relax_level(mg3d_t* mg, int level, int ncycles)
     for (int k = 0; k < ncycles; k++)
         for (int colour = 0; colour < 2; colour++) {
             if (overlap) {
-                if ((st = relax_launch(mg, L, colour, lo, lo + 1, 0))) return st;
-                if ((st = relax_launch(mg, L, colour, hi - 1, hi, 0))) return st;
+                MG_LAUNCH(mg->launches, mgk3d_relax_colour_pair(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, colour, lo, hi - 1));
                 MG_CUDA(cudaEventRecord(mg->ev_fork, mg->stream));
                 MG_CUDA(cudaStreamWaitEvent(mg->cstream, mg->ev_fork, 0));
                 if ((st = exchange_on(mg, level, L->v, 1 << colour, 1, 1, mg->cstream))) return st;
@@ -940,7 +991,8 @@ static int vcycle_rec(mg3d_t* mg, int level, int v1, int v2)
 {
     int st;
     mg_level3d* L0 = &mg->lv[level];
-    if (L0->g.n <= MGK3D_TAIL_N && !L0->dist && mg->nlevels - level <= MGK3D_TAIL_MAX_LEVELS && !getenv("MG_B200_NO_TAIL")) {
+    if (L0->g.n <= MGK3D_TAIL_N && !L0->dist && mg->nlevels - level <= MGK3D_TAIL_MAX_LEVELS && mg->smoother != MG_SMOOTHER_JACOBI &&
+        !getenv("MG_B200_NO_TAIL")) {
         /* the coarse tail: the whole recursion from here down in one launch of one CTA */
         mg_geom3d g[MGK3D_TAIL_MAX_LEVELS];
         mg_coef3d c[MGK3D_TAIL_MAX_LEVELS];

@@ -33,11 +33,11 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool FAST>
 __global__ void __launch_bounds__(256)
-k_relax_colour(T* __restrict__ v, const T* __restrict__ f, mg_geom3d g, Coef3<T> c, int colour, int zl_lo)
+k_relax_colour(T* __restrict__ v, const T* __restrict__ f, mg_geom3d g, Coef3<T> c, int colour, int zl_lo, int zl_step)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
-    const int zl = zl_lo + blockIdx.z;
+    const int zl = zl_lo + blockIdx.z * zl_step;
     if (y > g.n - 2) return;
     const int q = (colour + y + g.z0 + zl) & 1;
     const int x = 2 * i + q;
@@ -46,6 +46,39 @@ k_relax_colour(T* __restrict__ v, const T* __restrict__ f, mg_geom3d g, Coef3<T>
     const T* oth = v + (long long)(colour ^ 1) * g.cstride + idx;
     const long long own = (long long)colour * g.cstride + idx;
     v[own] = relax_point<T, FAST>(oth[q - 1], oth[q], oth[-g.hp], oth[g.hp], oth[-g.plane], oth[g.plane], f[own], c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weighted-Jacobi half of a sweep on ONE colour array: every interior point of `colour` becomes
+//     old + omega * (gs - old),   gs = the reference's Gauss-Seidel expression (N3/MultiGrid3D.cpp:532)
+// evaluated on the OLD values of the six neighbours (all of the other colour).  The reference has no
+// Jacobi smoother: the tests check this against a CPU restatement of the same formula.
+// dst/own/oth/f are colour-array base pointers.  dst may be `own` (in place: a point reads only its own
+// old value of that array) or a scratch array, which then also receives the non-interior points so that
+// it can stand in for the colour array in the next sweep.
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool FAST>
+__global__ void __launch_bounds__(256)
+k_jacobi_colour(T* __restrict__ dst, const T* own, const T* __restrict__ oth, const T* __restrict__ f, mg_geom3d g,
+                Coef3<T> c, T omega, int colour, int zl_lo)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int zl = zl_lo + blockIdx.z, z = g.z0 + zl;
+    if (y > g.n - 1) return;
+    const int q = (colour + y + z) & 1;
+    const int x = 2 * i + q;
+    if (x > g.n - 1) return;
+    const long long idx = (long long)zl * g.plane + (long long)y * g.hp + i;
+    const T old = own[idx];
+    const bool interior = x >= 1 && x <= g.n - 2 && y >= 1 && y <= g.n - 2 && z >= 1 && z <= g.n - 2;
+    T out = old;
+    if (interior) {
+        const T* o = oth + idx;
+        const T gs = relax_point<T, FAST>(o[q - 1], o[q], o[-g.hp], o[g.hp], o[-g.plane], o[g.plane], f[idx], c);
+        out = add(old, mul(omega, sub(gs, old)));
+    }
+    if (interior || dst != own) dst[idx] = out;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -362,13 +395,27 @@ inline void half_row_launch(int cols, int n, int nz, dim3& block, dim3& grid)
 }
 
 template <typename T>
-int relax_colour_t(cudaStream_t s, T* v, const T* f, mg_geom3d g, mg_coef3d c, int colour, int zl_lo, int zl_hi)
+int relax_colour_t(cudaStream_t s, T* v, const T* f, mg_geom3d g, mg_coef3d c, int colour, int zl_lo, int nplanes, int zl_step)
+{
+    if (nplanes <= 0 || g.n < 3) return 0;
+    dim3 block, grid;
+    half_row_launch((g.n - 1) / 2, g.n, nplanes, block, grid);
+    if (c.fast_den) k_relax_colour<T, true><<<grid, block, 0, s>>>(v, f, g, narrow<T>(c), colour, zl_lo, zl_step);
+    else k_relax_colour<T, false><<<grid, block, 0, s>>>(v, f, g, narrow<T>(c), colour, zl_lo, zl_step);
+    return launch_ok();
+}
+
+template <typename T>
+int jacobi_colour_t(cudaStream_t s, T* dst, const T* own, const T* oth, const T* f, mg_geom3d g, mg_coef3d c, double omega, int colour,
+                    int zl_lo, int zl_hi)
 {
     if (zl_hi <= zl_lo || g.n < 3) return 0;
-    dim3 block, grid;
-    half_row_launch((g.n - 1) / 2, g.n, zl_hi - zl_lo, block, grid);
-    if (c.fast_den) k_relax_colour<T, true><<<grid, block, 0, s>>>(v, f, g, narrow<T>(c), colour, zl_lo);
-    else k_relax_colour<T, false><<<grid, block, 0, s>>>(v, f, g, narrow<T>(c), colour, zl_lo);
+    const int cols = (g.n + 1) / 2;
+    int bx = 32;
+    while (bx < 128 && bx < cols) bx <<= 1;
+    dim3 block(bx, 256 / bx, 1), grid((cols + bx - 1) / bx, (g.n + block.y - 1) / block.y, zl_hi - zl_lo);
+    if (c.fast_den) k_jacobi_colour<T, true><<<grid, block, 0, s>>>(dst, own, oth, f, g, narrow<T>(c), (T)omega, colour, zl_lo);
+    else k_jacobi_colour<T, false><<<grid, block, 0, s>>>(dst, own, oth, f, g, narrow<T>(c), (T)omega, colour, zl_lo);
     return launch_ok();
 }
 
@@ -416,8 +463,26 @@ extern "C" {
 int mgk3d_relax_colour(cudaStream_t s, int dtype, void* v, const void* f, mg_geom3d g, mg_coef3d c, int colour,
                        int zl_lo, int zl_hi)
 {
-    return DISPATCH(dtype, relax_colour_t<float>(s, (float*)v, (const float*)f, g, c, colour, zl_lo, zl_hi),
-                    relax_colour_t<double>(s, (double*)v, (const double*)f, g, c, colour, zl_lo, zl_hi));
+    return DISPATCH(dtype, relax_colour_t<float>(s, (float*)v, (const float*)f, g, c, colour, zl_lo, zl_hi - zl_lo, 1),
+                    relax_colour_t<double>(s, (double*)v, (const double*)f, g, c, colour, zl_lo, zl_hi - zl_lo, 1));
+}
+
+/* weighted-Jacobi update of one colour array on local planes [zl_lo, zl_hi): see k_jacobi_colour */
+int mgk3d_jacobi_colour(cudaStream_t s, int dtype, void* dst, const void* own, const void* oth, const void* f, mg_geom3d g,
+                        mg_coef3d c, double omega, int colour, int zl_lo, int zl_hi)
+{
+    return DISPATCH(dtype,
+                    jacobi_colour_t<float>(s, (float*)dst, (const float*)own, (const float*)oth, (const float*)f, g, c, omega, colour, zl_lo, zl_hi),
+                    jacobi_colour_t<double>(s, (double*)dst, (const double*)own, (const double*)oth, (const double*)f, g, c, omega, colour, zl_lo, zl_hi));
+}
+
+/* the same half-sweep on the two planes zl_a and zl_b only (the boundary planes of a slab), one launch */
+int mgk3d_relax_colour_pair(cudaStream_t s, int dtype, void* v, const void* f, mg_geom3d g, mg_coef3d c, int colour,
+                            int zl_a, int zl_b)
+{
+    if (zl_b <= zl_a) return -1;
+    return DISPATCH(dtype, relax_colour_t<float>(s, (float*)v, (const float*)f, g, c, colour, zl_a, 2, zl_b - zl_a),
+                    relax_colour_t<double>(s, (double*)v, (const double*)f, g, c, colour, zl_a, 2, zl_b - zl_a));
 }
 
 int mgk3d_residual(cudaStream_t s, int dtype, const void* v, const void* f, void* r, mg_geom3d g, mg_coef3d c,

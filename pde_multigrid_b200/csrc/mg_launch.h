@@ -49,6 +49,13 @@ typedef struct {
 /* one colour of one RB Gauss-Seidel sweep, in place, on local planes [zl_lo, zl_hi) */
 int mgk3d_relax_colour(cudaStream_t s, int dtype, void* v, const void* f, mg_geom3d g, mg_coef3d c, int colour,
                        int zl_lo, int zl_hi);
+/* weighted Jacobi on one colour array: dst = own + omega*(GS(oth, f) - own) on the interior points of `colour`,
+   local planes [zl_lo, zl_hi); dst == own works in place, otherwise dst also receives the non-interior points */
+int mgk3d_jacobi_colour(cudaStream_t s, int dtype, void* dst, const void* own, const void* oth, const void* f, mg_geom3d g,
+                        mg_coef3d c, double omega, int colour, int zl_lo, int zl_hi);
+/* the same half-sweep on the two planes zl_a < zl_b only (the boundary planes of a slab) */
+int mgk3d_relax_colour_pair(cudaStream_t s, int dtype, void* v, const void* f, mg_geom3d g, mg_coef3d c, int colour,
+                            int zl_a, int zl_b);
 /* same half-sweep with TMA-staged z-marching shared-memory tiles (mg3d_smooth_tma.cu); tmap_other is the
    128-byte CUtensorMap of the OTHER colour's v array built with box (MGK3D_TMA_BOX_I(esize), MGK3D_TMA_BOX_Y, 1) */
 #define MGK3D_TMA_IT 128

@@ -216,6 +216,10 @@ class MultiGrid3D(_MultiGridBase):
     def set_smoother(self, smoother, sweeps_per_pass=1):
         self._call("set_smoother", ctypes.c_int(smoother), ctypes.c_int(sweeps_per_pass))
 
+    def set_jacobi_weight(self, omega):
+        """Relaxation weight of MG_SMOOTHER_JACOBI (default 6/7)."""
+        self._call("set_jacobi_weight", ctypes.c_double(omega))
+
     def owned_range(self, level):
         """(z_begin, z_count) of the global planes this rank owns on `level`."""
         zb, zc = ctypes.c_int(), ctypes.c_int()

@@ -94,6 +94,19 @@ def main():
                     zb, zc = d.owned_range(0)
                     if not same(d.get_v(0), s.get_v(0)[zb:zb + zc]):
                         failures.append("%s: plain-kernel V-cycle differs on rank %d" % (tag, rank))
+                if n == sizes[-1] and corrected:
+                    # weighted Jacobi (also partition-invariant): odd and even sweep counts, third cycle = graph replay
+                    d.init_problem()
+                    s.init_problem()
+                    d.set_smoother(mg.MG_SMOOTHER_JACOBI, 1)
+                    s.set_smoother(mg.MG_SMOOTHER_JACOBI, 1)
+                    for step in range(3):
+                        d.VCycle(0, 3, 2)
+                        s.VCycle(0, 3, 2)
+                    for l in range(d.numGrids):
+                        zb, zc = d.owned_range(l)
+                        if not same(d.get_v(l), s.get_v(l)[zb:zb + zc]):
+                            failures.append("%s: Jacobi V-cycle v level %d differs on rank %d" % (tag, l, rank))
                 d.close()
                 s.close()
     flag = torch.tensor([len(failures)], device="cuda")
