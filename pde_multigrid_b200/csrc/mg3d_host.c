@@ -790,7 +790,15 @@ static int relax_jacobi_level(mg3d_t* mg, int level, int ncycles)
             if ((st = exchange(mg, level, L->v, 2, 1, 1))) return st;
         }
     }
-    if (cur != red) MG_CUDA(cudaMemcpyAsync(red, cur, cbytes, cudaMemcpyDeviceToDevice, mg->stream));
+    if (cur != red) {
+        /* owned planes and the nearest ghost on each side (refreshed by the exchanges above).  Not the second lower
+           ghost: the scratch never receives it, and a neighbour that is already one exchange ahead may have pushed
+           its fresh value into v by now. */
+        const int a = L->own_lo > 0 ? L->own_lo - 1 : 0, b = L->own_hi < L->g.nzl ? L->own_hi + 1 : L->g.nzl;
+        const size_t off = (size_t)a * (size_t)L->g.plane * mg_esize(mg->dtype);
+        MG_CUDA(cudaMemcpyAsync(red + off, cur + off, (size_t)(b - a) * (size_t)L->g.plane * mg_esize(mg->dtype), cudaMemcpyDeviceToDevice,
+                                mg->stream));
+    }
     return MG_OK;
 }
 

@@ -39,6 +39,8 @@ def main():
 
     # default plan (levels n >= 257 distributed) at 513^3, and a deep-nesting plan (threshold lowered to 65) at 129/257
     runs = [(513, None)] + ([(129, "65"), (257, "65")] if world <= 4 else [(257, "65")])
+    if os.environ.get("DIST_CHECK_RUNS"):  # e.g. "257:65,513:" to repeat a subset while debugging
+        runs = [(int(a), b or None) for a, b in (r.split(":") for r in os.environ["DIST_CHECK_RUNS"].split(","))]
     sizes = [r[0] for r in runs]
     for n, min_n in runs:
         if min_n is None:
