@@ -955,15 +955,19 @@ int mg3d_residual_restrict(mg3d_t* mg, int fine_level)
     return residual_restrict_level(mg, fine_level);
 }
 
-static int interpolate_level(mg3d_t* mg, int fine_level, int add)
+/* colour_mask 3: the operator as the reference defines it.  colour_mask 2: only the colour-1 points -- what a V-cycle
+   with nu2 >= 1 needs, because the red half-sweep that follows recomputes every interior colour-0 point from its
+   colour-1 neighbours and f alone (N3/MultiGrid3D.cpp:532 never reads the point's own old value); the colour-0
+   ghosts are refreshed by that half-sweep's own exchange. */
+static int interpolate_level(mg3d_t* mg, int fine_level, int add, int colour_mask)
 {
     mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
     int lo, hi;
     interior_range(F, &lo, &hi);
     PROF_BEGIN(mg, fine_level, MG_OP_INTERPOLATE);
-    MG_LAUNCH(mg->launches, mgk3d_interpolate(mg->stream, mg->dtype, F->v, F->g, C->v, C->g, add, lo, hi));
+    MG_LAUNCH(mg->launches, mgk3d_interpolate(mg->stream, mg->dtype, F->v, F->g, C->v, C->g, add, colour_mask, lo, hi));
     PROF_END(mg);
-    return exchange(mg, fine_level, F->v, 3, 1, 1);
+    return exchange(mg, fine_level, F->v, colour_mask, 1, 1);
 }
 
 int mg3d_interpolate(mg3d_t* mg, int fine_level)
@@ -971,7 +975,7 @@ int mg3d_interpolate(mg3d_t* mg, int fine_level)
     int st = check_level(mg, fine_level);
     if (st) return st;
     if (fine_level == mg->nlevels - 1) return mg_fail(MG_ERR_ARG, "level %d is the coarsest", fine_level);
-    return interpolate_level(mg, fine_level, 0);
+    return interpolate_level(mg, fine_level, 0, 3);
 }
 
 int mg3d_interpolate_correct(mg3d_t* mg, int fine_level)
@@ -979,7 +983,7 @@ int mg3d_interpolate_correct(mg3d_t* mg, int fine_level)
     int st = check_level(mg, fine_level);
     if (st) return st;
     if (fine_level == mg->nlevels - 1) return mg_fail(MG_ERR_ARG, "level %d is the coarsest", fine_level);
-    return interpolate_level(mg, fine_level, 1);
+    return interpolate_level(mg, fine_level, 1, 3);
 }
 
 int mg3d_set_to_value(mg3d_t* mg, int level, int field, double value, int modify_boundaries)
@@ -1020,7 +1024,9 @@ static int vcycle_rec(mg3d_t* mg, int level, int v1, int v2)
     if (level != mg->nlevels - 1) {
         if ((st = residual_restrict_level(mg, level))) return st;
         if ((st = vcycle_rec(mg, level + 1, v1, v2))) return st;
-        if ((st = interpolate_level(mg, level, 1))) return st;
+        /* the colour-0 half of the correction is dead when a red-black post-smoothing sweep follows */
+        if ((st = interpolate_level(mg, level, 1, (v2 > 0 && mg->smoother != MG_SMOOTHER_JACOBI && !getenv("MG_B200_FULL_CORRECTION")) ? 2 : 3)))
+            return st;
     }
     return relax_level(mg, level, v2);
 }
@@ -1101,7 +1107,7 @@ static int fmg_rec(mg3d_t* mg, int level, int v0, int v1, int v2)
         PROF_END(mg);
         if ((st = after_restrict(mg, level, C->f))) return st;
         if ((st = fmg_rec(mg, level + 1, v0, v1, v2))) return st;
-        if ((st = interpolate_level(mg, level, 0))) return st;
+        if ((st = interpolate_level(mg, level, 0, 3))) return st;
     } else {
         mg_level3d* L = &mg->lv[level];
         MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, L->v, L->g, 0.0, 0, 0, L->g.nzl));
@@ -1173,7 +1179,7 @@ int mg3d_interpolate_host(mg3d_t* mg, void* fine, const int fs[3], const void* c
     st = copy_in(mg, df, &gf, fine, 0, fn); /* boundary of fine is kept */
     if (!st) st = copy_in(mg, dc, &gc, coarse, 0, cn);
     if (!st) {
-        int k = mgk3d_interpolate(mg->stream, mg->dtype, df, gf, dc, gc, 0, 1, fn - 1);
+        int k = mgk3d_interpolate(mg->stream, mg->dtype, df, gf, dc, gc, 0, 3, 1, fn - 1);
         if (k < 0) st = mg_fail(MG_ERR_CUDA, "interpolate launch failed"); else mg->launches += k;
     }
     if (!st) st = copy_out(mg, fine, df, &gf, 0, fn);

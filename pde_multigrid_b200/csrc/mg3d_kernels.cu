@@ -262,7 +262,11 @@ k_interpolate(T* __restrict__ fine, mg_geom3d gf, const T* __restrict__ coarse, 
 // formulas.  One coarse load per fine point instead of up to eight, no per-point 64-bit index arithmetic;
 // both colour arrays of the fine level are touched with unit stride (the pair x = 2cx, 2cx+1 shares the
 // half-index cx).
-template <typename T>
+// MASK selects the colours that are produced (bit c = colour c).  Inside a V-cycle with nu2 >= 1 the correction of
+// the colour-0 points is dead: the first half-sweep of the post-smoothing overwrites every interior colour-0 point
+// from its colour-1 neighbours alone (the Gauss-Seidel update never reads the point's own old value), so the cycle
+// asks for MASK = 2 and this kernel moves half the fine-level bytes; results are bit-identical.
+template <typename T, int MASK>
 __global__ void __launch_bounds__(256)
 k_interp_octet(T* __restrict__ fine, mg_geom3d gf, const T* __restrict__ coarse, mg_geom3d gc, int add_, int zl_lo,
                int zl_hi, int cz_first, int cz_last, int kchunk)
@@ -304,11 +308,11 @@ k_interp_octet(T* __restrict__ fine, mg_geom3d gf, const T* __restrict__ coarse,
 #pragma unroll
             for (int oy = 0; oy < 2; oy++) {
                 const int y = 2 * cy + oy;
-                const int c0 = (y + z) & 1;  // colour of the even-x point of the pair
+                const int c0 = (oy + oz) & 1;  // colour of the even-x point of the pair: (2cx + y + z) & 1, a compile-time value
                 const long long idx = (long long)zl * gf.plane + (long long)y * gf.hp + cx;
                 const bool ok = zok && y >= 1;  // y <= n-2 holds for every cell row
-                ptr[oz * 4 + oy * 2 + 0] = (ok && cx >= 1) ? fine + (long long)c0 * gf.cstride + idx : nullptr;
-                ptr[oz * 4 + oy * 2 + 1] = ok ? fine + (long long)(c0 ^ 1) * gf.cstride + idx : nullptr;
+                ptr[oz * 4 + oy * 2 + 0] = (ok && cx >= 1 && ((MASK >> c0) & 1)) ? fine + (long long)c0 * gf.cstride + idx : nullptr;
+                ptr[oz * 4 + oy * 2 + 1] = (ok && ((MASK >> (c0 ^ 1)) & 1)) ? fine + (long long)(c0 ^ 1) * gf.cstride + idx : nullptr;
             }
         }
         if (add_) {
@@ -520,7 +524,7 @@ int mgk3d_residual_restrict(cudaStream_t s, int dtype, const void* v, const void
 }
 
 int mgk3d_interpolate(cudaStream_t s, int dtype, void* fine, mg_geom3d gf, const void* coarse, mg_geom3d gc, int add,
-                      int zl_lo, int zl_hi)
+                      int colour_mask, int zl_lo, int zl_hi)
 {
     if (zl_hi <= zl_lo || gf.n < 3) return 0;
     const int cells = gc.n - 1;  // coarse cells per axis: cell c covers fine 2c, 2c+1
@@ -537,9 +541,11 @@ int mgk3d_interpolate(cudaStream_t s, int dtype, void* fine, mg_geom3d gf, const
     while (kchunk > 1 && (long long)((cells + bx - 1) / bx) * ((cells + by - 1) / by) * ((ncz + kchunk - 1) / kchunk) < 148 * 8) kchunk /= 2;
     dim3 block(bx, by, 1), grid((cells + bx - 1) / bx, (cells + by - 1) / by, (ncz + kchunk - 1) / kchunk);
     if (dtype == 0)
-        k_interp_octet<float><<<grid, block, 0, s>>>((float*)fine, gf, (const float*)coarse, gc, add, zl_lo, zl_hi, cz_first, cz_last, kchunk);
+        if (colour_mask == 2) k_interp_octet<float, 2><<<grid, block, 0, s>>>((float*)fine, gf, (const float*)coarse, gc, add, zl_lo, zl_hi, cz_first, cz_last, kchunk);
+        else k_interp_octet<float, 3><<<grid, block, 0, s>>>((float*)fine, gf, (const float*)coarse, gc, add, zl_lo, zl_hi, cz_first, cz_last, kchunk);
     else
-        k_interp_octet<double><<<grid, block, 0, s>>>((double*)fine, gf, (const double*)coarse, gc, add, zl_lo, zl_hi, cz_first, cz_last, kchunk);
+        if (colour_mask == 2) k_interp_octet<double, 2><<<grid, block, 0, s>>>((double*)fine, gf, (const double*)coarse, gc, add, zl_lo, zl_hi, cz_first, cz_last, kchunk);
+        else k_interp_octet<double, 3><<<grid, block, 0, s>>>((double*)fine, gf, (const double*)coarse, gc, add, zl_lo, zl_hi, cz_first, cz_last, kchunk);
     return launch_ok();
 }
 

@@ -102,9 +102,10 @@ int mgk3d_residual_restrict(cudaStream_t s, int dtype, const void* v, const void
 int mgk3d_residual_restrict_tma(cudaStream_t s, int dtype, const void* tmap_v_c0, const void* tmap_v_c1, const void* f,
                                 mg_geom3d gf, mg_coef3d c, int corrected, void* coarse_f, void* coarse_v, mg_geom3d gc,
                                 int czl_lo, int czl_hi);
-/* fine interior = Interpolate(coarse) (add == 0) or fine interior += Interpolate(coarse) (add != 0) */
+/* fine interior = Interpolate(coarse) (add == 0) or fine interior += Interpolate(coarse) (add != 0);
+   colour_mask 3 = every point, 2 = the colour-1 points only (see k_interp_octet) */
 int mgk3d_interpolate(cudaStream_t s, int dtype, void* fine, mg_geom3d gf, const void* coarse, mg_geom3d gc, int add,
-                      int zl_lo, int zl_hi);
+                      int colour_mask, int zl_lo, int zl_hi);
 /* fine interior += err interior (ApplyCorrection on two fine arrays) */
 int mgk3d_apply_correction(cudaStream_t s, int dtype, void* fine, const void* err, mg_geom3d g, int zl_lo, int zl_hi);
 /* setToValue */
