@@ -82,6 +82,28 @@ def main():
             rec["cpu_vcycle_ms"] = cpu_time(lambda: Or(3, dtype, True, n=257), lambda o: o.vcycle(0, 2, 2))
         out.append(rec)
         e.close()
+    # thesis replay: FullMultiGridVCycle(0, v0=2, nu=3000, nu=3000) at 257^3 in float, the run the
+    # thesis reports at 294 s on its GPU (T:p.69-72).  The thesis code carries the residual sign defect (REF_COMPAT);
+    # the memory traffic of the two modes is identical.
+    for mode, name in ((mg.MG_REF_COMPAT, "ref_compat"), (mg.MG_CORRECTED, "corrected")):
+        e = mg.MultiGrid3D(257, dtype=np.float32, residual_mode=mode)
+        s = torch.cuda.ExternalStream(e.stream)
+        e.init_problem()
+        e.sync()
+        l0 = e.kernel_launches
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(s)
+        e.FullMultiGridVCycle(0, 2, 3000, 3000)
+        b.record(s)
+        e.sync()
+        out.append({"config": "thesis replay: 3D Poisson 257^3 float32 FMG(v0=2, nu1=nu2=3000), %s" % name,
+                    "seconds": a.elapsed_time(b) / 1e3, "launches": int(e.kernel_launches - l0), "thesis_gpu_seconds": 294.0})
+        e.close()
+    # weighted-Jacobi option, 257^3 fp64 V(2,2)
+    e = mg.MultiGrid3D(257, dtype=np.float64, residual_mode=mg.MG_CORRECTED)
+    e.set_smoother(mg.MG_SMOOTHER_JACOBI)
+    out.append({"config": "3D Poisson 257^3 float64 V(2,2), weighted Jacobi (omega = 6/7)", "vcycle_ms": timed(e, lambda: e.VCycle(0, 2, 2), 50, warm=3)})
+    e.close()
     for r in out:
         print(json.dumps(r))
 
