@@ -3,17 +3,26 @@
 //     residual = CalculateResidual(fine)                       N3/MultiGrid3D.cpp:678-730
 //     Restrict(residual, ..., coarse->h_f, ...)                N3/MultiGrid3D.cpp:50-184
 //     setToValue(coarse->h_v, ..., 0, true)                    N3/MultiGrid3D.cpp:634
-// The fine residual only ever exists in shared memory.
+// The fine residual only ever exists in registers and shared memory.
 //
-// A CTA owns a (CXT x CYT) column of coarse points and marches along z one FINE plane at a time:
-//   * the two colour sub-tiles of fine v plane z+1 arrive by TMA (two cp.async.bulk.tensor.3d on one
-//     mbarrier) into a 4-slot ring while plane z is being processed; halo / out-of-domain elements are
-//     zero-filled by the hardware;
-//   * the residual of fine plane z is evaluated from the ring (7 conflict-free LDS per point) into a
-//     3-slot ring of residual planes stored parity-split in x, so that the 27 reads of the restriction
-//     are unit-stride as well; f is prefetched one plane ahead into registers;
-//   * after every odd fine plane 2k+1 the coarse plane k is produced from residual planes 2k-1, 2k, 2k+1
-//     with the reference's exact grouping of the 27 weights, and written together with coarse v = 0.
+// A CTA owns a (CXT x CYT) column of coarse points and marches along z, two FINE planes per iteration:
+//   * the two colour sub-tiles of the fine v planes arrive by TMA (two cp.async.bulk.tensor.3d on one
+//     mbarrier per plane) into a 6-slot ring, four planes ahead of their use; halo / out-of-domain
+//     elements are zero-filled by the hardware;
+//   * REGISTER TILING: thread (lane, warp) owns the 2x2 fine points under its coarse point -- half-index
+//     cx0+lane (x = 2cx, 2cx+1, one point in each colour array) of rows 2cy, 2cy+1 -- and keeps their v
+//     values of planes z-1, z, z+1 in registers.  Of the 7 stencil values of a residual, own value, D/U,
+//     one of O/E and one of N/S are then registers; 3 shared-memory loads per point remain (the new
+//     plane, the far O/E, the far N/S) instead of 7;
+//   * the residuals of the thread's 2x2 column stay in registers for its own restriction (12 of the 27
+//     taps); only the ones a neighbour needs go to a 3-slot ring of residual planes (parity-split in
+//     x, unit-stride reads), from which the other 15 taps are loaded.  The residual row below and the
+//     residual column left of the tile (81 points per plane) are computed by four warps the plain way;
+//   * after every odd fine plane 2k+1 the coarse plane k is produced with the reference's exact grouping
+//     of the 27 weights, and written together with coarse v = 0.
+// The version before this one read every stencil value from shared memory: the LSU data pipe was the
+// limiter (l1tex__data_pipe_lsu_wavefronts 76 % of peak, 815 M load wavefronts per launch at 1025^3;
+// profiles/r1_residual_restrict_tma_ncu_full.txt).
 // HBM traffic per fine point: v and f once (+ 19/16 x 36/32 halo re-reads that hit L2) and 2/8 coarse
 // writes: the algorithmic 2*B*N_l + 2*B*N_{l+1} of SURVEY.md 8(d).
 #include "mg3d_device.cuh"
@@ -30,8 +39,7 @@ constexpr int CYT = MGK3D_RR_CYT;       // coarse points per tile in y
 constexpr int VROWS = MGK3D_RR_BOX_Y;   // fine rows of a v tile: 2*CYT + 3
 constexpr int RROWS = 2 * CYT + 1;      // fine rows of a residual plane tile
 constexpr int RCOLS = CXT + 2;          // per-parity columns of a residual row (33 used, even pitch)
-constexpr int HPR = CXT + 1;            // half-indices per residual row and colour (33)
-constexpr int RING = 4;   // v planes: z-1, z, z+1 live + one in flight
+constexpr int RING = 6;   // v planes: z-1 .. z+2 live during a pair of planes + two in flight
 constexpr int RRING = 3;  // residual planes: 2k-1, 2k, 2k+1
 constexpr int NT = 256;
 
@@ -78,172 +86,200 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
     // v plane p (global) lives in slot (p - pbase) % RING; planes pbase = zf0-1 .. zf1+1 are streamed
     const int pbase = zf0 - 1;
     auto issue = [&](int p) {
-        const int s = (p - pbase) % RING;
+        const unsigned s = (unsigned)(p - pbase) % RING;
         T* dst = vring + (size_t)s * VSLOT;
         mbar_arrive_expect_tx(&bars[s], 2 * VSUB_BYTES);
         tma_load_3d(dst, &map_c0, &bars[s], hi_org, fy0 - 1, p - gf.z0);
         tma_load_3d(dst + VSUB_STRIDE, &map_c1, &bars[s], hi_org, fy0 - 1, p - gf.z0);
     };
+    auto wait_plane = [&](int p) {
+        const unsigned k = (unsigned)(p - pbase);
+        mbar_wait(&bars[k % RING], (k / RING) & 1);
+    };
+    auto slot_of = [&](int p) -> const T* { return vring + ((unsigned)(p - pbase) % RING) * VSLOT; };
     if (tid == 0)
         for (int p = pbase; p <= min(pbase + RING - 1, zf1 + 1); p++) issue(p);
 
-    // Thread -> residual points, fixed over the planes.  Warp w, lane l.  Four regular passes: colour
-    // (p >> 1), row ly = w + 8*(p & 1), half-index hl = l -- every index of these is ONE per-thread base plus
-    // a compile-time constant, so the z loop is loads, arithmetic and one store per point.  (The first
-    // versions kept per-point offset/flag arrays; under the register cap the compiler re-derived them from
-    // threadIdx every plane: 72 instructions per residual point, 4.8e9 warp instructions per launch at
-    // 1025^3, issue-bound at 0.53 of the HBM roofline -- profiles/r1_residual_restrict_tma_ncu_full.txt.)
-    // The fifth pass is the irregular rest: row 16 of both colours (warps 0, 1) and the 33rd half-index
-    // of the 34 (colour, row) pairs (warps 2, 3), with per-thread precomputed indices.
-    static_assert(CXT == 32 && CYT == 8 && NT == 256, "thread mapping of the residual stage");
+    static_assert(CXT == 32 && CYT == 8 && NT == 256, "thread mapping: one coarse point = one 2x2 fine column per thread");
     const int w = tid >> 5, lane = tid & 31;
     const int hp = gf.hp;
-    const int T0 = w * W + lane;           // + (8*jj + 1)*W + A - 1 -> element of a v colour sub-tile
-    const int T1 = w * 2 * RCOLS + lane;   // + jj*16*RCOLS          -> element of a residual plane
-    const int T2 = ((2 * w + 1) * 2) * RCOLS + lane;  // restriction stage: centre row of coarse point (lane, w)
+    // the thread's fine column: half-index hi = cx0 + lane; rows ya = 2*(cy0+w) (even, "row 0") and ya+1 ("row 1").
+    // Element of a colour sub-tile: row y - (fy0-1), column hi - hi_org.
+    const int Pa = (2 * w + 2) * W + lane + A, Pb = Pa + W;
+    const int T2 = (2 * w + 1) * 2 * RCOLS + lane;  // residual-plane element of (row ya, odd x = 2hi-1)
     // Per-thread predicates live in one opaque bit mask (otherwise ptxas re-derives each of them from
-    // blockIdx/threadIdx in every plane).  x parity q of a colour-c point in row y of plane z: (c + y + z) & 1.
+    // blockIdx/threadIdx in every plane).
     enum : unsigned {
-        F_A0 = 1u << 0, F_A1 = 1u << 1,  // rows w:     residual defined for the q = 0 / q = 1 point
-        F_B0 = 1u << 2, F_B1 = 1u << 3,  // rows w + 8
-        F_FA = 1u << 4, F_FB = 1u << 5,  // f needed in rows w / w + 8
-        F_L1 = 1u << 6,                  // lane >= 1: the q = 0 point belongs to the residual tile
-        F_PW = 1u << 7,                  // y parity of rows w, w + 8 (fy0 is odd)
-        F_TACT = 1u << 8, F_TST0 = 1u << 9, F_T0 = 1u << 10, F_T1 = 1u << 11, F_TF = 1u << 12, F_TP = 1u << 13,  // fifth pass
+        F_X0 = 1u << 0, F_X1 = 1u << 1,   // x = 2hi / 2hi+1 is an interior column
+        F_YA = 1u << 2, F_YB = 1u << 3,   // row ya / ya+1 is an interior row
+        F_FA = 1u << 4, F_FB = 1u << 5,   // f needed in row ya / ya+1
+        F_TACT = 1u << 8, F_TST0 = 1u << 9, F_T0 = 1u << 10, F_T1 = 1u << 11, F_TF = 1u << 12, F_TP = 1u << 13,  // edge pass
         F_CIN = 1u << 14, F_CBND = 1u << 15, F_CP = 1u << 16  // coarse point: inside the grid, on its boundary, (cx+cy)&1
     };
     unsigned fl = 0;
     int t_own, t_oth, t_r;
-    const T *fp, *tfp;  // f of this thread's first point / fifth-pass point in plane zf0 (advanced by one plane per iteration)
+    const T *fp, *tfp;  // f of the thread's (hi, ya) / edge-pass point in plane zf0 (advanced by one plane per plane)
     long long c_base;
     {
-        const int x0 = 2 * (cx0 - 1 + lane);  // x of a q = 0 point; q = 1: x0 + 1
-        const bool xv0 = lane >= 1 && x0 >= 1 && x0 <= n - 2;
-        const bool xv1 = x0 + 1 >= 1 && x0 + 1 <= n - 2;
-        const int ya = fy0 + w, yb = ya + 8;
-        const bool yva = ya >= 1 && ya <= n - 2, yvb = yb >= 1 && yb <= n - 2;
-        fl |= (yva && xv0 ? F_A0 : 0) | (yva && xv1 ? F_A1 : 0) | (yvb && xv0 ? F_B0 : 0) | (yvb && xv1 ? F_B1 : 0);
+        const int hi = cx0 + lane, ya = 2 * (cy0 + w);
+        const bool xv0 = 2 * hi >= 1 && 2 * hi <= n - 2, xv1 = 2 * hi + 1 <= n - 2;
+        const bool yva = ya >= 1 && ya <= n - 2, yvb = ya + 1 <= n - 2;
+        fl |= (xv0 ? F_X0 : 0) | (xv1 ? F_X1 : 0) | (yva ? F_YA : 0) | (yvb ? F_YB : 0);
         fl |= (yva && (xv0 || xv1) ? F_FA : 0) | (yvb && (xv0 || xv1) ? F_FB : 0);  // f is only read where a residual is evaluated
-        fl |= (lane >= 1 ? F_L1 : 0) | (((w + 1) & 1) ? F_PW : 0);
         const long long zoff = (long long)(zf0 - gf.z0) * gf.plane;
-        fp = f + (zoff + (long long)ya * hp + (cx0 - 1 + lane));
+        fp = f + (zoff + (long long)ya * hp + hi);
 
-        // fifth pass: row 16 of both colours (warps 0, 1) and the 33rd half-index of the 34 (colour, row)
-        // pairs (warps 2, 3)
+        // edge pass: the residual row below the tile (ly = 0: warps 0, 1 = colour 0, 1 at half-indices cx0..cx0+31)
+        // and the half-index left of it (hl = 0, every (colour, row) pair: 34 lanes of warps 2, 3)
         int col, ly, hl;
         bool act;
-        if (w < 2) { col = w; ly = RROWS - 1; hl = lane; act = true; }
+        if (w < 2) { col = w; ly = 0; hl = lane + 1; act = true; }
         else {
             const int u = (w - 2) * 32 + lane;
             act = w < 4 && u < 2 * RROWS;
             col = (act && u >= RROWS) ? 1 : 0;
             ly = act ? u - col * RROWS : 0;
-            hl = 32;
+            hl = 0;
         }
-        const int y = fy0 + ly, hi = cx0 - 1 + hl, cc = (ly + 1) * W + hl + A - 1;
+        const int y = fy0 + ly, thi = cx0 - 1 + hl, cc = (ly + 1) * W + hl + A - 1;
         t_own = col * VSUB_STRIDE + cc;
         t_oth = (col ^ 1) * VSUB_STRIDE + cc;
         t_r = ly * 2 * RCOLS + hl;
         const bool tyv = act && y >= 1 && y <= n - 2;
-        const bool tx0 = hl >= 1 && 2 * hi >= 1 && 2 * hi <= n - 2, tx1 = 2 * hi + 1 >= 1 && 2 * hi + 1 <= n - 2;
+        const bool tx0 = hl >= 1 && 2 * thi >= 1 && 2 * thi <= n - 2, tx1 = 2 * thi + 1 >= 1 && 2 * thi + 1 <= n - 2;
         fl |= (act ? F_TACT : 0) | (act && hl >= 1 ? F_TST0 : 0) | (tyv && tx0 ? F_T0 : 0) | (tyv && tx1 ? F_T1 : 0) |
               (tyv && (tx0 || tx1) ? F_TF : 0) | (((col + y) & 1) ? F_TP : 0);
-        tfp = f + (zoff + (long long)col * gf.cstride + (long long)y * hp + hi);
+        tfp = f + (zoff + (long long)col * gf.cstride + (long long)y * hp + thi);
 
-        // the thread's coarse point (restriction stage): cx = cx0 + lane, cy = cy0 + w
+        // the thread's coarse point: cx = cx0 + lane, cy = cy0 + w
         const int cx = cx0 + lane, cy = cy0 + w;
         fl |= (cx < gc.n && cy < gc.n ? F_CIN : 0) | ((cx == 0 || cx == gc.n - 1 || cy == 0 || cy == gc.n - 1) ? F_CBND : 0) |
               (((cx + cy) & 1) ? F_CP : 0);
         c_base = (long long)cy * gc.hp + (cx >> 1);
     }
     asm volatile("" : "+r"(fl));
-    const long long f_b = 8ll * hp, f_c1 = gf.cstride;  // f offsets of rows w + 8 / of colour 1, in elements
+    const long long f_c1 = gf.cstride;  // f offset of colour 1, in elements (row ya+1: + hp)
 
     const int nzl = gf.nzl;
-    // f of plane z (fp/tfp point into that plane) -> dst; addresses of points without a residual are never formed
+    // f of plane z (fp/tfp point into that plane) -> dst[row*2 + colour], dst[4] = edge pass
     auto load_f = [&](int z, T (&dst)[5]) {
         const int zl = z - gf.z0;
         const unsigned m = (zl >= 0 && zl < nzl) ? fl : 0u;
         dst[0] = (m & F_FA) ? __ldg(fp) : T(0);
-        dst[1] = (m & F_FB) ? __ldg(fp + f_b) : T(0);
-        dst[2] = (m & F_FA) ? __ldg(fp + f_c1) : T(0);
-        dst[3] = (m & F_FB) ? __ldg(fp + f_c1 + f_b) : T(0);
+        dst[1] = (m & F_FA) ? __ldg(fp + f_c1) : T(0);
+        dst[2] = (m & F_FB) ? __ldg(fp + hp) : T(0);
+        dst[3] = (m & F_FB) ? __ldg(fp + f_c1 + hp) : T(0);
         dst[4] = (m & F_TF) ? __ldg(tfp) : T(0);
     };
-    T fnext[5];
-    load_f(zf0, fnext);
 
-    unsigned rs = 0;  // residual-ring slot of plane z: (z - zf0) % RRING
-    for (int z = zf0; z <= zf1; z++) {
-        const unsigned k = (unsigned)(z - pbase);  // ring index of v plane z (>= 1)
-        T fcur[5];
+    // v of the thread's column: vm/vc/vu[row*2 + colour] at planes z-1, z, z+1
+    T vm[4], vc[4], vu[4];
+    // residuals of the thread's column by [row*2 + x parity]: planes 2k-1, 2k, 2k+1
+    T rm[4] = {T(0), T(0), T(0), T(0)}, rc[4], rp[4];
+    T fcur[5], fnext[5];
+
+    // residual of fine plane z (ZP = z & 1) for the thread's column and the edge pass; v ring slots of planes
+    // z-1, z, z+1 must have landed.  Shifts the register window by one plane at the end.
+    auto plane = [&](int z, auto ZPc, T (&res)[4]) {
+        constexpr int ZP = decltype(ZPc)::value;
+        const T* sD = slot_of(z - 1);
+        const T* sC = slot_of(z);
+        const T* sU = slot_of(z + 1);
+        T* rz = rring + ((unsigned)(z - zf0) % RRING) * RSLOT;
+        vu[0] = sU[Pa]; vu[1] = sU[VSUB_STRIDE + Pa]; vu[2] = sU[Pb]; vu[3] = sU[VSUB_STRIDE + Pb];
+        const unsigned vmask = (z >= 1 && z <= n - 2) ? fl : 0u;  // residual is zero on the boundary planes
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int col = 0; col < 2; col++) {
+                const int q = (col + r + ZP) & 1;  // x parity of this colour in this row of this plane: compile time
+                const int oth = col ^ 1;
+                const int P = r ? Pb : Pa;
+                const T side = sC[oth * VSUB_STRIDE + P + (q ? 1 : -1)];
+                const T own_oth = vc[r * 2 + oth];
+                const T O = q ? own_oth : side, E = q ? side : own_oth;
+                const T N = r ? vc[0 * 2 + oth] : sC[oth * VSUB_STRIDE + Pa - W];
+                const T S = r ? sC[oth * VSUB_STRIDE + Pb + W] : vc[1 * 2 + oth];
+                const T val = residual_point<T, FAST>(O, E, N, S, vm[r * 2 + oth], vu[r * 2 + oth], vc[r * 2 + col], fcur[r * 2 + col], c, corrected);
+                const bool ok = (vmask & (r ? F_YB : F_YA)) && (vmask & (q ? F_X1 : F_X0));
+                res[r * 2 + q] = ok ? val : T(0);
+            }
+        // what the neighbours' restrictions read: the odd-x points (thread lane+1) and row ya+1 (warp w+1)
+        rz[T2 + 1] = res[1];                         // (ya,   2hi+1): parity array 0 at lane+1
+        rz[T2 + 2 * RCOLS + 1] = res[3];             // (ya+1, 2hi+1)
+        rz[T2 + 2 * RCOLS + RCOLS] = res[2];         // (ya+1, 2hi):   parity array 1 at lane
+        if (w < 4) {  // warp-uniform: the edge pass, every stencil value from shared memory
+            const int q = ((fl / F_TP) ^ z) & 1;
+            T val = T(0);
+            if (vmask & (q ? F_T1 : F_T0)) {
+                const int o = t_oth;
+                val = residual_point<T, FAST>(sC[o - 1 + q], sC[o + q], sC[o - W], sC[o + W], sD[o], sU[o], sC[t_own], fcur[4], c, corrected);
+            }
+            if (fl & (q ? F_TACT : F_TST0)) rz[t_r + (q ? 0 : RCOLS - 1)] = val;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) { vm[j] = vc[j]; vc[j] = vu[j]; }
+    };
+    auto step_f = [&](int z) {  // fcur <- f of plane z (prefetched), fnext <- f of plane z+1
 #pragma unroll
         for (int j = 0; j < 5; j++) fcur[j] = fnext[j];
         fp += gf.plane;
         tfp += gf.plane;
         if (z < zf1) load_f(z + 1, fnext);
-        if (z == zf0) {
-            mbar_wait(&bars[(k - 1) & (RING - 1)], ((k - 1) / RING) & 1);
-            mbar_wait(&bars[k & (RING - 1)], (k / RING) & 1);
-        }
-        mbar_wait(&bars[(k + 1) & (RING - 1)], ((k + 1) / RING) & 1);
+    };
 
-        // ---- residual of fine plane z -> rring[rs] ----
-        const T* vD = vring + ((k - 1) & (RING - 1)) * VSLOT + T0;
-        const T* vC = vring + (k & (RING - 1)) * VSLOT + T0;
-        const T* vU = vring + ((k + 1) & (RING - 1)) * VSLOT + T0;
-        T* rz = rring + rs * RSLOT;
-        const unsigned vm = (z >= 1 && z <= n - 2) ? fl : 0u;  // residual is zero on the boundary planes
-        const int q0 = ((fl / F_PW) ^ z) & 1;  // x parity of the colour-0 points of this thread's rows in this plane
+    // ---- prologue: the odd plane zf0 = 2*cz0 - 1 ----
+    load_f(zf0, fnext);
+    step_f(zf0);
+    wait_plane(zf0 - 1);
+    wait_plane(zf0);
+    wait_plane(zf0 + 1);
+    {
+        const T *s0 = slot_of(zf0 - 1), *s1 = slot_of(zf0);
+        vm[0] = s0[Pa]; vm[1] = s0[VSUB_STRIDE + Pa]; vm[2] = s0[Pb]; vm[3] = s0[VSUB_STRIDE + Pb];
+        vc[0] = s1[Pa]; vc[1] = s1[VSUB_STRIDE + Pa]; vc[2] = s1[Pb]; vc[3] = s1[VSUB_STRIDE + Pb];
+    }
+    plane(zf0, std::integral_constant<int, 1>{}, rm);
+    __syncthreads();  // v slot of plane zf0-1 free
+    if (tid == 0 && zf0 + RING - 1 <= zf1 + 1) issue(zf0 + RING - 1);
+
+    // ---- pairs of planes (2cz, 2cz+1), then coarse plane cz ----
+    for (int z = zf0 + 1; z < zf1; z += 2) {
+        step_f(z);
+        wait_plane(z + 1);
+        plane(z, std::integral_constant<int, 0>{}, rc);
+        step_f(z + 1);
+        wait_plane(z + 2);
+        plane(z + 1, std::integral_constant<int, 1>{}, rp);
+        __syncthreads();  // residual planes z-1, z, z+1 complete in shared memory; v slots of planes z-1, z free
+        if (tid == 0) {
+            if (z + RING - 1 <= zf1 + 1) issue(z + RING - 1);
+            if (z + RING <= zf1 + 1) issue(z + RING);
+        }
+        const int cz = z >> 1, czl = cz - gc.z0;
+        if (fl & F_CIN) {
+            T out = T(0);  // boundary: injection of the zero boundary residual (N3/MultiGrid3D.cpp:113-119, :705)
+            if (!((fl & F_CBND) || cz == 0 || cz == gc.n - 1)) {
+                const unsigned s0 = (unsigned)(z - 1 - zf0) % RRING;
+                const T* qm = rring + s0 * RSLOT + T2;                                 // plane z-1
+                const T* qc = rring + (s0 == RRING - 1 ? 0u : s0 + 1) * RSLOT + T2;    // plane z
+                const T* qp = rring + (s0 == 0 ? RRING - 1u : s0 - 1) * RSLOT + T2;    // plane z+1
+                // centre (2cx, 2cy) = the thread's (row 0, even x).  dx, dy in {0, 1}: own registers; dx = -1: parity
+                // array 0 at lane of rows ya-1 .. ya+1; dy = -1: row ya-1, even x: array 1 at lane, odd x: array 0 at lane+1
+                out = restrict_point<T>([&](int dx, int dy, int dz) {
+                    if (dx >= 0 && dy >= 0) return dz < 0 ? rm[dy * 2 + dx] : (dz == 0 ? rc[dy * 2 + dx] : rp[dy * 2 + dx]);
+                    const T* pl = dz < 0 ? qm : (dz == 0 ? qc : qp);
+                    if (dx < 0) return pl[dy * 2 * RCOLS];
+                    return dx == 0 ? pl[-2 * RCOLS + RCOLS] : pl[-2 * RCOLS + 1];
+                });
+            }
+            const long long ci = ((((fl / F_CP) ^ cz) & 1) ? gc.cstride : 0ll) + (long long)czl * gc.plane + c_base;
+            cf[ci] = out;
+            cv[ci] = T(0);  // setToValue(coarse->h_v, 0, true), N3/MultiGrid3D.cpp:634
+        }
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
-            const int col = p >> 1, jj = p & 1;  // compile-time after unrolling
-            const int cp = (8 * jj + 1) * W + A - 1;
-            const int q = q0 ^ col;
-            const T* own = vC + col * VSUB_STRIDE + cp;
-            const T* oc = vC + (col ^ 1) * VSUB_STRIDE + cp;
-            const T* od = vD + (col ^ 1) * VSUB_STRIDE + cp;
-            const T* ou = vU + (col ^ 1) * VSUB_STRIDE + cp;
-            T val = T(0);
-            if (vm & (jj ? (q ? F_B1 : F_B0) : (q ? F_A1 : F_A0)))
-                val = residual_point<T, FAST>(oc[q - 1], oc[q], oc[-W], oc[W], od[0], ou[0], own[0], fcur[p], c, corrected);
-            if (q || (fl & F_L1)) rz[T1 + jj * 16 * RCOLS + (q ? 0 : RCOLS - 1)] = val;
-        }
-        if (w < 4) {  // warp-uniform: warps 4..7 have no fifth-pass point
-            const int q = ((fl / F_TP) ^ z) & 1;
-            T val = T(0);
-            if (vm & (q ? F_T1 : F_T0)) {
-                const T *c0 = vC - T0, *d0 = vD - T0, *u0 = vU - T0;
-                const int o = t_oth;
-                val = residual_point<T, FAST>(c0[o - 1 + q], c0[o + q], c0[o - W], c0[o + W], d0[o], u0[o], c0[t_own], fcur[4], c, corrected);
-            }
-            if (fl & (q ? F_TACT : F_TST0)) rz[t_r + (q ? 0 : RCOLS - 1)] = val;
-        }
-        __syncthreads();  // residual plane z complete; v slot of plane z-1 free
-        if (tid == 0 && z + RING - 1 <= zf1 + 1) issue(z + RING - 1);
-
-        // ---- after an odd fine plane z = 2*cz+1: restrict planes z-2, z-1, z -> coarse plane cz ----
-        if ((z & 1) && z > zf0) {
-            const int cz = (z - 1) >> 1, czl = cz - gc.z0;
-            if (fl & F_CIN) {
-                T out = T(0);  // boundary: injection of the zero boundary residual (N3/MultiGrid3D.cpp:113-119, :705)
-                if (!((fl & F_CBND) || cz == 0 || cz == gc.n - 1)) {
-                    const T* rm = rring + (rs == 2 ? 0u : rs + 1) * RSLOT + T2;  // plane z-2
-                    const T* rc = rring + (rs == 0 ? 2u : rs - 1) * RSLOT + T2;  // plane z-1
-                    const T* rp = rz + T2;
-                    // centre lx = 2*lane+1 (odd: parity array 1 at lane); dx = -1/+1 -> even lx: array 0 at lane / lane+1
-                    out = restrict_point<T>([&](int dx, int dy, int dz) {
-                        const T* pl = dz < 0 ? rm : (dz == 0 ? rc : rp);
-                        return dx == 0 ? pl[dy * 2 * RCOLS + RCOLS] : pl[dy * 2 * RCOLS + (dx > 0)];
-                    });
-                }
-                const long long ci = ((((fl / F_CP) ^ cz) & 1) ? gc.cstride : 0ll) + (long long)czl * gc.plane + c_base;
-                cf[ci] = out;
-                cv[ci] = T(0);  // setToValue(coarse->h_v, 0, true), N3/MultiGrid3D.cpp:634
-            }
-            __syncthreads();  // the 3-slot residual ring: plane z-2 is overwritten by the next iteration
-        }
-        rs = rs == RRING - 1 ? 0 : rs + 1;
+        for (int j = 0; j < 4; j++) rm[j] = rp[j];
+        __syncthreads();  // the 3-slot residual ring: plane z-1 is overwritten by plane z+2
     }
 }
 
