@@ -762,6 +762,27 @@ static int relax_launch(mg3d_t* mg, mg_level3d* L, int colour, int lo, int hi, i
     return MG_OK;
 }
 
+/* 1 when relax_level(level, n > 0) takes the overlapped path: the boundary planes of the slab and their halo exchange
+   run on the side stream while the interior planes are swept; every half-sweep ends with a join */
+static int relax_overlaps(const mg3d_t* mg, int level)
+{
+    const mg_level3d* L = &mg->lv[level];
+    int lo, hi;
+    interior_range(L, &lo, &hi);
+    return L->dist && mg->overlap && !mg->prof.enabled && hi - lo >= 4 && mg->smoother != MG_SMOOTHER_JACOBI;
+}
+
+/* A halo exchange whose ghost planes are first read by the boundary-plane kernel of the smoothing call that follows
+   (an overlapped one: the caller checks relax_overlaps): it goes to the side stream, the main stream carries on with
+   the interior sweep, and the join of that call's first half-sweep covers it.  Exchanges keep their global order:
+   everything on the side stream is joined before the next exchange on the main stream. */
+static int exchange_deferred(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int down)
+{
+    MG_CUDA(cudaEventRecord(mg->ev_fork, mg->stream));
+    MG_CUDA(cudaStreamWaitEvent(mg->cstream, mg->ev_fork, 0));
+    return exchange_on(mg, level, field, colour_mask, depth_up, down, mg->cstream);
+}
+
 /* Weighted Jacobi, ncycles sweeps.  On the colour-split layout a sweep is two launches: the new colour-0 values go
    to a scratch array (colour 1 still needs the old ones), colour 1 is then updated in place (a point reads only
    its own old value of that array).  The scratch array IS the colour-0 array of the next sweep, so the roles of
@@ -825,13 +846,14 @@ static int relax_level(mg3d_t* mg, int level, int ncycles)
     }
     /* distributed level: the two boundary planes of the slab are swept first, their halo exchange then runs on
        the side stream while the interior planes are swept; the next half-sweep waits for both */
-    const int overlap = L->dist && mg->overlap && !mg->prof.enabled && hi - lo >= 4;
+    const int overlap = relax_overlaps(mg, level);
     for (int k = 0; k < ncycles; k++)
         for (int colour = 0; colour < 2; colour++) {
             if (overlap) {
-                MG_LAUNCH(mg->launches, mgk3d_relax_colour_pair(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, colour, lo, hi - 1));
+                /* boundary planes and interior planes are disjoint writes of the same colour: they run concurrently */
                 MG_CUDA(cudaEventRecord(mg->ev_fork, mg->stream));
                 MG_CUDA(cudaStreamWaitEvent(mg->cstream, mg->ev_fork, 0));
+                MG_LAUNCH(mg->launches, mgk3d_relax_colour_pair(mg->cstream, mg->dtype, L->v, L->f, L->g, L->c, colour, lo, hi - 1));
                 if ((st = exchange_on(mg, level, L->v, 1 << colour, 1, 1, mg->cstream))) return st;
                 MG_CUDA(cudaEventRecord(mg->ev_join, mg->cstream));
                 if ((st = relax_launch(mg, L, colour, lo + 1, hi - 1, use_tma))) return st;
@@ -904,9 +926,10 @@ static void coarse_share(const mg3d_t* mg, int fine_level, int* czl_lo, int* czl
 }
 
 /* what follows a restriction onto level+1: refresh ghosts (distributed) or gather (first agglomerated level) */
-static int after_restrict(mg3d_t* mg, int fine_level, void* coarse_field)
+static int after_restrict(mg3d_t* mg, int fine_level, void* coarse_field, int defer)
 {
     const mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
+    if (C->dist && defer) return exchange_deferred(mg, fine_level + 1, coarse_field, 3, MG_GHOST_LO, 1);
     if (C->dist) return exchange(mg, fine_level + 1, coarse_field, 3, MG_GHOST_LO, 1);
     if (F->dist) return gather_level(mg, fine_level + 1, coarse_field, 1);
     return MG_OK;
@@ -924,10 +947,12 @@ int mg3d_restrict(mg3d_t* mg, int fine_level, int field)
     PROF_BEGIN(mg, fine_level, MG_OP_OTHER);
     MG_LAUNCH(mg->launches, mgk3d_restrict(mg->stream, mg->dtype, field_ptr(F, field), F->g, field_ptr(C, field), C->g, lo, hi));
     PROF_END(mg);
-    return after_restrict(mg, fine_level, field_ptr(C, field));
+    return after_restrict(mg, fine_level, field_ptr(C, field), 0);
 }
 
-static int residual_restrict_level(mg3d_t* mg, int fine_level)
+/* defer_f_halo: the coarse f ghosts are not read before the coarse level's residual (the smoother reads f at its own
+   points only), so inside a V-cycle their exchange overlaps the first coarse half-sweep */
+static int residual_restrict_level(mg3d_t* mg, int fine_level, int defer_f_halo)
 {
     mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
     int lo, hi, st;
@@ -944,7 +969,7 @@ static int residual_restrict_level(mg3d_t* mg, int fine_level)
     if (F->dist) /* coarse v = 0 everywhere this rank stores it (ghost planes, or the whole agglomerated level) */
         MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, C->v, C->g, 0.0, 1, 0, C->g.nzl));
     PROF_END(mg);
-    return after_restrict(mg, fine_level, C->f);
+    return after_restrict(mg, fine_level, C->f, defer_f_halo);
 }
 
 int mg3d_residual_restrict(mg3d_t* mg, int fine_level)
@@ -952,14 +977,14 @@ int mg3d_residual_restrict(mg3d_t* mg, int fine_level)
     int st = check_level(mg, fine_level);
     if (st) return st;
     if (fine_level == mg->nlevels - 1) return mg_fail(MG_ERR_ARG, "level %d is the coarsest", fine_level);
-    return residual_restrict_level(mg, fine_level);
+    return residual_restrict_level(mg, fine_level, 0);
 }
 
 /* colour_mask 3: the operator as the reference defines it.  colour_mask 2: only the colour-1 points -- what a V-cycle
    with nu2 >= 1 needs, because the red half-sweep that follows recomputes every interior colour-0 point from its
    colour-1 neighbours and f alone (N3/MultiGrid3D.cpp:532 never reads the point's own old value); the colour-0
    ghosts are refreshed by that half-sweep's own exchange. */
-static int interpolate_level(mg3d_t* mg, int fine_level, int add, int colour_mask)
+static int interpolate_level(mg3d_t* mg, int fine_level, int add, int colour_mask, int defer_halo)
 {
     mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
     int lo, hi;
@@ -967,6 +992,7 @@ static int interpolate_level(mg3d_t* mg, int fine_level, int add, int colour_mas
     PROF_BEGIN(mg, fine_level, MG_OP_INTERPOLATE);
     MG_LAUNCH(mg->launches, mgk3d_interpolate(mg->stream, mg->dtype, F->v, F->g, C->v, C->g, add, colour_mask, lo, hi));
     PROF_END(mg);
+    if (defer_halo && F->dist) return exchange_deferred(mg, fine_level, F->v, colour_mask, 1, 1);
     return exchange(mg, fine_level, F->v, colour_mask, 1, 1);
 }
 
@@ -975,7 +1001,7 @@ int mg3d_interpolate(mg3d_t* mg, int fine_level)
     int st = check_level(mg, fine_level);
     if (st) return st;
     if (fine_level == mg->nlevels - 1) return mg_fail(MG_ERR_ARG, "level %d is the coarsest", fine_level);
-    return interpolate_level(mg, fine_level, 0, 3);
+    return interpolate_level(mg, fine_level, 0, 3, 0);
 }
 
 int mg3d_interpolate_correct(mg3d_t* mg, int fine_level)
@@ -983,7 +1009,7 @@ int mg3d_interpolate_correct(mg3d_t* mg, int fine_level)
     int st = check_level(mg, fine_level);
     if (st) return st;
     if (fine_level == mg->nlevels - 1) return mg_fail(MG_ERR_ARG, "level %d is the coarsest", fine_level);
-    return interpolate_level(mg, fine_level, 1, 3);
+    return interpolate_level(mg, fine_level, 1, 3, 0);
 }
 
 int mg3d_set_to_value(mg3d_t* mg, int level, int field, double value, int modify_boundaries)
@@ -1022,10 +1048,11 @@ static int vcycle_rec(mg3d_t* mg, int level, int v1, int v2)
     st = relax_level(mg, level, v1);
     if (st) return st;
     if (level != mg->nlevels - 1) {
-        if ((st = residual_restrict_level(mg, level))) return st;
+        if ((st = residual_restrict_level(mg, level, v1 > 0 && relax_overlaps(mg, level + 1)))) return st;
         if ((st = vcycle_rec(mg, level + 1, v1, v2))) return st;
         /* the colour-0 half of the correction is dead when a red-black post-smoothing sweep follows */
-        if ((st = interpolate_level(mg, level, 1, (v2 > 0 && mg->smoother != MG_SMOOTHER_JACOBI && !getenv("MG_B200_FULL_CORRECTION")) ? 2 : 3)))
+        if ((st = interpolate_level(mg, level, 1, (v2 > 0 && mg->smoother != MG_SMOOTHER_JACOBI && !getenv("MG_B200_FULL_CORRECTION")) ? 2 : 3,
+                                    v2 > 0 && relax_overlaps(mg, level))))
             return st;
     }
     return relax_level(mg, level, v2);
@@ -1105,9 +1132,9 @@ static int fmg_rec(mg3d_t* mg, int level, int v0, int v1, int v2)
         PROF_BEGIN(mg, level, MG_OP_OTHER);
         MG_LAUNCH(mg->launches, mgk3d_restrict(mg->stream, mg->dtype, F->f, F->g, C->f, C->g, lo, hi));
         PROF_END(mg);
-        if ((st = after_restrict(mg, level, C->f))) return st;
+        if ((st = after_restrict(mg, level, C->f, 0))) return st;
         if ((st = fmg_rec(mg, level + 1, v0, v1, v2))) return st;
-        if ((st = interpolate_level(mg, level, 0, 3))) return st;
+        if ((st = interpolate_level(mg, level, 0, 3, 0))) return st;
     } else {
         mg_level3d* L = &mg->lv[level];
         MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, L->v, L->g, 0.0, 0, 0, L->g.nzl));
