@@ -190,7 +190,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1025, help="finest grid size per axis (2^k+1)")
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=1025,
+                    help="finest grid size per axis (2^k+1); under torchrun spell it --grid (torchrun treats --n as an abbreviation of its own options)")
     ap.add_argument("--dtype", default="f64", choices=["f32", "f64"])
     ap.add_argument("--cpu-n", type=int, default=257, help="grid of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=2)
