@@ -94,6 +94,8 @@ struct mg3d_s {
     int use_graphs;
     mg_graph_slot graphs[MG_GRAPH_SLOTS];
     double omega;   /* weight of MG_SMOOTHER_JACOBI */
+    int no_tail;         /* MG_B200_NO_TAIL: coarse levels as separate launches */
+    int full_correction; /* MG_B200_FULL_CORRECTION: correct both colours after prolongation inside a cycle */
 };
 
 #define PROF_BEGIN(mg, level, op) mg_prof_begin(&(mg)->prof, (mg)->stream, (level), (op), (mg)->launches)
@@ -454,6 +456,8 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
     mg->sweeps_per_pass = 1;
     mg->use_graphs = getenv("MG_B200_NO_GRAPH") ? 0 : 1;
     mg->omega = 6.0 / 7.0;
+    mg->no_tail = getenv("MG_B200_NO_TAIL") != NULL;
+    mg->full_correction = getenv("MG_B200_FULL_CORRECTION") != NULL;
     memcpy(mg->range, range, sizeof mg->range);
     mg->nlevels = mg_num_levels_for(n);
     mg->lv = (mg_level3d*)calloc((size_t)mg->nlevels, sizeof(mg_level3d));
@@ -1030,7 +1034,7 @@ static int vcycle_rec(mg3d_t* mg, int level, int v1, int v2)
     int st;
     mg_level3d* L0 = &mg->lv[level];
     if (L0->g.n <= MGK3D_TAIL_N && !L0->dist && mg->nlevels - level <= MGK3D_TAIL_MAX_LEVELS && mg->smoother != MG_SMOOTHER_JACOBI &&
-        !getenv("MG_B200_NO_TAIL")) {
+        !mg->no_tail) {
         /* the coarse tail: the whole recursion from here down in one launch of one CTA */
         mg_geom3d g[MGK3D_TAIL_MAX_LEVELS];
         mg_coef3d c[MGK3D_TAIL_MAX_LEVELS];
@@ -1051,7 +1055,7 @@ static int vcycle_rec(mg3d_t* mg, int level, int v1, int v2)
         if ((st = residual_restrict_level(mg, level, v1 > 0 && relax_overlaps(mg, level + 1)))) return st;
         if ((st = vcycle_rec(mg, level + 1, v1, v2))) return st;
         /* the colour-0 half of the correction is dead when a red-black post-smoothing sweep follows */
-        if ((st = interpolate_level(mg, level, 1, (v2 > 0 && mg->smoother != MG_SMOOTHER_JACOBI && !getenv("MG_B200_FULL_CORRECTION")) ? 2 : 3,
+        if ((st = interpolate_level(mg, level, 1, (v2 > 0 && mg->smoother != MG_SMOOTHER_JACOBI && !mg->full_correction) ? 2 : 3,
                                     v2 > 0 && relax_overlaps(mg, level))))
             return st;
     }

@@ -226,37 +226,8 @@ k_residual_restrict(const T* __restrict__ v, const T* __restrict__ f, mg_geom3d 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Interpolate (+ ApplyCorrection when add != 0).  Thread (i, y, zl) owns the fine pair x = 2i, 2i+1 of
-// row (y, zl): both live at half-index i, one in each colour array (coalesced, no divergence: x-parity
-// is per statement, (y,z) parity is uniform per row).
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_interpolate(T* __restrict__ fine, mg_geom3d gf, const T* __restrict__ coarse, mg_geom3d gc, int add_, int zl_lo)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // pair index: x = 2i, 2i+1
-    const int y = 1 + blockIdx.y * blockDim.y + threadIdx.y;
-    const int zl = zl_lo + blockIdx.z;
-    const int z = gf.z0 + zl;
-    if (y > gf.n - 2 || 2 * i > gf.n - 2) return;
-    const int oy = y & 1, oz = z & 1;
-    const int cy = y >> 1, czl = (z >> 1) - gc.z0;
-    auto C = [&](int dx, int dy, int dz) { return coarse[off3(gc, i + dx, cy + dy, czl + dz)]; };
-    const int c0 = (y + z) & 1;  // colour of the even-x point of the pair
-    const long long idx = (long long)zl * gf.plane + (long long)y * gf.hp + i;
-    if (i >= 1) {  // x = 2i even, interior
-        T* p = fine + (long long)c0 * gf.cstride + idx;
-        const T e = interp_point<T>(C, 0, oy, oz);
-        *p = add_ ? add(*p, e) : e;
-    }
-    if (2 * i + 1 <= gf.n - 2) {
-        T* p = fine + (long long)(c0 ^ 1) * gf.cstride + idx;
-        const T e = interp_point<T>(C, 1, oy, oz);
-        *p = add_ ? add(*p, e) : e;
-    }
-}
-
-// The same operator, organised by coarse cell: a thread owns the coarse cell (cx, cy) and marches along z;
+// Interpolate (+ ApplyCorrection when add != 0), N3/MultiGrid3D.cpp:186-335 and :649-676, organised by coarse
+// cell: a thread owns the coarse cell (cx, cy) and marches along z;
 // per cell it holds the 8 corner values in registers (the 4 upper corners become the next cell's lower
 // ones) and produces the 2x2x2 fine points (2cx+ox, 2cy+oy, 2cz+oz) with the reference's per-parity
 // formulas.  One coarse load per fine point instead of up to eight, no per-point 64-bit index arithmetic;
