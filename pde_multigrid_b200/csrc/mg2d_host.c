@@ -20,8 +20,19 @@ typedef struct {
     void* f;
 } mg_level2d;
 
+/* CUDA-graph cache of whole V-cycles (key = level, v1, v2): at 1025^2 a V(2,2) is ~60 dependent launches on
+   L2-resident fields, i.e. pure launch latency; the second call with a key captures the cycle, later calls replay it */
+#define MG2_GRAPH_SLOTS 4
+typedef struct {
+    int used, level, v1, v2, calls;
+    cudaGraphExec_t exec;
+    long long launches;
+} mg2_graph_slot;
+
 struct mg2d_s {
     int dtype, nlevels;
+    int use_graphs;
+    mg2_graph_slot graphs[MG2_GRAPH_SLOTS];
     cudaStream_t stream;
     mg_level2d* lv;
     void* arena;
@@ -81,6 +92,7 @@ int mg2d_create(mg2d_t** out, const int sz[2], const double range[4], const doub
     mg2d_t* mg = (mg2d_t*)calloc(1, sizeof *mg);
     if (!mg) return mg_fail(MG_ERR_NOMEM, "host allocation failed");
     mg->dtype = dtype;
+    mg->use_graphs = getenv("MG_B200_NO_GRAPH") ? 0 : 1;
     mg->nlevels = mg_num_levels_for(n);
     mg->lv = (mg_level2d*)calloc((size_t)mg->nlevels, sizeof(mg_level2d));
     if (!mg->lv) { free(mg); return mg_fail(MG_ERR_NOMEM, "host allocation failed"); }
@@ -122,7 +134,10 @@ int mg2d_create(mg2d_t** out, const int sz[2], const double range[4], const doub
 int mg2d_destroy(mg2d_t* mg)
 {
     if (!mg) return MG_OK;
-    if (mg->stream) { cudaStreamSynchronize(mg->stream); cudaStreamDestroy(mg->stream); }
+    if (mg->stream) cudaStreamSynchronize(mg->stream);
+    for (int i = 0; i < MG2_GRAPH_SLOTS; i++)
+        if (mg->graphs[i].used && mg->graphs[i].exec) cudaGraphExecDestroy(mg->graphs[i].exec);
+    if (mg->stream) cudaStreamDestroy(mg->stream);
     if (mg->arena) cudaFree(mg->arena);
     if (mg->d_scratch) cudaFree(mg->d_scratch);
     if (mg->h_out2) cudaFreeHost(mg->h_out2);
@@ -366,7 +381,39 @@ int mg2d_vcycle(mg2d_t* mg, int level, int v1, int v2)
     int st = check_level(mg, level);
     if (st) return st;
     if (v1 < 0 || v2 < 0) return mg_fail(MG_ERR_ARG, "negative sweep count");
-    return vcycle_rec(mg, level, v1, v2);
+    const long long per_cycle = 2LL * (v1 + v2) * (mg->nlevels - level);
+    if (!mg->use_graphs || mg->prof.enabled || per_cycle > 4096) return vcycle_rec(mg, level, v1, v2);
+    mg2_graph_slot* g = NULL;
+    for (int i = 0; i < MG2_GRAPH_SLOTS && !g; i++)
+        if (mg->graphs[i].used && mg->graphs[i].level == level && mg->graphs[i].v1 == v1 && mg->graphs[i].v2 == v2) g = &mg->graphs[i];
+    if (!g) {
+        for (int i = 0; i < MG2_GRAPH_SLOTS && !g; i++)
+            if (!mg->graphs[i].used) g = &mg->graphs[i];
+        if (!g) return vcycle_rec(mg, level, v1, v2); /* cache full: run eagerly */
+        memset(g, 0, sizeof *g);
+        g->used = 1; g->level = level; g->v1 = v1; g->v2 = v2;
+    }
+    if (++g->calls == 1) return vcycle_rec(mg, level, v1, v2); /* first call eager: kernel attributes, lazy loading */
+    if (!g->exec) {
+        const long long l0 = mg->launches;
+        cudaGraph_t graph = NULL;
+        MG_CUDA(cudaStreamBeginCapture(mg->stream, cudaStreamCaptureModeThreadLocal));
+        st = vcycle_rec(mg, level, v1, v2);
+        cudaError_t e = cudaStreamEndCapture(mg->stream, &graph);
+        g->launches = mg->launches - l0;
+        mg->launches = l0; /* nothing ran during the capture */
+        if (!st && e == cudaSuccess && graph) e = cudaGraphInstantiate(&g->exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (st || e != cudaSuccess || !g->exec) {
+            g->exec = NULL;
+            cudaGetLastError();
+            mg->use_graphs = 0; /* capture is not possible here: stay eager */
+            return st ? st : vcycle_rec(mg, level, v1, v2);
+        }
+    }
+    MG_CUDA(cudaGraphLaunch(g->exec, mg->stream));
+    mg->launches += g->launches;
+    return MG_OK;
 }
 
 /* FullMultiGridVCycle, N2/MultiGrid2D.cpp:296-312 */
