@@ -291,6 +291,20 @@ def main():
     ms_step_profiled = p0.elapsed_time(p1) / args.steps
     eng._call("profile", 0)
 
+    # ---- third figure (SURVEY.md 8d "norm pass accounting"): every cycle followed by the residual norm the parity
+    #      runs report (one extra read of v and f on the finest level + a 16-byte read-back), host clock ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.VCycle(0, NU1, NU2)
+        eng.residual_norm(0)
+    barrier()
+    ms_step_with_norm = (time.perf_counter() - t0) / args.steps * 1e3
+    if dist is not None:
+        t = torch.tensor([ms_step_with_norm], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step_with_norm = float(t.item())
+
     # ---- per-operator breakdown from the live event timers (this rank) ----
     import ctypes
     ops = {"relax": 0, "residual_restrict": 1, "interpolate_correct": 2, "other": 3}
@@ -388,7 +402,10 @@ def main():
             "residual_l2": {"before": r0[0], "after": r1[0]},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches), "halo_bytes_per_cycle_rank0": int(halo_bytes) // max(args.steps, 1),
-            "ms_per_step_profiled_pass": ms_step_profiled, "breakdown_ms_per_cycle": breakdown,
+            "ms_per_step_profiled_pass": ms_step_profiled,
+            "with_per_cycle_norm": {"ms_per_step": ms_step_with_norm, "value": 1e3 / ms_step_with_norm, "unit": "V-cycles/s",
+                                    "what": "V-cycle + residual_norm(0) per step, host clock (the norm is read back every cycle)"},
+            "breakdown_ms_per_cycle": breakdown,
         }
         print(json.dumps(line), flush=True)
     eng.close()

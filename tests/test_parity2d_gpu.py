@@ -136,6 +136,29 @@ def test_vcycle_history(mg, n, nu, dtype, rng_range):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_vcycle_full_size_config(mg, dtype):
+    """BASELINE.json configs[1] at its full size, 1025 x 1025, V(2,2): four cycles (eager, captured, two graph
+    replays) bit for bit against the oracle on every level, and the SURVEY.md 8c history of the reference
+    (9.637410504e+04 -> 2.626493724e+04, 1.122402051e+04, 8.076382287e+03 in float)."""
+    n = 1025
+    eng = mg.MultiGrid2D(n, dtype=dtype)
+    orcs = oracles(2, dtype, False, n)
+    hist = [eng.residual_norm(0)[0]]
+    for _ in range(4):
+        eng.VCycle(0, 2, 2)
+        hist.append(eng.residual_norm(0)[0])
+    for o in orcs:
+        for _ in range(4):
+            o.vcycle(0, 2, 2)
+        for l in range(eng.numGrids):
+            assert_bits_equal(eng.get_v(l), o.v(l), "v level %d" % l)
+    want = [9.637410504e+04, 2.626493724e+04, 1.122402051e+04, 8.076382287e+03]
+    for a, b in zip(hist, want):
+        assert abs(a - b) <= 2e-5 * b, (hist, want)
+    eng.close()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_fmg_and_mean_abs_error(mg, dtype):
     """FMG with the thesis parameters at n = 65 on [0,20]^2: the known answer of thesis Fig. 4.3
     (mean absolute error 5.32 at n = 65) and bit equality with the oracle."""
