@@ -3,12 +3,16 @@
 Two processes hold the slabs that mg3d_plan_level (the product's own partition arithmetic, called through the
 C ABI) assigns them; everything outside a slab is NaN.  They run V(2,2) cycles with numpy stand-ins for the
 kernels, restricted to the planes a rank owns, and exchange planes over gloo exactly where the C driver does:
-  * after every half-sweep: the just-updated colour's top plane up / bottom plane down (depth 1),
+  * after every half-sweep: the just-updated colour's top plane up / bottom plane down (depth 1) -- ONLY the points
+    of that colour travel, the other colour of the ghost plane keeps whatever it held,
   * before the fused residual+restrict: the two top planes up (the kernel reads v two planes below the slab),
   * after it: coarse f planes (distributed coarse level) or an all-gather (first agglomerated level),
-  * after prolongation+correction: fine v, depth 1 both ways.
-If a ghost depth or an exchange were missing, a NaN would reach an owned plane.  The owned planes must equal the
-same cycles run sequentially on the whole grid, bit for bit (RB Gauss-Seidel is partition-invariant)."""
+  * after prolongation+correction: fine v, depth 1 both ways -- and, as in the engine's V-cycle, the correction is
+    applied to the colour-1 points only and only colour 1 travels: the red half-sweep that follows overwrites every
+    interior colour-0 point without reading it.
+If a ghost depth or an exchange were missing, a NaN (or a stale value) would reach an owned plane.  The owned planes
+must equal the same cycles run sequentially on the whole grid WITH THE FULL CORRECTION, bit for bit (RB Gauss-Seidel
+is partition-invariant, and the colour-0 half of the correction is dead)."""
 import os
 import socket
 
@@ -72,7 +76,13 @@ def residual_restrict(v, f, cf, cv, clo, chi):
         cf[cz, 1:-1, 1:-1] = acc
 
 
-def interpolate_add(v, cv, lo, hi):
+def colour_mask(n, z, colour):
+    """points (y, x) of plane z whose colour (x + y + z) & 1 equals `colour`"""
+    y, x = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    return ((x + y + z) % 2) == colour
+
+
+def interpolate_add(v, cv, lo, hi, colour=None):
     n = v.shape[1]
     for z in range(lo, hi):
         cz = z // 2
@@ -83,7 +93,12 @@ def interpolate_add(v, cv, lo, hi):
         e = np.empty((n, n))
         e[:, 0::2] = py
         e[:, 1::2] = 0.5 * (py[:, :-1] + py[:, 1:])
-        v[z, 1:-1, 1:-1] += e[1:-1, 1:-1]
+        if colour is None:
+            v[z, 1:-1, 1:-1] += e[1:-1, 1:-1]
+        else:
+            m = colour_mask(n, z, colour)[1:-1, 1:-1]
+            blk = v[z, 1:-1, 1:-1]
+            blk[m] += e[1:-1, 1:-1][m]
 
 
 # ---- the driver's schedule ---------------------------------------------------------------------------
@@ -102,7 +117,7 @@ class Level:
 
 
 def exchange(L, arr, rank, world, depth_up, down, colour=None):
-    """colour is ignored (whole planes travel): a superset of what the engine sends."""
+    """colour None: whole planes; otherwise only that colour's points of the ghost planes are overwritten."""
     if not L.dist:
         return
     reqs = []
@@ -120,10 +135,19 @@ def exchange(L, arr, rank, world, depth_up, down, colour=None):
             reqs.append(dist.irecv(lo_ghost, rank - 1))
     for r in reqs:
         r.wait()
+
+    def put(z, plane):
+        if colour is None:
+            arr[z] = plane
+        else:
+            m = colour_mask(L.n, z, colour)
+            arr[z][m] = plane[m]
+
     if rank + 1 < world and down:
-        arr[L.b:L.b + 1] = up_ghost.numpy()
+        put(L.b, up_ghost.numpy()[0])
     if rank > 0 and depth_up:
-        arr[L.a - depth_up:L.a] = lo_ghost.numpy()
+        for k in range(depth_up):
+            put(L.a - depth_up + k, lo_ghost.numpy()[k])
 
 
 def relax(L, rank, world, nu):
@@ -134,7 +158,9 @@ def relax(L, rank, world, nu):
             exchange(L, L.v, rank, world, 1, 1, colour)
 
 
-def vcycle(levels, l, rank, world):
+def vcycle(levels, l, rank, world, engine_schedule=True):
+    """engine_schedule: colour-1-only correction (and exchange) as in mg3d_host.c::vcycle_rec; False = the reference's
+    full ApplyCorrection, used for the sequential run the slabs are compared with."""
     L = levels[l]
     relax(L, rank, world, NU)
     if l + 1 < len(levels):
@@ -158,10 +184,10 @@ def vcycle(levels, l, rank, world):
             top = torch.from_numpy(C.f[C.n - 1:C.n].copy())
             dist.broadcast(top, world - 1)
             C.f[C.n - 1] = top.numpy()[0]
-        vcycle(levels, l + 1, rank, world)
+        vcycle(levels, l + 1, rank, world, engine_schedule)
         lo, hi = L.interior()
-        interpolate_add(L.v, C.v, lo, hi)
-        exchange(L, L.v, rank, world, 1, 1)
+        interpolate_add(L.v, C.v, lo, hi, 1 if engine_schedule else None)
+        exchange(L, L.v, rank, world, 1, 1, 1 if engine_schedule else None)
     relax(L, rank, world, NU)
 
 
@@ -206,7 +232,7 @@ def test_slab_schedule_world2_gloo(mg, monkeypatch):
         L.v[...] = 0.0
         L.f[...] = 0.0
     for _ in range(CYCLES):
-        vcycle(ref_levels, 0, 0, 1)
+        vcycle(ref_levels, 0, 0, 1, engine_schedule=False)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = free_port()
