@@ -16,6 +16,16 @@
 // redundantly are never consumed beyond their validity).  Plane p-5 is then final and is written to the
 // OUTPUT field (out of place: neighbouring CTAs still need the old values of their halos).  Arithmetic per
 // point is relax_point of mg3d_device.cuh, so the result is bit-identical to four colour launches.
+//
+// MEASURED (1025^3, one B200): 13.0 ms per two-sweep pass in fp64 and 11.1 ms in fp32, against 8.4 / 4.5 ms for the
+// four colour launches it replaces -- NOT the default.  The pass moves 33 GB instead of 51.6 GB, but every stencil
+// value is a shared-memory load (7 LDS + 1 STS per update, four stages per plane): the LSU data pipe saturates, the
+// same limiter the residual+restrict kernel had before its register tiling (mg3d_rr_tma.cu).  Next step, worked
+// out but not built: register tiling of this pipeline -- thread (i, y) computes all four stages of its own column,
+// so D/U, the own-position O-or-E and (with two rows per thread) one of N/S are registers of the thread's own
+// z-windows (raw colour 1: planes p-1..p+1, stage 1: p-3..p, stage 2: p-4..p-1, stage 3: p-5..p-3); 3 LDS + 1 STS
+// per update through single-plane exchange buffers, raw v and f read by plain coalesced loads.  In fp64 the
+// ceiling is modest (~3.6 ms of fp64 pipe + ~4.5 ms of issue slots per pass).
 #include "mg3d_device.cuh"
 #include "mg_tma.cuh"
 
@@ -158,13 +168,8 @@ k_relax_fused2(const __grid_constant__ FusedMaps maps, T* __restrict__ v_out, mg
             if (on[s]) ring[sb[d] + col * SUBS + cc[k][s]] = relax_point<T, FAST>(O[s], E[s], N[s], S[s], D[s], U[s], F[s], c);
     };
 
-    // STATUS (round 1, 1025^3 fp64): 14.0 ms per pass against 8.4 ms for the four colour launches it replaces.  It
-    // moves the bytes it should (ncu: 24.6 GB read + 8.7 GB written per pass, 33 GB against 51.6 GB) but it is
-    // latency-bound: the 8-slot ring fills the SM's shared memory (221 KB), so there is one CTA per SM and only
-    // the planes p+1, p+2 can be in flight; a TMA plane (4 boxes of 24 rows x 288 B) issued at the end of iteration p
-    // has to land within one iteration.  Neither fewer instructions (hoisted ring offsets) nor more ILP (4 slots per
-    // thread) changed the time.  Next steps: per-colour rings with different phases to free slots for a deeper
-    // prefetch, or 2-CTA clusters sharing halos through DSMEM.  Kept opt-in (MG_SMOOTHER_FUSED); bit-identical.
+    // (Measured status and the planned register-tiled successor: file header.  Neither fewer instructions -- hoisted
+    // ring offsets -- nor more ILP -- 4 slots per thread -- changed the time of this shared-memory version.)
     for (int p = pb; p <= plast + 1; p++) {
         if (p <= plast) mbar_wait(&bars[(p - pb) & (NS - 1)], ((p - pb) / NS) & 1);
         int sb[7];  // element offset of the slot of plane p-j
