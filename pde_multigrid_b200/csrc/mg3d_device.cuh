@@ -32,6 +32,27 @@ __device__ __forceinline__ long long off3(const mg_geom3d& g, int x, int y, int 
     return (long long)c * g.cstride + (long long)zl * g.plane + (long long)y * g.hp + (x >> 1);
 }
 
+// block-wide {sum, max} of one double pair per thread: warp shuffles, then one warp over the per-warp results
+// (deterministic for a given block size); sh holds 64 doubles.  The result is valid in thread 0.
+__device__ __forceinline__ void block_sum_max(double& s, double& m, double* sh)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    if (l == 0) { sh[w] = s; sh[32 + w] = m; }
+    __syncthreads();
+    if (w == 0) {
+        s = (l < nw) ? sh[l] : 0.0;
+        m = (l < nw) ? sh[32 + l] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        }
+    }
+}
+
 // N3/MultiGrid3D.cpp:532 -- left-to-right sum of the six weighted neighbours, minus f*hx2*hy2*hz2,
 // divided by 2*(hy2*hz2 + hx2*hz2 + hx2*hy2).  O/E = x-1/x+1, N/S = y-1/y+1, D/U = z-1/z+1.
 // FAST: the divisor is 6*2^e (cubic grid, power-of-two h: the reference problem) -> correctly rounded

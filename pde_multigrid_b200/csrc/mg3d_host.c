@@ -83,7 +83,7 @@ struct mg3d_s {
     mg_p2p p2p;
     mg_level3d* lv;
     void* arena;
-    double* d_scratch; /* 2*MGK_NORM_BLOCKS partials + 2 outputs */
+    double* d_scratch; /* 2*MGK_NORM_MAX_PARTS partials + 2 outputs */
     double* d_tables;  /* 3*n0 doubles: sin tables of InitF */
     double* h_out2;    /* pinned */
     void* staging;     /* dense device staging buffer for host<->device field copies */
@@ -385,7 +385,7 @@ static int p2p_setup(mg3d_t* mg, size_t arena_bytes)
     }
     free(all);
     /* every rank must agree on the transport: all-reduce the success bit */
-    double* d2 = mg->d_scratch + 2 * MGK_NORM_BLOCKS;
+    double* d2 = mg->d_scratch + 2 * MGK_NORM_MAX_PARTS;
     double h2[2] = {ok ? 0.0 : 1.0, 0.0};
     MG_CUDA(cudaMemcpyAsync(d2, h2, sizeof h2, cudaMemcpyHostToDevice, mg->stream));
     if ((st = mg_comm_allreduce_sum_max(mg->comm, d2, mg->stream))) return st;
@@ -404,7 +404,7 @@ static void p2p_teardown(mg3d_t* mg)
         free(q->nb_off[k]); free(q->nb_geom[k]); free(q->nb_own[k]);
     }
     if (mg->comm && q->flags) { /* nobody unmaps or frees while a neighbour may still be pushing */
-        double* d2 = mg->d_scratch + 2 * MGK_NORM_BLOCKS;
+        double* d2 = mg->d_scratch + 2 * MGK_NORM_MAX_PARTS;
         if (mg_comm_allreduce_sum_max(mg->comm, d2, mg->stream) == MG_OK) cudaStreamSynchronize(mg->stream);
     }
     if (q->flags) cudaFree(q->flags);
@@ -491,7 +491,7 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
         if (level_fields(L) == 3) { L->vbuf[1] = p; p += field_bytes(L, dtype); }
     }
     if (cudaStreamCreateWithFlags(&mg->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc((void**)&mg->d_scratch, (2 * MGK_NORM_BLOCKS + 2) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&mg->d_scratch, (2 * MGK_NORM_MAX_PARTS + 2) * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&mg->d_tables, 3 * (size_t)n * sizeof(double)) != cudaSuccess ||
         cudaMallocHost((void**)&mg->h_out2, 2 * sizeof(double)) != cudaSuccess) {
         int code = mg_fail(MG_ERR_CUDA, "stream/scratch setup failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -898,14 +898,28 @@ int mg3d_residual(mg3d_t* mg, int level, void* host_out)
     return st;
 }
 
+static void coarse_share(const mg3d_t* mg, int fine_level, int* czl_lo, int* czl_hi);
+
 int mg3d_residual_norm(mg3d_t* mg, int level, double* l2, double* linf)
 {
     int st = check_level(mg, level);
     if (st) return st;
     mg_level3d* L = &mg->lv[level];
-    double* out2 = mg->d_scratch + 2 * MGK_NORM_BLOCKS;
-    MG_LAUNCH(mg->launches, mgk3d_residual_norm(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, mg->mode == MG_CORRECTED,
-                                                L->own_lo, L->own_hi, mg->d_scratch, out2));
+    double* out2 = mg->d_scratch + 2 * MGK_NORM_MAX_PARTS;
+    int k = -2;
+    if (L->has_tma && mg->smoother != MG_SMOOTHER_COLOUR && level + 1 < mg->nlevels) {
+        /* large levels: the staging of the fused residual+restrict kernel; the coarse planes this rank restricts to
+           lie over exactly the fine planes it owns */
+        int clo, chi;
+        coarse_share(mg, level, &clo, &chi);
+        k = mgk3d_residual_norm_tma(mg->stream, mg->dtype, L->tmap_rr[L->cur][0], L->tmap_rr[L->cur][1], L->f, L->g, L->c,
+                                    mg->mode == MG_CORRECTED, mg->lv[level + 1].g, clo, chi, mg->d_scratch, MGK_NORM_MAX_PARTS, out2);
+        if (k == -1) return mg_fail(MG_ERR_CUDA, "residual norm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (k > 0) mg->launches += k;
+    }
+    if (k == -2)
+        MG_LAUNCH(mg->launches, mgk3d_residual_norm(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, mg->mode == MG_CORRECTED,
+                                                    L->own_lo, L->own_hi, mg->d_scratch, out2));
     if (L->dist && (st = mg_comm_allreduce_sum_max(mg->comm, out2, mg->stream))) return st;
     MG_CUDA(cudaMemcpyAsync(mg->h_out2, out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, mg->stream));
     MG_CUDA(cudaStreamSynchronize(mg->stream));

@@ -103,25 +103,6 @@ __global__ void k_residual(const T* __restrict__ v, const T* __restrict__ f, T* 
 // Residual norms: sum r^2 (fp64) and max |r|, residual recomputed on the fly, warp-shuffle
 // reduction, one partial per block (deterministic), finished by k_norm_final.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void block_reduce_sum_max(double& s, double& m, double* sh)
-{
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    }
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
-    if (l == 0) { sh[w] = s; sh[32 + w] = m; }
-    __syncthreads();
-    if (w == 0) {
-        s = (l < nw) ? sh[l] : 0.0;
-        m = (l < nw) ? sh[32 + l] : 0.0;
-        for (int o = 16; o > 0; o >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-        }
-    }
-}
-
 template <typename T, bool FAST>
 __global__ void __launch_bounds__(256)
 k_residual_norm(const T* __restrict__ v, const T* __restrict__ f, mg_geom3d g, Coef3<T> c, int corrected, int zl_lo,
@@ -142,7 +123,7 @@ k_residual_norm(const T* __restrict__ v, const T* __restrict__ f, mg_geom3d g, C
             m = fmax(m, fabs(rd));
         }
     }
-    block_reduce_sum_max(s, m, sh);
+    block_sum_max(s, m, sh);
     if (threadIdx.x == 0) { part[blockIdx.x] = s; part[gridDim.x + blockIdx.x] = m; }
 }
 
@@ -154,7 +135,7 @@ __global__ void k_norm_final(const double* __restrict__ part, int nparts, double
         s += part[i];
         m = fmax(m, part[nparts + i]);
     }
-    block_reduce_sum_max(s, m, sh);
+    block_sum_max(s, m, sh);
     if (threadIdx.x == 0) { out2[0] = s; out2[1] = m; }
 }
 
@@ -440,6 +421,13 @@ int mgk3d_relax_colour(cudaStream_t s, int dtype, void* v, const void* f, mg_geo
 {
     return DISPATCH(dtype, relax_colour_t<float>(s, (float*)v, (const float*)f, g, c, colour, zl_lo, zl_hi - zl_lo, 1),
                     relax_colour_t<double>(s, (double*)v, (const double*)f, g, c, colour, zl_lo, zl_hi - zl_lo, 1));
+}
+
+/* {sum, max} of nparts partial pairs (part[0..nparts) sums, part[nparts..2 nparts) maxima) into out2 */
+int mgk_norm_final(cudaStream_t s, const double* part, int nparts, double* out2)
+{
+    k_norm_final<<<1, 256, 0, s>>>(part, nparts, out2);
+    return launch_ok();
 }
 
 /* weighted-Jacobi update of one colour array on local planes [zl_lo, zl_hi): see k_jacobi_colour */

@@ -48,11 +48,14 @@ template <typename T> struct VBox {
     static constexpr int W = (CXT + A + 1 + A - 1) / A * A;       // 36 doubles / 40 floats
 };
 
-template <typename T, bool FAST>
+// NORM = true turns the kernel into the residual-norm pass (sum r^2 in fp64 and max |r| over the fine planes 2cz, 2cz+1 of
+// the chunk's coarse planes -- every fine plane exactly once over the grid): same staging and register tiling, no
+// residual ring, no restriction, one partial per CTA in part[0 .. nblocks) / part[nblocks .. 2 nblocks).
+template <typename T, bool FAST, bool NORM>
 __global__ void __launch_bounds__(NT, 2)
 k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid_constant__ CUtensorMap map_c1,
                         const T* __restrict__ f, mg_geom3d gf, Coef3<T> c, int corrected, T* __restrict__ cf,
-                        T* __restrict__ cv, mg_geom3d gc, int czl_lo, int czl_hi, int zchunk)
+                        T* __restrict__ cv, mg_geom3d gc, int czl_lo, int czl_hi, int zchunk, double* __restrict__ part)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int A = VBox<T>::A, W = VBox<T>::W;
@@ -177,10 +180,11 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
     // residuals of the thread's column by [row*2 + x parity]: planes 2k-1, 2k, 2k+1
     T rm[4] = {T(0), T(0), T(0), T(0)}, rc[4], rp[4];
     T fcur[5], fnext[5];
+    double nsum = 0.0, nmax = 0.0;  // NORM: this thread's share
 
     // residual of fine plane z (ZP = z & 1) for the thread's column and the edge pass; v ring slots of planes
     // z-1, z, z+1 must have landed.  Shifts the register window by one plane at the end.
-    auto plane = [&](int z, auto ZPc, T (&res)[4]) {
+    auto plane = [&](int z, auto ZPc, T (&res)[4], bool count) {
         constexpr int ZP = decltype(ZPc)::value;
         const T* sD = slot_of(z - 1);
         const T* sC = slot_of(z);
@@ -204,6 +208,16 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
                 const bool ok = (vmask & (r ? F_YB : F_YA)) && (vmask & (q ? F_X1 : F_X0));
                 res[r * 2 + q] = ok ? val : T(0);
             }
+        if constexpr (NORM) {
+            if (count) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const double rd = (double)res[j];
+                    nsum += rd * rd;
+                    nmax = fmax(nmax, fabs(rd));
+                }
+            }
+        } else {
         // what the neighbours' restrictions read: the odd-x points (thread lane+1) and row ya+1 (warp w+1)
         rz[T2 + 1] = res[1];                         // (ya,   2hi+1): parity array 0 at lane+1
         rz[T2 + 2 * RCOLS + 1] = res[3];             // (ya+1, 2hi+1)
@@ -216,6 +230,7 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
                 val = residual_point<T, FAST>(sC[o - 1 + q], sC[o + q], sC[o - W], sC[o + W], sD[o], sU[o], sC[t_own], fcur[4], c, corrected);
             }
             if (fl & (q ? F_TACT : F_TST0)) rz[t_r + (q ? 0 : RCOLS - 1)] = val;
+        }
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) { vm[j] = vc[j]; vc[j] = vu[j]; }
@@ -239,7 +254,7 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
         vm[0] = s0[Pa]; vm[1] = s0[VSUB_STRIDE + Pa]; vm[2] = s0[Pb]; vm[3] = s0[VSUB_STRIDE + Pb];
         vc[0] = s1[Pa]; vc[1] = s1[VSUB_STRIDE + Pa]; vc[2] = s1[Pb]; vc[3] = s1[VSUB_STRIDE + Pb];
     }
-    plane(zf0, std::integral_constant<int, 1>{}, rm);
+    plane(zf0, std::integral_constant<int, 1>{}, rm, false);  // counted by the chunk below (or a ghost plane)
     __syncthreads();  // v slot of plane zf0-1 free
     if (tid == 0 && zf0 + RING - 1 <= zf1 + 1) issue(zf0 + RING - 1);
 
@@ -247,15 +262,16 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
     for (int z = zf0 + 1; z < zf1; z += 2) {
         step_f(z);
         wait_plane(z + 1);
-        plane(z, std::integral_constant<int, 0>{}, rc);
+        plane(z, std::integral_constant<int, 0>{}, rc, true);
         step_f(z + 1);
         wait_plane(z + 2);
-        plane(z + 1, std::integral_constant<int, 1>{}, rp);
+        plane(z + 1, std::integral_constant<int, 1>{}, rp, true);
         __syncthreads();  // residual planes z-1, z, z+1 complete in shared memory; v slots of planes z-1, z free
         if (tid == 0) {
             if (z + RING - 1 <= zf1 + 1) issue(z + RING - 1);
             if (z + RING <= zf1 + 1) issue(z + RING);
         }
+        if constexpr (NORM) continue;
         const int cz = z >> 1, czl = cz - gc.z0;
         if (fl & F_CIN) {
             T out = T(0);  // boundary: injection of the zero boundary residual (N3/MultiGrid3D.cpp:113-119, :705)
@@ -281,6 +297,16 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
         for (int j = 0; j < 4; j++) rm[j] = rp[j];
         __syncthreads();  // the 3-slot residual ring: plane z-1 is overwritten by plane z+2
     }
+    if constexpr (NORM) {
+        __shared__ double sh[64];
+        block_sum_max(nsum, nmax, sh);
+        if (tid == 0) {
+            const unsigned nb = gridDim.x * gridDim.y * gridDim.z;
+            const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+            part[bid] = nsum;
+            part[nb + bid] = nmax;
+        }
+    }
 }
 
 template <typename T>
@@ -290,14 +316,23 @@ size_t smem_bytes_t()
     return RING * 2 * vsub + (size_t)RRING * RROWS * 2 * RCOLS * sizeof(T) + RING * sizeof(uint64_t);
 }
 
-template <typename T, bool FAST>
+static void tile_grid(const mg_geom3d& gc, int czl_lo, int czl_hi, dim3& grid, int& zchunk)
+{
+    const int planes = czl_hi - czl_lo;
+    const int tiles_xy = ((gc.n + CXT - 1) / CXT) * ((gc.n + CYT - 1) / CYT);
+    zchunk = 32;
+    while (zchunk > 8 && (long long)tiles_xy * ((planes + zchunk - 1) / zchunk) < 148 * 4) zchunk /= 2;
+    grid = dim3((gc.n + CXT - 1) / CXT, (gc.n + CYT - 1) / CYT, (planes + zchunk - 1) / zchunk);
+}
+
+template <typename T, bool FAST, bool NORM>
 int launch_k(cudaStream_t s, const CUtensorMap& m0, const CUtensorMap& m1, const T* f, mg_geom3d gf, mg_coef3d c, int corrected, T* cf,
-             T* cv, mg_geom3d gc, int czl_lo, int czl_hi, dim3 grid, int zchunk)
+             T* cv, mg_geom3d gc, int czl_lo, int czl_hi, dim3 grid, int zchunk, double* part)
 {
     const size_t smem = smem_bytes_t<T>();
-    static bool attr = (cudaFuncSetAttribute(k_residual_restrict_tma<T, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_t<T>()), true);
+    static bool attr = (cudaFuncSetAttribute(k_residual_restrict_tma<T, FAST, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_t<T>()), true);
     (void)attr;
-    k_residual_restrict_tma<T, FAST><<<grid, NT, smem, s>>>(m0, m1, f, gf, narrow<T>(c), corrected, cf, cv, gc, czl_lo, czl_hi, zchunk);
+    k_residual_restrict_tma<T, FAST, NORM><<<grid, NT, smem, s>>>(m0, m1, f, gf, narrow<T>(c), corrected, cf, cv, gc, czl_lo, czl_hi, zchunk, part);
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -307,16 +342,31 @@ int launch(cudaStream_t s, const void* tmap_c0, const void* tmap_c1, const T* f,
 {
     if (czl_hi <= czl_lo) return 0;
     static_assert(NT == CXT * CYT, "one coarse point per thread");
-    const int planes = czl_hi - czl_lo;
-    const int tiles_xy = ((gc.n + CXT - 1) / CXT) * ((gc.n + CYT - 1) / CYT);
-    int zchunk = 32;
-    while (zchunk > 8 && (long long)tiles_xy * ((planes + zchunk - 1) / zchunk) < 148 * 4) zchunk /= 2;
-    dim3 grid((gc.n + CXT - 1) / CXT, (gc.n + CYT - 1) / CYT, (planes + zchunk - 1) / zchunk);
+    dim3 grid;
+    int zchunk;
+    tile_grid(gc, czl_lo, czl_hi, grid, zchunk);
     CUtensorMap m0, m1;
     memcpy(&m0, tmap_c0, sizeof m0);
     memcpy(&m1, tmap_c1, sizeof m1);
-    if (c.fast_h) return launch_k<T, true>(s, m0, m1, f, gf, c, corrected, cf, cv, gc, czl_lo, czl_hi, grid, zchunk);
-    return launch_k<T, false>(s, m0, m1, f, gf, c, corrected, cf, cv, gc, czl_lo, czl_hi, grid, zchunk);
+    if (c.fast_h) return launch_k<T, true, false>(s, m0, m1, f, gf, c, corrected, cf, cv, gc, czl_lo, czl_hi, grid, zchunk, nullptr);
+    return launch_k<T, false, false>(s, m0, m1, f, gf, c, corrected, cf, cv, gc, czl_lo, czl_hi, grid, zchunk, nullptr);
+}
+
+template <typename T>
+int launch_norm(cudaStream_t s, const void* tmap_c0, const void* tmap_c1, const T* f, mg_geom3d gf, mg_coef3d c, int corrected,
+                mg_geom3d gc, int czl_lo, int czl_hi, double* part, int max_parts, int* nparts)
+{
+    dim3 grid;
+    int zchunk;
+    tile_grid(gc, czl_lo, czl_hi, grid, zchunk);
+    const long long nb = (long long)grid.x * grid.y * grid.z;
+    if (czl_hi <= czl_lo || nb > max_parts) return -2;  // the caller takes the plain kernel
+    *nparts = (int)nb;
+    CUtensorMap m0, m1;
+    memcpy(&m0, tmap_c0, sizeof m0);
+    memcpy(&m1, tmap_c1, sizeof m1);
+    if (c.fast_h) return launch_k<T, true, true>(s, m0, m1, f, gf, c, corrected, nullptr, nullptr, gc, czl_lo, czl_hi, grid, zchunk, part);
+    return launch_k<T, false, true>(s, m0, m1, f, gf, c, corrected, nullptr, nullptr, gc, czl_lo, czl_hi, grid, zchunk, part);
 }
 
 }  // namespace
@@ -328,4 +378,20 @@ extern "C" int mgk3d_residual_restrict_tma(cudaStream_t s, int dtype, const void
     if (dtype == 0)
         return launch<float>(s, tmap_v_c0, tmap_v_c1, (const float*)f, gf, c, corrected, (float*)coarse_f, (float*)coarse_v, gc, czl_lo, czl_hi);
     return launch<double>(s, tmap_v_c0, tmap_v_c1, (const double*)f, gf, c, corrected, (double*)coarse_f, (double*)coarse_v, gc, czl_lo, czl_hi);
+}
+
+/* residual norm of the fine planes under the coarse planes [czl_lo, czl_hi) with the staging of the kernel above: partials into
+   scratch[0 .. 2*nparts), then {sum r^2, max |r|} into out2.  Returns -2 (nothing launched) when the tiling needs more
+   than max_parts partials. */
+extern "C" int mgk3d_residual_norm_tma(cudaStream_t s, int dtype, const void* tmap_v_c0, const void* tmap_v_c1, const void* f,
+                                       mg_geom3d gf, mg_coef3d c, int corrected, mg_geom3d gc, int czl_lo, int czl_hi,
+                                       double* scratch, int max_parts, double* out2)
+{
+    int nparts = 0;
+    const int k = dtype == 0
+        ? launch_norm<float>(s, tmap_v_c0, tmap_v_c1, (const float*)f, gf, c, corrected, gc, czl_lo, czl_hi, scratch, max_parts, &nparts)
+        : launch_norm<double>(s, tmap_v_c0, tmap_v_c1, (const double*)f, gf, c, corrected, gc, czl_lo, czl_hi, scratch, max_parts, &nparts);
+    if (k < 0) return k;
+    const int k2 = mgk_norm_final(s, scratch, nparts, out2);
+    return k2 < 0 ? -1 : k + k2;
 }

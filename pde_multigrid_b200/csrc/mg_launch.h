@@ -84,6 +84,14 @@ int mgk3d_residual(cudaStream_t s, int dtype, const void* v, const void* f, void
 /* partial sums of r^2 and max|r| over local planes [zl_lo, zl_hi), residual computed on the fly;
    out2 = {sum, max} (device doubles), scratch >= 2*MGK_NORM_BLOCKS doubles */
 #define MGK_NORM_BLOCKS 1184
+#define MGK_NORM_MAX_PARTS 32768 /* partial pairs the scratch array of a handle has room for */
+int mgk_norm_final(cudaStream_t s, const double* part, int nparts, double* out2);
+/* the same norm with the TMA staging and register tiling of mgk3d_residual_restrict_tma (levels that have tensor maps);
+   gc = geometry of the next coarser level, [czl_lo, czl_hi) = the coarse planes over the fine planes to be covered.
+   Returns -2 without launching when more than max_parts partials would be needed. */
+int mgk3d_residual_norm_tma(cudaStream_t s, int dtype, const void* tmap_v_c0, const void* tmap_v_c1, const void* f,
+                            mg_geom3d gf, mg_coef3d c, int corrected, mg_geom3d gc, int czl_lo, int czl_hi,
+                            double* scratch, int max_parts, double* out2);
 int mgk3d_residual_norm(cudaStream_t s, int dtype, const void* v, const void* f, mg_geom3d g, mg_coef3d c,
                         int corrected, int zl_lo, int zl_hi, double* scratch, double* out2);
 /* coarse = Restrict(fine) on coarse local planes [czl_lo, czl_hi) */
