@@ -248,6 +248,32 @@ def test_smoother_variants_are_bit_identical(mg, n, dtype):
     assert_bits_equal(outs[0], outs[1], "smoother variants")
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,nu2", [(65, 2), (257, 1), (257, 2)])
+def test_colour1_only_correction_is_exact(mg, monkeypatch, n, nu2, dtype):
+    """Inside a V-cycle the engine corrects only the colour-1 points after the prolongation (the red half-sweep that
+    follows overwrites every interior colour-0 point unread).  MG_B200_FULL_CORRECTION=1 switches that off: both
+    engines must leave the same bits on every level."""
+    rng = np.random.default_rng(4242)
+    v0 = random_field(rng, (n,) * 3, dtype)
+    f0 = random_field(rng, (n,) * 3, dtype)
+    outs = []
+    for full in (False, True):
+        if full:
+            monkeypatch.setenv("MG_B200_FULL_CORRECTION", "1")
+        else:
+            monkeypatch.delenv("MG_B200_FULL_CORRECTION", raising=False)
+        eng = mg.MultiGrid3D(n, RANGES[1], dtype=dtype, residual_mode=mg.MG_CORRECTED)
+        eng.set_v(0, v0)
+        eng.set_f(0, f0)
+        for _ in range(3):  # eager, captured, replayed
+            eng.VCycle(0, 2, nu2)
+        outs.append([eng.get_v(l) for l in range(eng.numGrids)])
+        eng.close()
+    for l, (a, b) in enumerate(zip(*outs)):
+        assert_bits_equal(a, b, "level %d" % l)
+
+
 # ---- temporally blocked smoother (two sweeps per HBM pass) ----------------------------------------
 
 @pytest.mark.parametrize("rng_range", RANGES)
