@@ -173,7 +173,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "3D Poisson V(2,2) cycles/s", "value": value, "unit": "V-cycles/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 / scale,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D Poisson %d^3 fp64 V(2,2), reference problem (BASELINE.json configs[3])" % args.n,
+        "config": {"workload": "3D Poisson %d^3 fp64 V(%d,%d), reference problem (BASELINE.json configs[3]), "
+                               "sign-corrected residual" % (args.n, NU1, NU2),
                    "sample_grid": n_sample, "host_cpu": model, "host_cores": cores},
         "grid_point_updates_per_s": updates_per_cycle(n_sample) / sec,
         "cpu_baseline": {"value": value, "unit": "V-cycles/s", "cores": 1, "kind": kind, "sample": sample},
