@@ -55,7 +55,8 @@ class Grid2D
 		void PrintGrid_v(int logfd) { dump(logfd, h_v); }
 		void PrintGrid_f(int logfd) { dump(logfd, h_f); }
 		void PrintResidual(int, float*, int) {}
-		double MeanAbsError() const // PrintMeanAbsoluteError of the CUDA twin, C2/Grid2D.cu:123-154
+		void PrintMeanAbsoluteError() { printf("MeanAbsoluteError: %f\n", MeanAbsError()); } // CUDA twin, C2/Grid2D.cu:123-154
+		double MeanAbsError() const
 		{
 			double tot = 0;
 			long cnt = 0;

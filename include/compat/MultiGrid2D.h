@@ -21,6 +21,13 @@ class MultiGrid2D
 			InitA(_A, A_size, alfa_);
 			InitGrids(finestGridSizeXY, range);
 		}
+		/* the CUDA twin's constructor takes the (square) size as a scalar, CUDA_TESI/CUDA Lyapunov 2D/MultiGrid2D.h:16 */
+		MultiGrid2D(int finestGridSize, float range[], float* _A, int A_sizeX, int alfa_)
+		{
+			int s[2] = {finestGridSize, finestGridSize};
+			InitA(_A, A_sizeX, alfa_);
+			InitGrids(s, range);
+		}
 		~MultiGrid2D()
 		{
 			for (int i = 0; i < numGrids; i++) delete grids2D[i];
@@ -87,6 +94,7 @@ class MultiGrid2D
 		void PrintAllGrids_v() { int fd = mg_compat_open_log("log/log_v.txt"); for (int i = 0; i < numGrids; i++) grids2D[i]->PrintGrid_v(fd); }
 		void PrintAllGrids_f() { int fd = mg_compat_open_log("log/log_f.txt"); for (int i = 0; i < numGrids; i++) grids2D[i]->PrintGrid_f(fd); }
 		void PrintResidual(int) {}
+		void PrintMeanAbsoluteError() { grids2D[0]->PrintMeanAbsoluteError(); } // CUDA twin, C2/MultiGrid2D.cu:234-237
 
 	private:
 		int level_of(Grid2D* g)
