@@ -18,8 +18,6 @@ import pytest
 
 from util import assert_bits_equal
 
-pytestmark = pytest.mark.gpu
-
 N = 1025
 
 
@@ -32,6 +30,7 @@ def test_closed_form_matches_survey_values():
     assert abs(closed_form_r0(129) - 1.515971236007382e+04) < 1e-9 * 1.5e4
 
 
+@pytest.mark.gpu
 def test_full_size_residual_history(mg):
     eng = mg.MultiGrid3D(N, dtype=np.float64, residual_mode=mg.MG_CORRECTED)
     r0 = eng.residual_norm(0)[0]
@@ -47,6 +46,7 @@ def test_full_size_residual_history(mg):
     eng.close()
 
 
+@pytest.mark.gpu
 def test_full_size_reference_residual_diverges_like_the_reference(mg):
     eng = mg.MultiGrid3D(N, dtype=np.float64, residual_mode=mg.MG_REF_COMPAT)
     r0 = eng.residual_norm(0)[0]
@@ -56,6 +56,7 @@ def test_full_size_reference_residual_diverges_like_the_reference(mg):
     eng.close()
 
 
+@pytest.mark.gpu
 def test_full_size_linearity_and_kernel_variants(mg):
     """One pass over three engines: default kernels with f, default kernels with 2 f, plain kernels with f."""
     a = mg.MultiGrid3D(N, dtype=np.float64, residual_mode=mg.MG_CORRECTED)
