@@ -10,6 +10,9 @@ kernels, restricted to the planes a rank owns, and exchange planes over gloo exa
   * after prolongation+correction: fine v, depth 1 both ways -- and, as in the engine's V-cycle, the correction is
     applied to the colour-1 points only and only colour 1 travels: the red half-sweep that follows overwrites every
     interior colour-0 point without reading it.
+The weighted-Jacobi option runs through the same test with its own slab schedule (new colour 0 into a scratch array whose
+roles alternate with v, colour 1 in place, per-colour exchanges of whichever array holds the new values, copy back of the
+owned planes and the nearest ghosts after an odd number of sweeps) against the whole-grid definition of the sweep.
 If a ghost depth or an exchange were missing, a NaN (or a stale value) would reach an owned plane.  The owned planes
 must equal the same cycles run sequentially on the whole grid WITH THE FULL CORRECTION, bit for bit (RB Gauss-Seidel
 is partition-invariant, and the colour-0 half of the correction is dead)."""
@@ -24,6 +27,7 @@ import torch.multiprocessing as mp
 
 N = 65
 NU = 2
+NU_J = 3  # odd: every Jacobi smoothing call ends on the scratch array and copies back
 CYCLES = 2
 
 
@@ -158,11 +162,74 @@ def relax(L, rank, world, nu):
             exchange(L, L.v, rank, world, 1, 1, colour)
 
 
-def vcycle(levels, l, rank, world, engine_schedule=True):
+OMEGA = 6.0 / 7.0
+
+
+def jacobi_colour(dst, own, oth, f, colour, lo, hi):
+    """k_jacobi_colour on planes [lo, hi): the points of `colour` become old + omega*(gs - old), gs from the values
+    `oth` holds at the six neighbours; non-interior points are copied when dst is not own."""
+    n = dst.shape[1]
+    h2 = (1.0 / (n - 1)) ** 2
+    for z in range(lo, hi):
+        m = colour_mask(n, z, colour)
+        if dst is not own:
+            dst[z][m] = own[z][m]
+        if z < 1 or z > n - 2:
+            continue
+        gs = (oth[z, 1:-1, :-2] + oth[z, 1:-1, 2:] + oth[z, :-2, 1:-1] + oth[z, 2:, 1:-1] + oth[z - 1, 1:-1, 1:-1] +
+              oth[z + 1, 1:-1, 1:-1] - f[z, 1:-1, 1:-1] * h2) / 6.0
+        old = own[z, 1:-1, 1:-1]
+        new = old + OMEGA * (gs - old)
+        mi = m[1:-1, 1:-1]
+        blk = dst[z, 1:-1, 1:-1]
+        blk[mi] = new[mi]
+
+
+def relax_jacobi(L, rank, world, nu):
+    """mg3d_host.c::relax_jacobi_level: new colour 0 into a scratch array, colour 1 in place, scratch and v swap roles
+    every sweep; per-colour halo exchanges; an odd count ends with a copy back of the owned planes and the nearest ghost
+    on each side only."""
+    if not hasattr(L, "scratch"):
+        L.scratch = np.full((L.n,) * 3, np.nan)
+    cur = L.v
+    for _ in range(nu):
+        nxt = L.scratch if cur is L.v else L.v
+        jacobi_colour(nxt, cur, L.v, L.f, 0, L.a, L.b)    # colour-1 neighbours always live in v
+        jacobi_colour(L.v, L.v, cur, L.f, 1, L.a, L.b)    # in place; colour-0 neighbours = the OLD ones
+        cur = nxt
+        exchange(L, cur, rank, world, 1, 1, 0)
+        exchange(L, L.v, rank, world, 1, 1, 1)
+    if cur is not L.v:
+        for z in range(max(L.a - 1, max(L.z0, 0)), min(L.b + 1, L.z0 + L.nzl, L.n)):
+            m = colour_mask(L.n, z, 0)
+            L.v[z][m] = cur[z][m]
+
+
+def relax_jacobi_whole(L, nu):
+    """the definition: every interior point from the old values (oracle/mg_oracle_impl.h::orc3d_relax_jacobi)"""
+    n = L.n
+    h2 = (1.0 / (n - 1)) ** 2
+    for _ in range(nu):
+        v = L.v
+        gs = (v[1:-1, 1:-1, :-2] + v[1:-1, 1:-1, 2:] + v[1:-1, :-2, 1:-1] + v[1:-1, 2:, 1:-1] + v[:-2, 1:-1, 1:-1] +
+              v[2:, 1:-1, 1:-1] - L.f[1:-1, 1:-1, 1:-1] * h2) / 6.0
+        nv = v.copy()
+        nv[1:-1, 1:-1, 1:-1] = v[1:-1, 1:-1, 1:-1] + OMEGA * (gs - v[1:-1, 1:-1, 1:-1])
+        L.v = nv
+
+
+def vcycle(levels, l, rank, world, engine_schedule=True, smoother="gs"):
     """engine_schedule: colour-1-only correction (and exchange) as in mg3d_host.c::vcycle_rec; False = the reference's
-    full ApplyCorrection, used for the sequential run the slabs are compared with."""
+    full ApplyCorrection, used for the sequential run the slabs are compared with.  smoother "jacobi": the weighted
+    Jacobi option (full correction, both colours exchanged); the sequential run uses the whole-grid definition."""
     L = levels[l]
-    relax(L, rank, world, NU)
+    if smoother == "jacobi":
+        smooth = (lambda: relax_jacobi(L, rank, world, NU_J)) if engine_schedule else (lambda: relax_jacobi_whole(L, NU_J))
+        engine_colour = None
+    else:
+        smooth = lambda: relax(L, rank, world, NU)
+        engine_colour = 1 if engine_schedule else None
+    smooth()
     if l + 1 < len(levels):
         C = levels[l + 1]
         exchange(L, L.v, rank, world, 2, 0)                       # plane a-2 for the fused residual+restrict
@@ -184,11 +251,11 @@ def vcycle(levels, l, rank, world, engine_schedule=True):
             top = torch.from_numpy(C.f[C.n - 1:C.n].copy())
             dist.broadcast(top, world - 1)
             C.f[C.n - 1] = top.numpy()[0]
-        vcycle(levels, l + 1, rank, world, engine_schedule)
+        vcycle(levels, l + 1, rank, world, engine_schedule, smoother)
         lo, hi = L.interior()
-        interpolate_add(L.v, C.v, lo, hi, 1 if engine_schedule else None)
-        exchange(L, L.v, rank, world, 1, 1, 1 if engine_schedule else None)
-    relax(L, rank, world, NU)
+        interpolate_add(L.v, C.v, lo, hi, engine_colour)
+        exchange(L, L.v, rank, world, 1, 1, engine_colour)
+    smooth()
 
 
 def problem(n):
@@ -197,7 +264,7 @@ def problem(n):
     return np.zeros((n, n, n)), f
 
 
-def worker(rank, world, port, plans, out_queue):
+def worker(rank, world, port, plans, out_queue, smoother="gs"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -207,7 +274,7 @@ def worker(rank, world, port, plans, out_queue):
     sl = slice(L0.z0, L0.z0 + L0.nzl)
     L0.v[sl], L0.f[sl] = v0[sl], f0[sl]
     for _ in range(CYCLES):
-        vcycle(levels, 0, rank, world)
+        vcycle(levels, 0, rank, world, True, smoother)
     out_queue.put((rank, L0.a, L0.b, L0.v[L0.a:L0.b].copy()))
     dist.barrier()
     dist.destroy_process_group()
@@ -219,7 +286,8 @@ def free_port():
         return s.getsockname()[1]
 
 
-def test_slab_schedule_world2_gloo(mg, monkeypatch):
+@pytest.mark.parametrize("smoother", ["gs", "jacobi"])
+def test_slab_schedule_world2_gloo(mg, monkeypatch, smoother):
     world = 2
     monkeypatch.setenv("MG_B200_DIST_MIN_N", "65")  # distribute the small test grid too (default threshold: n >= 257)
     plans = {(n, r): mg.MultiGrid3D.plan_level(n, world, r) for n in sizes(N) for r in range(world)}
@@ -232,11 +300,11 @@ def test_slab_schedule_world2_gloo(mg, monkeypatch):
         L.v[...] = 0.0
         L.f[...] = 0.0
     for _ in range(CYCLES):
-        vcycle(ref_levels, 0, 0, 1, engine_schedule=False)
+        vcycle(ref_levels, 0, 0, 1, engine_schedule=False, smoother=smoother)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = free_port()
-    procs = [ctx.Process(target=worker, args=(r, world, port, plans, q)) for r in range(world)]
+    procs = [ctx.Process(target=worker, args=(r, world, port, plans, q, smoother)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=240) for _ in range(world)]
