@@ -83,3 +83,32 @@ def test_compat_shim_headers_compile(tmp_path):
                    '#include "Grid1D.h"\n#include "MultiGrid1D.h"\nint main(){return 0;}\n')
     subprocess.run(["g++", "-Wall", "-I", compat, "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o",
                     str(tmp_path / "t.o")], check=True)
+
+
+EXAMPLE = os.path.join(ROOT, "tests", "_build", "example_poisson3d")
+
+
+def test_c_example_builds_and_fails_loudly_without_a_gpu(mg):
+    """examples/poisson3d_vcycle.c: the ABI from plain C.  Built into tests/_build/ (shipped to the GPU box); in a
+    container without a GPU it must stop at mg3d_create with the no-CPU-fallback message, not compute anything."""
+    os.makedirs(os.path.dirname(EXAMPLE), exist_ok=True)
+    subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "poisson3d_vcycle.c"), "-o", EXAMPLE,
+                    "-L", os.path.join(ROOT, "pde_multigrid_b200"), "-lmg_b200",
+                    "-Wl,-rpath,$ORIGIN/../../pde_multigrid_b200", "-lm"], check=True)
+    import torch
+    if not torch.cuda.is_available():
+        out = subprocess.run([EXAMPLE, "33", "1"], capture_output=True, text=True)
+        assert out.returncode == 1 and "no CPU fallback" in out.stderr, out.stderr
+
+
+@pytest.mark.gpu
+def test_c_example_runs_on_the_gpu():
+    if not os.path.exists(EXAMPLE):
+        pytest.skip("tests/_build/example_poisson3d not built (the CPU test builds it)")
+    out = subprocess.run([EXAMPLE, "65", "3"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    norms = [float(l.split("||r||_2 =")[1].split()[0]) for l in out.stdout.splitlines() if "||r||_2 =" in l]
+    assert len(norms) == 3 and norms[2] < 0.2 * norms[1] < 0.04 * norms[0] * 5, out.stdout
+    centre = float(out.stdout.split("v(centre) =")[1].split()[0])
+    assert abs(centre - 1.0) < 0.01, out.stdout
