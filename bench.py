@@ -339,7 +339,8 @@ def main():
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": "finest-level smoother launch (Relax, level 0)", "achieved": achieved,
-                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8000_gbs": achieved / 8000.0,
+                    "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_ms,
                     "launches_per_cycle": relax0["launches"],
                     "share_of_step": relax0["ms"] / ms_step_profiled,
@@ -399,7 +400,13 @@ def main():
             "grid_point_updates_per_s": updates_per_cycle(n) * value,
             "algorithmic_bytes_per_cycle": bytes_cycle,
             "hbm_roofline_cycle": {"achieved_gbs": bytes_cycle / (ms_step * 1e-3) / 1e9 / world, "peak_gbs": peak,
-                                   "frac": bytes_cycle / (ms_step * 1e-3) / 1e9 / world / peak, "per": "GPU"},
+                                   "frac": bytes_cycle / (ms_step * 1e-3) / 1e9 / world / peak, "per": "GPU",
+                                   "frac_of_nominal_8000_gbs": bytes_cycle / (ms_step * 1e-3) / 1e9 / world / 8000.0},
+            # halo traffic of rank 0 against one direction of NVLink 5 (900 GB/s): the exchanges are latency-, not bandwidth-bound
+            "nvlink_halo": (None if world == 1 else
+                            {"bytes_per_cycle_rank0": int(halo_bytes) // max(args.steps, 1),
+                             "achieved_gbs": halo_bytes / max(args.steps, 1) / (ms_step * 1e-3) / 1e9, "peak_gbs": 900.0,
+                             "frac": halo_bytes / max(args.steps, 1) / (ms_step * 1e-3) / 1e9 / 900.0}),
             "residual_l2": {"before": r0[0], "after": r1[0]},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches), "halo_bytes_per_cycle_rank0": int(halo_bytes) // max(args.steps, 1),
