@@ -137,12 +137,13 @@ def host_cpu_info():
     return model, os.cpu_count()
 
 
-def time_reference_cpu(n_sample, steps, warmup, dtype=np.float64):
+def time_reference_cpu(n_sample, steps, warmup, dtype=np.float64, opt="O2"):
     """The reference's own CPU implementation of the path (NOCUDA_TESI VCycle(0,2,2), single-threaded as
-    shipped), from oracle/_ref when it is present, else the plain-C port.  Returns seconds per cycle."""
+    shipped), from oracle/_ref when it is present, else the plain-C port.  Returns seconds per cycle.
+    opt="O0": the as-shipped build (the reference's CompileAndLink passes no optimisation flag)."""
     from oracle import port, ref
     if ref.available():
-        o = ref.RefMG(3, dtype, corrected=True, n=n_sample)
+        o = ref.RefMG(3, dtype, corrected=True, n=n_sample, opt=opt)
         kind = "reference"
     else:
         o = port.PortMG(3, dtype, corrected=True, n=n_sample)
@@ -379,7 +380,14 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, kind = time_reference_cpu(args.cpu_n, args.cpu_steps, 0)
         scale = updates_per_cycle(args.cpu_n) / updates_per_cycle(n)
-        cpu_baseline = {"value": scale / sec, "unit": "V-cycles/s", "cores": 1, "kind": kind,
+        as_shipped = None
+        if kind == "reference":
+            try:  # same sources without optimisation flags, as the reference's own build script compiles them
+                sec0, _ = time_reference_cpu(args.cpu_n, 1, 0, opt="O0")
+                as_shipped = {"value": scale / sec0, "unit": "V-cycles/s", "seconds_per_cycle_at_sample": sec0, "flags": "-O0"}
+            except Exception:
+                as_shipped = None
+        cpu_baseline = {"value": scale / sec, "unit": "V-cycles/s", "cores": 1, "kind": kind, "as_shipped_O0": as_shipped,
                         "grid_point_updates_per_s": updates_per_cycle(args.cpu_n) / sec,
                         "sample": "%d V(2,2) cycles of the reference NOCUDA_TESI solver (g++ -O2, 1 thread: it is single-threaded) "
                                   "at %d^3 fp64, sign-corrected residual, %.2f s/cycle; V-cycles/s scaled to %d^3 by grid-point "

@@ -10,6 +10,8 @@ Variants (one object each, every one in its own C++ namespace):
     ref3d_f32  ref3d_f64  ref3d_f32c  ref3d_f64c     (c = CORRECTED residual signs)
     ref2d_f32  ref2d_f64
     ref1d_f32  ref1d_f64  ref1d_f32c  ref1d_f64c
+    ref3d_f64cO0   = ref3d_f64c built with -O0, i.e. as shipped (the reference's CompileAndLink passes no flags);
+                     only bench.py's CPU baseline times it, next to the -O2 figure
 
 The CORRECTED variants include a patched copy of MultiGrid3D.cpp / MultiGrid1D.cpp that is
 written to a temporary directory at build time and deleted afterwards.  Each patch must
@@ -86,10 +88,11 @@ def build(verbose=False):
                 variants.append((dim, prec, False))
                 if dim in PATCHES:
                     variants.append((dim, prec, True))
-        for dim, prec, corrected in variants:
-            prefix = "ref%s_%s%s" % (dim, prec, "c" if corrected else "")
+        variants = [v + ("O2",) for v in variants] + [("3d", "f64", True, "O0")]
+        for dim, prec, corrected, opt in variants:
+            prefix = "ref%s_%s%s%s" % (dim, prec, "c" if corrected else "", "" if opt == "O2" else opt)
             obj = os.path.join(OUT, prefix + ".o")
-            cmd = list(common)
+            cmd = [("-" + opt) if a == "-O2" else a for a in common]
             cmd += ["-DREF_PREFIX=" + prefix]
             if prec == "f64":
                 cmd += ["-DREF_F64"]

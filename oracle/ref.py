@@ -41,15 +41,18 @@ def norms(r):
 
 
 class RefMG:
-    def __init__(self, dim, dtype, corrected=False, n=33, range=None, A=(-1.0, -2.0, 0.0, -3.0), alfa=2):
+    def __init__(self, dim, dtype, corrected=False, n=33, range=None, A=(-1.0, -2.0, 0.0, -3.0), alfa=2, opt="O2"):
+        """opt="O0": the as-shipped build (no compiler flags), available for 3D double corrected only (timing)."""
         self.dim = dim
         self.np_dtype = np.dtype(dtype)
         assert self.np_dtype in (np.dtype(np.float32), np.dtype(np.float64))
         prec = "f32" if self.np_dtype == np.dtype(np.float32) else "f64"
         if corrected and dim == 2:
             corrected = False  # the 2D residual has no defect
-        self.prefix = "ref%dd_%s%s" % (dim, prec, "c" if corrected else "")
+        self.prefix = "ref%dd_%s%s%s" % (dim, prec, "c" if corrected else "", "" if opt == "O2" else opt)
         self.L = lib()
+        if not hasattr(self.L, self.prefix + "_create"):
+            raise RuntimeError("oracle/_ref has no variant %s" % self.prefix)
         self.creal_p = ctypes.POINTER(ctypes.c_float if prec == "f32" else ctypes.c_double)
         if range is None:
             range = [0.0, 1.0] * dim
