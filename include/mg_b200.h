@@ -47,11 +47,21 @@ extern "C" {
 #define MG_FIELD_F 1 /* Grid?D::h_f  right-hand side / restricted residual */
 
 /* smoother implementation (results are bit-identical; the choice only affects speed) */
-#define MG_SMOOTHER_AUTO 0
-#define MG_SMOOTHER_COLOUR 1 /* one colour per launch, in place */
-#define MG_SMOOTHER_FUSED 2  /* red+black (and several sweeps) per HBM pass, z-marching smem tiles */
+#define MG_SMOOTHER_AUTO 0   /* the fastest available per level and call: MG_SMOOTHER_PIPE for pairs of sweeps where it
+                                applies, MG_SMOOTHER_TMA for the rest, plain kernels on the small levels */
+#define MG_SMOOTHER_COLOUR 1 /* one colour per launch, in place, plain kernels */
+#define MG_SMOOTHER_FUSED 2  /* two RB sweeps per HBM pass, all stages through shared memory, the reference's literal
+                                arithmetic (slower than MG_SMOOTHER_TMA; it is the exact fallback of MG_SMOOTHER_PIPE) */
 #define MG_SMOOTHER_JACOBI 3 /* weighted Jacobi (3D only): v += omega*(GS(v_old) - v_old), all points from old values.
                                 Not in the reference (it only has red-black Gauss-Seidel): no parity contract with it */
+
+#define MG_SMOOTHER_TMA 4    /* one colour per launch with TMA-staged z-marching tiles on the large levels (no temporal blocking) */
+#define MG_SMOOTHER_PIPE 5   /* two RB sweeps per HBM pass, register-tiled z-pipeline (large, cubic, power-of-two-h levels on
+                                one GPU; elsewhere as MG_SMOOTHER_TMA) */
+
+/* arithmetic of the temporally blocked smoother (mg3d_set_arith) */
+#define MG_ARITH_EXACT 0 /* every rounding of the reference reproduced: results bit-identical to NOCUDA_TESI (default) */
+#define MG_ARITH_FAST 1  /* pairwise sums, FMA, multiplication by 1/6: within 1e-10 (fp64) / 1e-5 (fp32) relative */
 
 /* operator classes of the per-operator device timers (mg?d_profile_read) */
 #define MG_OP_RELAX 0             /* Relax */
@@ -89,7 +99,10 @@ int mg3d_destroy(mg3d_t* mg); /* ~MultiGrid3D */
 int mg3d_num_levels(const mg3d_t* mg);         /* MultiGrid3D::numGrids */
 int mg3d_level_size(const mg3d_t* mg, int level); /* grids3D[level]->sizeX */
 double mg3d_level_h(const mg3d_t* mg, int level); /* grids3D[level]->h_x */
+/* sweeps_per_pass must name what the implementation does: 2 for MG_SMOOTHER_FUSED / MG_SMOOTHER_PIPE, 1 for the
+   others; MG_SMOOTHER_AUTO takes 1 or 2 */
 int mg3d_set_smoother(mg3d_t* mg, int smoother, int sweeps_per_pass);
+int mg3d_set_arith(mg3d_t* mg, int arith); /* MG_ARITH_EXACT (default) or MG_ARITH_FAST */
 /* relaxation weight of MG_SMOOTHER_JACOBI, 0 < omega <= 1 (default 6/7, the optimal smoothing weight of the 7-point
    Laplacian); rounded to the handle's dtype */
 int mg3d_set_jacobi_weight(mg3d_t* mg, double omega);
@@ -110,6 +123,13 @@ int mg3d_init_problem(mg3d_t* mg);
 int mg3d_relax(mg3d_t* mg, int level, int ncycles);                 /* Relax(grids3D[level], ncycles) */
 int mg3d_residual(mg3d_t* mg, int level, void* host_out);           /* CalculateResidual(grids3D[level]) -> caller-owned n^3 */
 int mg3d_residual_norm(mg3d_t* mg, int level, double* l2, double* linf); /* norms of that residual (the reference has none) */
+/* Grid3D::PrintDiff (N3/Grid3D.cpp:136-159) as a device reduction: mean and max over all n^3 points of
+   |realSol - approxSol|, realSol = (real)(sin(PI x)sin(PI y)sin(PI z)); all ranks return the global values */
+int mg3d_abs_error(mg3d_t* mg, int level, double* mean_abs, double* max_abs);
+/* position-keyed additive checksum (mod 2^64) of a whole level field, bit-pattern based: equal checksums <=> equal bits
+   for all practical purposes; slab partial sums are combined over the ranks.  Used by bench.py to show that a run on N
+   GPUs holds the bits of the reference CPU solver (tests/golden/hashes3d.json) without moving the field to the host. */
+int mg3d_field_checksum(mg3d_t* mg, int level, int field, unsigned long long* out);
 int mg3d_restrict(mg3d_t* mg, int fine_level, int field);           /* Restrict(fine->field, ..., coarse->field, ...) */
 int mg3d_residual_restrict(mg3d_t* mg, int fine_level);             /* Restrict(CalculateResidual(fine), coarse->h_f) + setToValue(coarse->h_v,0,true), fused */
 int mg3d_interpolate(mg3d_t* mg, int fine_level);                   /* Interpolate(fine->h_v, ..., coarse->h_v, ...) */

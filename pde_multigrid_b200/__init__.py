@@ -5,9 +5,10 @@ include/mg_b200.h).  This package only loads it (ctypes) and mirrors the referen
 for tests and benchmarks.  There is no CPU or PyTorch compute path.
 """
 from ._lib import (MG_CORRECTED, MG_F32, MG_F64, MG_FIELD_F, MG_FIELD_V, MG_REF_COMPAT, MG_SMOOTHER_AUTO,
-                   MG_SMOOTHER_COLOUR, MG_SMOOTHER_FUSED, MG_SMOOTHER_JACOBI, MGError, lib)
+                   MG_SMOOTHER_COLOUR, MG_SMOOTHER_FUSED, MG_SMOOTHER_JACOBI, MG_SMOOTHER_TMA, MG_SMOOTHER_PIPE,
+                   MG_ARITH_EXACT, MG_ARITH_FAST, MGError, lib)
 from .multigrid import MultiGrid1D, MultiGrid2D, MultiGrid3D
 
 __all__ = ["MultiGrid1D", "MultiGrid2D", "MultiGrid3D", "MGError", "lib", "MG_F32", "MG_F64", "MG_REF_COMPAT",
            "MG_CORRECTED", "MG_FIELD_V", "MG_FIELD_F", "MG_SMOOTHER_AUTO", "MG_SMOOTHER_COLOUR", "MG_SMOOTHER_FUSED",
-           "MG_SMOOTHER_JACOBI"]
+           "MG_SMOOTHER_JACOBI", "MG_SMOOTHER_TMA", "MG_SMOOTHER_PIPE", "MG_ARITH_EXACT", "MG_ARITH_FAST"]

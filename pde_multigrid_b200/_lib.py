@@ -13,7 +13,8 @@ MG_OK, MG_ERR_ARG, MG_ERR_CUDA, MG_ERR_NOMEM, MG_ERR_STATE, MG_ERR_COMM = 0, 1, 
 MG_F32, MG_F64 = 0, 1
 MG_REF_COMPAT, MG_CORRECTED = 0, 1
 MG_FIELD_V, MG_FIELD_F = 0, 1
-MG_SMOOTHER_AUTO, MG_SMOOTHER_COLOUR, MG_SMOOTHER_FUSED, MG_SMOOTHER_JACOBI = 0, 1, 2, 3
+MG_SMOOTHER_AUTO, MG_SMOOTHER_COLOUR, MG_SMOOTHER_FUSED, MG_SMOOTHER_JACOBI, MG_SMOOTHER_TMA, MG_SMOOTHER_PIPE = 0, 1, 2, 3, 4, 5
+MG_ARITH_EXACT, MG_ARITH_FAST = 0, 1
 
 _lib = None
 

@@ -7,6 +7,19 @@
 #include "mg_exact.cuh"
 #include "mg_launch.h"
 
+// Raise a kernel's dynamic shared-memory limit once per DEVICE (the attribute is per device: a process may hold
+// handles on several GPUs).  The static lives at the call site, i.e. once per kernel instantiation.
+#define MG_SET_SMEM_LIMIT(kernel, bytes)                                                                        \
+    do {                                                                                                        \
+        static unsigned char done_[64];                                                                         \
+        int dev_ = 0;                                                                                           \
+        cudaGetDevice(&dev_);                                                                                   \
+        if (dev_ < 0 || dev_ >= 64 || !done_[dev_]) {                                                           \
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));            \
+            if (dev_ >= 0 && dev_ < 64) done_[dev_] = 1;                                                        \
+        }                                                                                                       \
+    } while (0)
+
 namespace mg3 {
 using namespace mgx;
 

@@ -28,6 +28,9 @@
 
 #define MG_GHOST_LO 2
 #define MG_GHOST_HI 1
+/* bytes of addressable slack in front of and behind the fields of the arena: the pipelined smoother (mg3d_smooth_pipe.cu)
+   issues unclamped, masked loads for halo sites up to 4 rows outside a field */
+#define MG_ARENA_SLACK ((size_t)1 << 20)
 
 typedef struct {
     mg_geom3d g;
@@ -47,6 +50,9 @@ typedef struct {
     unsigned char tmap_rr[2][2][128] __attribute__((aligned(64))); /* residual+restrict boxes */
     unsigned char tmap_fu[2][2][128] __attribute__((aligned(64))); /* fused-smoother boxes of v */
     unsigned char tmap_ff[2][128] __attribute__((aligned(64)));    /* fused-smoother boxes of f: [colour] */
+    unsigned char tmap_pp[2][128] __attribute__((aligned(64)));    /* pipelined smoother: colour-1 array of v, [buffer] */
+    unsigned char tmap_pf[2][128] __attribute__((aligned(64)));    /* pipelined smoother: f (L2 prefetch), [colour] */
+    int iso;        /* hx2 == hy2 == hz2 */
 } mg_level3d;
 
 /* direct NVLink halo path (mg_halo_p2p.cu): the neighbours' arenas and flag words mapped with CUDA IPC */
@@ -63,9 +69,10 @@ typedef struct {
 /* CUDA-graph cache of whole V-cycles: the cycle is ~100 dependent launches, most of them tiny (coarse
    levels, halo kernels); replaying them from a graph removes the per-launch gaps that dominate at 257^3
    and on the 8-GPU slabs.  Key = (level, v1, v2, smoother). */
-#define MG_GRAPH_SLOTS 8
+#define MG_GRAPH_SLOTS 16
 typedef struct {
-    int used, level, v1, v2, smoother, calls;
+    int used, level, v1, v2, smoother, arith, calls;
+    unsigned cur_start, cur_end; /* bit l = which v buffer level l works on when the graph starts / has finished */
     cudaGraphExec_t exec;
     long long launches, halo_bytes;
 } mg_graph_slot;
@@ -82,7 +89,8 @@ struct mg3d_s {
     mg_comm* comm;
     mg_p2p p2p;
     mg_level3d* lv;
-    void* arena;
+    void* arena;     /* first field */
+    void* arena_raw; /* the allocation: arena - MG_ARENA_SLACK */
     double* d_scratch; /* 2*MGK_NORM_MAX_PARTS partials + 2 outputs */
     double* d_tables;  /* 3*n0 doubles: sin tables of InitF */
     double* h_out2;    /* pinned */
@@ -94,6 +102,9 @@ struct mg3d_s {
     int use_graphs;
     mg_graph_slot graphs[MG_GRAPH_SLOTS];
     double omega;   /* weight of MG_SMOOTHER_JACOBI */
+    int arith;           /* MG_ARITH_EXACT / MG_ARITH_FAST */
+    int no_pipe;         /* MG_B200_NO_PIPE: MG_SMOOTHER_AUTO without temporal blocking (the round-1 default) */
+    unsigned int* d_flag; /* {exactness flag of the pipelined smoother, completion counter of its fallback} */
     int no_tail;         /* MG_B200_NO_TAIL: coarse levels as separate launches */
     int full_correction; /* MG_B200_FULL_CORRECTION: correct both colours after prolongation inside a cycle */
 };
@@ -354,7 +365,7 @@ static int p2p_setup(mg3d_t* mg, size_t arena_bytes)
     cudaIpcMemHandle_t mine[2];
     int ok = 1; /* a rank without IPC still takes part in the collectives below, then everybody keeps NCCL */
     memset(mine, 0, sizeof mine);
-    if (cudaIpcGetMemHandle(&mine[0], mg->arena) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], q->flags) != cudaSuccess) {
+    if (cudaIpcGetMemHandle(&mine[0], mg->arena_raw) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], q->flags) != cudaSuccess) {
         cudaGetLastError();
         ok = 0;
     }
@@ -380,7 +391,7 @@ static int p2p_setup(mg3d_t* mg, size_t arena_bytes)
             ok = 0;
             break;
         }
-        q->peer_arena[k] = (char*)pa;
+        q->peer_arena[k] = (char*)pa + MG_ARENA_SLACK;
         q->peer_flags[k] = (unsigned int*)pf;
     }
     free(all);
@@ -399,7 +410,7 @@ static void p2p_teardown(mg3d_t* mg)
 {
     mg_p2p* q = &mg->p2p;
     for (int k = 0; k < 2; k++) {
-        if (q->peer_arena[k]) cudaIpcCloseMemHandle(q->peer_arena[k]);
+        if (q->peer_arena[k]) cudaIpcCloseMemHandle(q->peer_arena[k] - MG_ARENA_SLACK);
         if (q->peer_flags[k]) cudaIpcCloseMemHandle(q->peer_flags[k]);
         free(q->nb_off[k]); free(q->nb_geom[k]); free(q->nb_own[k]);
     }
@@ -457,6 +468,8 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
     mg->use_graphs = getenv("MG_B200_NO_GRAPH") ? 0 : 1;
     mg->omega = 6.0 / 7.0;
     mg->no_tail = getenv("MG_B200_NO_TAIL") != NULL;
+    mg->no_pipe = getenv("MG_B200_NO_PIPE") != NULL;
+    mg->arith = MG_ARITH_EXACT;
     mg->full_correction = getenv("MG_B200_FULL_CORRECTION") != NULL;
     memcpy(mg->range, range, sizeof mg->range);
     mg->nlevels = mg_num_levels_for(n);
@@ -477,11 +490,12 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
         total += (size_t)level_fields(L) * field_bytes(L, dtype);
         nl = (nl - 1) / 2 + 1; /* N3/MultiGrid3D.cpp:40-42 */
     }
-    cudaError_t e = cudaMalloc(&mg->arena, total);
+    cudaError_t e = cudaMalloc(&mg->arena_raw, total + 2 * MG_ARENA_SLACK);
     if (e != cudaSuccess) {
         free(mg->lv); free(mg);
         return mg_fail(e == cudaErrorMemoryAllocation ? MG_ERR_NOMEM : MG_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", total, cudaGetErrorString(e));
     }
+    mg->arena = (char*)mg->arena_raw + MG_ARENA_SLACK;
     char* p = (char*)mg->arena;
     for (int l = 0; l < mg->nlevels; l++) {
         mg_level3d* L = &mg->lv[l];
@@ -493,6 +507,7 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
     if (cudaStreamCreateWithFlags(&mg->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc((void**)&mg->d_scratch, (2 * MGK_NORM_MAX_PARTS + 2) * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&mg->d_tables, 3 * (size_t)n * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&mg->d_flag, 256) != cudaSuccess || cudaMemsetAsync(mg->d_flag, 0, 256, mg->stream) != cudaSuccess ||
         cudaMallocHost((void**)&mg->h_out2, 2 * sizeof(double)) != cudaSuccess) {
         int code = mg_fail(MG_ERR_CUDA, "stream/scratch setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         mg3d_destroy(mg);
@@ -523,15 +538,19 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
                 st = mg_tma_make_colour_map(L->tmap_v[b][col], dtype, base, &L->g, MGK3D_TMA_BOX_I(es), MGK3D_TMA_BOX_Y);
                 if (!st) st = mg_tma_make_colour_map(L->tmap_rr[b][col], dtype, base, &L->g, MGK3D_RR_BOX_I(es), MGK3D_RR_BOX_Y);
                 if (!st) st = mg_tma_make_colour_map(L->tmap_fu[b][col], dtype, base, &L->g, MGK3D_FU_BOX_I(es), MGK3D_FU_BOX_Y);
+                if (!st && col == 1) st = mg_tma_make_colour_map(L->tmap_pp[b], dtype, base, &L->g, MGK3D_PP_BOX_I(es), MGK3D_PP_BOX_Y);
             }
         }
-        for (int col = 0; col < 2 && !st; col++)
+        for (int col = 0; col < 2 && !st; col++) {
             st = mg_tma_make_colour_map(L->tmap_ff[col], dtype, plane_ptr(mg, L, L->f, col, 0), &L->g, MGK3D_FU_BOX_I(es), MGK3D_FU_BOX_Y);
+            if (!st) st = mg_tma_make_colour_map(L->tmap_pf[col], dtype, plane_ptr(mg, L, L->f, col, 0), &L->g, MGK3D_PP_BOX_I(es), MGK3D_PP_BOX_Y);
+        }
+        L->iso = L->c.hx2 == L->c.hy2 && L->c.hy2 == L->c.hz2;
         if (st) { mg3d_destroy(mg); return st; }
         L->has_tma = 1;
     }
     /* pad elements of the layout are never used by a kernel, but keep them defined */
-    if (cudaMemsetAsync(mg->arena, 0, total, mg->stream) != cudaSuccess) {
+    if (cudaMemsetAsync(mg->arena_raw, 0, total + 2 * MG_ARENA_SLACK, mg->stream) != cudaSuccess) {
         int code = mg_fail(MG_ERR_CUDA, "arena clear failed: %s", cudaGetErrorString(cudaGetLastError()));
         mg3d_destroy(mg);
         return code;
@@ -565,9 +584,10 @@ int mg3d_destroy(mg3d_t* mg)
     if (mg->ev_fork) cudaEventDestroy(mg->ev_fork);
     if (mg->ev_join) cudaEventDestroy(mg->ev_join);
     if (mg->stream) cudaStreamDestroy(mg->stream);
-    if (mg->arena) cudaFree(mg->arena);
+    if (mg->arena_raw) cudaFree(mg->arena_raw);
     if (mg->d_scratch) cudaFree(mg->d_scratch);
     if (mg->d_tables) cudaFree(mg->d_tables);
+    if (mg->d_flag) cudaFree(mg->d_flag);
     if (mg->h_out2) cudaFreeHost(mg->h_out2);
     if (mg->staging) cudaFree(mg->staging);
     mg_prof_free(&mg->prof);
@@ -598,10 +618,23 @@ int mg3d_owned_range(const mg3d_t* mg, int level, int* z_begin, int* z_count)
 int mg3d_set_smoother(mg3d_t* mg, int smoother, int sweeps_per_pass)
 {
     if (!mg) return mg_fail(MG_ERR_ARG, "null handle");
-    if (smoother < MG_SMOOTHER_AUTO || smoother > MG_SMOOTHER_JACOBI) return mg_fail(MG_ERR_ARG, "bad smoother %d", smoother);
-    if (sweeps_per_pass < 1 || sweeps_per_pass > 4) return mg_fail(MG_ERR_ARG, "sweeps_per_pass must be 1..4");
+    if (smoother < MG_SMOOTHER_AUTO || smoother > MG_SMOOTHER_PIPE) return mg_fail(MG_ERR_ARG, "bad smoother %d", smoother);
+    /* sweeps per HBM pass is a property of the implementation: the temporally blocked smoothers do two, the others one;
+       MG_SMOOTHER_AUTO picks per level and call, so it takes either value */
+    const int two = smoother == MG_SMOOTHER_FUSED || smoother == MG_SMOOTHER_PIPE;
+    if (smoother == MG_SMOOTHER_AUTO ? (sweeps_per_pass != 1 && sweeps_per_pass != 2) : sweeps_per_pass != (two ? 2 : 1))
+        return mg_fail(MG_ERR_ARG, "sweeps_per_pass %d is not what smoother %d does (%s)", sweeps_per_pass, smoother,
+                       smoother == MG_SMOOTHER_AUTO ? "1 or 2" : two ? "2" : "1");
     mg->smoother = smoother;
     mg->sweeps_per_pass = sweeps_per_pass;
+    return MG_OK;
+}
+
+int mg3d_set_arith(mg3d_t* mg, int arith)
+{
+    if (!mg) return mg_fail(MG_ERR_ARG, "null handle");
+    if (arith != MG_ARITH_EXACT && arith != MG_ARITH_FAST) return mg_fail(MG_ERR_ARG, "bad arithmetic mode %d", arith);
+    mg->arith = arith;
     return MG_OK;
 }
 
@@ -700,40 +733,50 @@ int mg3d_get_field(mg3d_t* mg, int level, int field, void* host_dense)
     return copy_out(mg, host_dense, field_ptr(L, field), &L->g, L->own_lo, L->own_hi);
 }
 
+/* sin(PI*coord) per axis for one level, computed with the host libm exactly like N3/Grid3D.cpp:88-92 and
+   N3/Grid3D.cpp:146-150 (float coordinate, double sine), uploaded into mg->d_tables (x | y | z, n each) */
+static int upload_sin_tables(mg3d_t* mg, int level)
+{
+    const double PI = 3.141592653589793; /* N3/inclusion.h:9 */
+    const mg_level3d* L = &mg->lv[level];
+    const int n = L->g.n;
+    double* tab = (double*)malloc(3 * (size_t)n * sizeof(double));
+    if (!tab) return mg_fail(MG_ERR_NOMEM, "host allocation failed");
+    for (int a = 0; a < 3; a++)
+        for (int i = 0; i < n; i++) {
+            /* float x = x_a + posX*h_x;  sin(PI*x) in double */
+            double x;
+            if (mg->dtype == MG_F32) {
+                float xf = (float)mg->range[2 * a] + i * (float)L->h[a];
+                x = xf;
+            } else {
+                x = mg->range[2 * a] + i * L->h[a];
+            }
+            tab[(size_t)a * n + i] = sin(PI * x);
+        }
+    cudaError_t e = cudaMemcpyAsync(mg->d_tables, tab, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, mg->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(mg->stream);
+    free(tab);
+    if (e != cudaSuccess) return mg_fail(MG_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e));
+    return MG_OK;
+}
+
 /* Grid3D::InitV / InitF on every level (N3/Grid3D.cpp:61-96); ghost planes are initialised like owned ones */
 int mg3d_init_problem(mg3d_t* mg)
 {
     if (!mg) return mg_fail(MG_ERR_ARG, "null handle");
-    const double PI = 3.141592653589793; /* N3/inclusion.h:9 */
-    const int n0 = mg->lv[0].g.n;
-    double* tab = (double*)malloc(3 * (size_t)n0 * sizeof(double));
-    if (!tab) return mg_fail(MG_ERR_NOMEM, "host allocation failed");
     for (int l = 0; l < mg->nlevels; l++) {
         mg_level3d* L = &mg->lv[l];
         const int n = L->g.n;
-        for (int a = 0; a < 3; a++)
-            for (int i = 0; i < n; i++) {
-                /* float x = x_a + posX*h_x;  sin(PI*x) in double (N3/Grid3D.cpp:88-92) */
-                double x;
-                if (mg->dtype == MG_F32) {
-                    float xf = (float)mg->range[2 * a] + i * (float)L->h[a];
-                    x = xf;
-                } else {
-                    x = mg->range[2 * a] + i * L->h[a];
-                }
-                tab[(size_t)a * n + i] = sin(PI * x);
-            }
-        cudaError_t e = cudaMemcpyAsync(mg->d_tables, tab, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, mg->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(mg->stream);
-        if (e != cudaSuccess) { free(tab); return mg_fail(MG_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e)); }
+        int st = upload_sin_tables(mg, l);
+        if (st) return st;
         int k1 = mgk3d_set(mg->stream, mg->dtype, L->v, L->g, 0.0, 1, 0, L->g.nzl);
         int k2 = mgk3d_init_f(mg->stream, mg->dtype, L->f, L->g, mg->d_tables, mg->d_tables + n, mg->d_tables + 2 * n, 0, L->g.nzl);
-        if (k1 < 0 || k2 < 0) { free(tab); return mg_fail(MG_ERR_CUDA, "init launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
+        if (k1 < 0 || k2 < 0) return mg_fail(MG_ERR_CUDA, "init launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         mg->launches += k1 + k2;
-        e = cudaStreamSynchronize(mg->stream); /* d_tables is reused by the next level */
-        if (e != cudaSuccess) { free(tab); return mg_fail(MG_ERR_CUDA, "init failed: %s", cudaGetErrorString(e)); }
+        cudaError_t e = cudaStreamSynchronize(mg->stream); /* d_tables is reused by the next level */
+        if (e != cudaSuccess) return mg_fail(MG_ERR_CUDA, "init failed: %s", cudaGetErrorString(e));
     }
-    free(tab);
     /* The init kernels wrote the ghost planes locally.  With the direct-store halo transport a neighbour that
        is already past this point could push into them before those kernels ran here: a bidirectional
        exchange per distributed level is the handshake that orders the two (and it is cheap). */
@@ -835,12 +878,33 @@ static int relax_level(mg3d_t* mg, int level, int ncycles)
     if (ncycles <= 0) return MG_OK;
     if (mg->smoother == MG_SMOOTHER_JACOBI) return relax_jacobi_level(mg, level, ncycles);
     const int use_tma = L->has_tma && mg->smoother != MG_SMOOTHER_COLOUR;
-    /* temporally blocked smoother: two full sweeps per pass over HBM, out of place (v ping-pongs) */
+    /* register-tiled temporally blocked smoother (the default where it applies): two full sweeps per pass, out of place.
+       Bit-exact mode: the pass range-checks everything it touches; the conditional literal-arithmetic pass behind it only
+       runs (and then recomputes the same output buffer from the untouched input) if that check failed. */
+    if ((mg->smoother == MG_SMOOTHER_PIPE || (mg->smoother == MG_SMOOTHER_AUTO && !mg->no_pipe)) && L->has_tma && L->vbuf[1] && !L->dist &&
+        L->c.fast_den && L->iso) {
+        while (ncycles >= 2) {
+            const void* maps3[3] = {L->tmap_pp[L->cur], L->tmap_pf[0], L->tmap_pf[1]};
+            const void* maps4[4] = {L->tmap_fu[L->cur][0], L->tmap_fu[L->cur][1], L->tmap_ff[0], L->tmap_ff[1]};
+            PROF_BEGIN(mg, level, MG_OP_RELAX);
+            MG_LAUNCH(mg->launches, mgk3d_relax_pipe2(mg->stream, mg->dtype, maps3, L->vbuf[L->cur], L->f, L->vbuf[L->cur ^ 1], L->g, L->c,
+                                                      mg->arith == MG_ARITH_FAST, mg->d_flag));
+            if (mg->arith != MG_ARITH_FAST)
+                MG_LAUNCH(mg->launches, mgk3d_relax_fused2(mg->stream, mg->dtype, maps4, L->vbuf[L->cur ^ 1], L->g, L->c, mg->d_flag));
+            PROF_END(mg);
+            L->cur ^= 1;
+            L->v = L->vbuf[L->cur];
+            ncycles -= 2;
+        }
+        if (ncycles <= 0) return MG_OK;
+    }
+    /* the shared-memory version of the same idea (literal arithmetic; slower than four colour launches, kept as the
+       exact fallback above and selectable for tests) */
     if (mg->smoother == MG_SMOOTHER_FUSED && L->has_tma && L->vbuf[1] && !L->dist) {
         while (ncycles >= 2) {
             const void* maps4[4] = {L->tmap_fu[L->cur][0], L->tmap_fu[L->cur][1], L->tmap_ff[0], L->tmap_ff[1]};
             PROF_BEGIN(mg, level, MG_OP_RELAX);
-            MG_LAUNCH(mg->launches, mgk3d_relax_fused2(mg->stream, mg->dtype, maps4, L->vbuf[L->cur ^ 1], L->g, L->c));
+            MG_LAUNCH(mg->launches, mgk3d_relax_fused2(mg->stream, mg->dtype, maps4, L->vbuf[L->cur ^ 1], L->g, L->c, NULL));
             PROF_END(mg);
             L->cur ^= 1;
             L->v = L->vbuf[L->cur];
@@ -941,6 +1005,45 @@ static void coarse_share(const mg3d_t* mg, int fine_level, int* czl_lo, int* czl
         *czl_hi = (b - 1) / 2 + 1; /* the last rank's b = n makes this n_c: it also produces the top plane */
         if (mg->rank < mg->nranks - 1) *czl_hi = b / 2;
     }
+}
+
+/* Position-keyed additive checksum of a level's field over the whole grid (tests/golden_util.py:field_checksum is
+   the same sum in numpy; tests/golden/hashes3d.json holds the reference CPU solver's values).  Every rank sums the
+   planes it owns; distributed levels are combined over the ranks, so each rank returns the global value. */
+int mg3d_field_checksum(mg3d_t* mg, int level, int field, unsigned long long* out)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (!out || (field != MG_FIELD_V && field != MG_FIELD_F)) return mg_fail(MG_ERR_ARG, "bad field/pointer");
+    mg_level3d* L = &mg->lv[level];
+    unsigned long long* d = (unsigned long long*)(mg->d_scratch + 2 * MGK_NORM_MAX_PARTS);
+    MG_CUDA(cudaMemsetAsync(d, 0, sizeof *d, mg->stream));
+    MG_LAUNCH(mg->launches, mgk3d_field_checksum(mg->stream, mg->dtype, field_ptr(L, field), L->g, L->own_lo, L->own_hi, d));
+    if (L->dist && (st = mg_comm_allreduce_u64_sum(mg->comm, d, mg->stream))) return st;
+    MG_CUDA(cudaMemcpyAsync(mg->h_out2, d, sizeof *d, cudaMemcpyDeviceToHost, mg->stream));
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
+    memcpy(out, mg->h_out2, sizeof *out);
+    return halo_error_check(mg);
+}
+
+/* Grid3D::PrintDiff (N3/Grid3D.cpp:136-159) as a reduction: mean and max over ALL points of |realSol - approxSol|,
+   realSol = (real)(sin(PI x) sin(PI y) sin(PI z)), the difference taken in the grid's own precision */
+int mg3d_abs_error(mg3d_t* mg, int level, double* mean_abs, double* max_abs)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    mg_level3d* L = &mg->lv[level];
+    const int n = L->g.n;
+    if ((st = upload_sin_tables(mg, level))) return st;
+    double* out2 = mg->d_scratch + 2 * MGK_NORM_MAX_PARTS;
+    MG_LAUNCH(mg->launches, mgk3d_abs_error(mg->stream, mg->dtype, L->v, L->g, mg->d_tables, mg->d_tables + n, mg->d_tables + 2 * n,
+                                            L->own_lo, L->own_hi, mg->d_scratch, out2));
+    if (L->dist && (st = mg_comm_allreduce_sum_max(mg->comm, out2, mg->stream))) return st;
+    MG_CUDA(cudaMemcpyAsync(mg->h_out2, out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, mg->stream));
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
+    if (mean_abs) *mean_abs = mg->h_out2[0] / ((double)n * n * n);
+    if (max_abs) *max_abs = mg->h_out2[1];
+    return halo_error_check(mg);
 }
 
 /* what follows a restriction onto level+1: refresh ghosts (distributed) or gather (first agglomerated level) */
@@ -1087,32 +1190,37 @@ int mg3d_vcycle(mg3d_t* mg, int level, int v1, int v2)
     if (v1 < 0 || v2 < 0) return mg_fail(MG_ERR_ARG, "negative sweep count");
     const long long per_cycle = 2LL * (v1 + v2) * (mg->nlevels - level) * 2;
     if (!mg->use_graphs || mg->prof.enabled || per_cycle > 4096) return vcycle_rec(mg, level, v1, v2);
+    /* a captured graph bakes in which of its two v buffers every level works on (the temporally blocked smoothers
+       ping-pong), so that state is part of the key; a cycle with an odd number of passes ends on the other buffers and
+       the next call finds (or captures) the graph that starts there */
+    unsigned cur_now = 0;
+    for (int l = 0; l < mg->nlevels && l < 32; l++) cur_now |= (unsigned)mg->lv[l].cur << l;
     mg_graph_slot* g = NULL;
     for (int i = 0; i < MG_GRAPH_SLOTS && !g; i++)
         if (mg->graphs[i].used && mg->graphs[i].level == level && mg->graphs[i].v1 == v1 && mg->graphs[i].v2 == v2 &&
-            mg->graphs[i].smoother == mg->smoother)
+            mg->graphs[i].smoother == mg->smoother && mg->graphs[i].arith == mg->arith && mg->graphs[i].cur_start == cur_now)
             g = &mg->graphs[i];
     if (!g) {
         for (int i = 0; i < MG_GRAPH_SLOTS && !g; i++)
             if (!mg->graphs[i].used) g = &mg->graphs[i];
         if (!g) return vcycle_rec(mg, level, v1, v2); /* cache full: run eagerly */
         memset(g, 0, sizeof *g);
-        g->used = 1; g->level = level; g->v1 = v1; g->v2 = v2; g->smoother = mg->smoother;
+        g->used = 1; g->level = level; g->v1 = v1; g->v2 = v2; g->smoother = mg->smoother; g->arith = mg->arith;
+        g->cur_start = cur_now;
     }
     g->calls++;
     if (g->calls == 1) return vcycle_rec(mg, level, v1, v2);
     if (!g->exec) {
         const long long l0 = mg->launches, h0 = mg->halo_bytes;
         cudaGraph_t graph = NULL;
-        int cur0[MG_PROF_MAX_LEVELS];
-        for (int l = 0; l < mg->nlevels; l++) cur0[l] = mg->lv[l].cur;
         MG_CUDA(cudaStreamBeginCapture(mg->stream, cudaStreamCaptureModeThreadLocal));
         st = vcycle_rec(mg, level, v1, v2);
         cudaError_t e = cudaStreamEndCapture(mg->stream, &graph);
+        g->cur_end = 0;
         for (int l = 0; l < mg->nlevels; l++) { /* nothing ran during the capture: undo the host-side buffer flips */
-            if (mg->lv[l].cur != cur0[l] && e == cudaSuccess) e = cudaErrorNotSupported; /* a replay must end on the buffers it started from */
-            mg->lv[l].cur = cur0[l];
-            mg->lv[l].v = mg->lv[l].vbuf[cur0[l]];
+            if (l < 32) g->cur_end |= (unsigned)mg->lv[l].cur << l;
+            mg->lv[l].cur = (int)((cur_now >> l) & 1u);
+            mg->lv[l].v = mg->lv[l].vbuf[mg->lv[l].cur];
         }
         g->launches = mg->launches - l0;
         g->halo_bytes = mg->halo_bytes - h0;
@@ -1134,6 +1242,10 @@ int mg3d_vcycle(mg3d_t* mg, int level, int v1, int v2)
         }
     }
     MG_CUDA(cudaGraphLaunch(g->exec, mg->stream));
+    for (int l = 0; l < mg->nlevels && l < 32; l++) { /* the replay leaves every level on the buffer the capture ended on */
+        mg->lv[l].cur = (int)((g->cur_end >> l) & 1u);
+        mg->lv[l].v = mg->lv[l].vbuf[mg->lv[l].cur];
+    }
     mg->launches += g->launches;
     mg->halo_bytes += g->halo_bytes;
     return MG_OK;

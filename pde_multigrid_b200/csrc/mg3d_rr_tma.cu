@@ -330,8 +330,7 @@ int launch_k(cudaStream_t s, const CUtensorMap& m0, const CUtensorMap& m1, const
              T* cv, mg_geom3d gc, int czl_lo, int czl_hi, dim3 grid, int zchunk, double* part)
 {
     const size_t smem = smem_bytes_t<T>();
-    static bool attr = (cudaFuncSetAttribute(k_residual_restrict_tma<T, FAST, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_t<T>()), true);
-    (void)attr;
+    MG_SET_SMEM_LIMIT((k_residual_restrict_tma<T, FAST, NORM>), smem_bytes_t<T>());
     k_residual_restrict_tma<T, FAST, NORM><<<grid, NT, smem, s>>>(m0, m1, f, gf, narrow<T>(c), corrected, cf, cv, gc, czl_lo, czl_hi, zchunk, part);
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }

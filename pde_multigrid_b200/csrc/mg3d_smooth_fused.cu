@@ -58,8 +58,11 @@ struct FusedMaps {
 
 template <typename T, bool FAST>
 __global__ void __launch_bounds__(NT, 1)
-k_relax_fused2(const __grid_constant__ FusedMaps maps, T* __restrict__ v_out, mg_geom3d g, Coef3<T> c, int zchunk)
+k_relax_fused2(const __grid_constant__ FusedMaps maps, T* __restrict__ v_out, mg_geom3d g, Coef3<T> c, int zchunk, unsigned int* cond)
 {
+    // conditional launch (the exact fallback of mg3d_smooth_pipe.cu): nothing to do unless the flag was raised.  Nobody
+    // changes the flag while this grid runs (the last CTA to finish clears it), so every CTA takes the same branch.
+    if (cond && *reinterpret_cast<volatile unsigned int*>(cond) == 0u) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int A = FBox<T>::A, W = FBox<T>::W, SUBS = FBox<T>::SUB_STRIDE, SLOT = FBox<T>::SLOT;
     constexpr uint32_t SUB_BYTES = FBox<T>::SUB * sizeof(T);
@@ -194,22 +197,29 @@ k_relax_fused2(const __grid_constant__ FusedMaps maps, T* __restrict__ v_out, mg
                 if (st_ok[s]) __stcs(v_out + st_dst[s] + (long long)ps * g.plane, ring[sb[5] + st_src[s]]);
         }
     }
+    if (cond) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+            if (atomicAdd(cond + 1, 1u) == total - 1) { cond[1] = 0u; __threadfence(); cond[0] = 0u; }
+        }
+    }
 }
 
 template <typename T>
 size_t smem_bytes_t() { return (size_t)NS * FBox<T>::SLOT * sizeof(T) + NS * sizeof(uint64_t); }
 
 template <typename T, bool FAST>
-int launch_k(cudaStream_t s, const FusedMaps& m, T* v_out, mg_geom3d g, mg_coef3d c, dim3 grid, int zchunk)
+int launch_k(cudaStream_t s, const FusedMaps& m, T* v_out, mg_geom3d g, mg_coef3d c, dim3 grid, int zchunk, unsigned int* cond)
 {
-    static bool attr = (cudaFuncSetAttribute(k_relax_fused2<T, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_t<T>()), true);
-    (void)attr;
-    k_relax_fused2<T, FAST><<<grid, NT, smem_bytes_t<T>(), s>>>(m, v_out, g, narrow<T>(c), zchunk);
+    MG_SET_SMEM_LIMIT((k_relax_fused2<T, FAST>), smem_bytes_t<T>());
+    k_relax_fused2<T, FAST><<<grid, NT, smem_bytes_t<T>(), s>>>(m, v_out, g, narrow<T>(c), zchunk, cond);
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 
 template <typename T>
-int launch(cudaStream_t s, const void* const maps4[4], T* v_out, mg_geom3d g, mg_coef3d c)
+int launch(cudaStream_t s, const void* const maps4[4], T* v_out, mg_geom3d g, mg_coef3d c, unsigned int* cond)
 {
     FusedMaps m;
     memcpy(&m.v[0], maps4[0], sizeof(CUtensorMap));
@@ -229,16 +239,17 @@ int launch(cudaStream_t s, const void* const maps4[4], T* v_out, mg_geom3d g, mg
     }
     const int zchunk = (g.nzl + nchunk - 1) / nchunk;
     dim3 grid(tx, ty, (g.nzl + zchunk - 1) / zchunk);
-    if (c.fast_den) return launch_k<T, true>(s, m, v_out, g, c, grid, zchunk);
-    return launch_k<T, false>(s, m, v_out, g, c, grid, zchunk);
+    if (c.fast_den) return launch_k<T, true>(s, m, v_out, g, c, grid, zchunk, cond);
+    return launch_k<T, false>(s, m, v_out, g, c, grid, zchunk, cond);
 }
 
 }  // namespace
 
 /* maps4: tensor maps of {v_in colour 0, v_in colour 1, f colour 0, f colour 1} with box
    (MGK3D_FU_BOX_I(esize), MGK3D_FU_BOX_Y, 1); v_out: the other v buffer of the level (all planes are written) */
-extern "C" int mgk3d_relax_fused2(cudaStream_t s, int dtype, const void* const maps4[4], void* v_out, mg_geom3d g, mg_coef3d c)
+extern "C" int mgk3d_relax_fused2(cudaStream_t s, int dtype, const void* const maps4[4], void* v_out, mg_geom3d g, mg_coef3d c,
+                                  unsigned int* cond)
 {
-    if (dtype == 0) return launch<float>(s, maps4, (float*)v_out, g, c);
-    return launch<double>(s, maps4, (double*)v_out, g, c);
+    if (dtype == 0) return launch<float>(s, maps4, (float*)v_out, g, c, cond);
+    return launch<double>(s, maps4, (double*)v_out, g, c, cond);
 }

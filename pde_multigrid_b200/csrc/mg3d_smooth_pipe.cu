@@ -1,0 +1,434 @@
+// mg3d_smooth_pipe.cu -- temporally blocked smoother, register-tiled: TWO full red-black Gauss-Seidel sweeps (four
+// half-sweeps R1, B1, R2, B2) of MultiGrid3D::Relax (N3/MultiGrid3D.cpp:489-567) in ONE pass over HBM.
+//
+// HBM traffic per pass: the colour-1 ("black") half of v in, f in, both halves of v out = 2.5*B*N bytes for two
+// sweeps; the four colour launches of mg3d_smooth_tma.cu move 6*B*N.  (The colour-0 half of v is never read: the
+// first half-sweep overwrites every interior colour-0 point from its colour-1 neighbours and f alone, :532; only
+// the Dirichlet points of colour 0 are fetched.)
+//
+// Organisation.  A CTA owns a column of LW x TYT (half-index x row) sites and marches along z; a site (i, y) holds
+// the two points x = 2i, 2i+1 of the row.  A thread owns the sites (lane, R consecutive rows) and keeps, in REGISTERS,
+// the z-window (3 planes) of every stage's output at its own sites, so of the six neighbours of an update
+//     D, U          are registers (same site, planes z-1 / z+1 of the previous stage),
+//     O or E        one is a register (the other point of the same site), the other comes from the x-neighbour lane,
+//     N, S          one is a register (the thread's other row), the other comes from the neighbouring thread row,
+// i.e. 2 shared-memory loads + 1 store per update instead of 7 + 1 in mg3d_smooth_fused.cu (whose shared-memory data
+// pipe was the limiter).  The stages are skewed by ONE plane each: at step p (raw plane p arrives by TMA)
+//     R1 @ p-1,  B1 @ p-2,  R2 @ p-3,  B2 @ p-4   -> plane p-4 is final and is stored (out of place).
+// Stage s+1 needs the neighbours' stage-s values only on its own centre plane, which was published one step earlier,
+// and its own stage-s value of the plane above straight from a register: ONE __syncthreads per step.
+// Halo: four half-sweeps consume 4 points on every side of the tile (2 half-indices in x, 4 rows in y, 4 planes in z at
+// the ends of a z chunk); values in the halo are computed redundantly and never stored.
+//
+// Arithmetic, bit-identical to the reference.  This kernel is only used when every h^2 is a power of two and
+// hx = hy = hz (the reference problem on [0,1]^3): all weights are c = h^4, exact scalings, so with s6 the
+// reference's left-to-right sum O+E+N+S+D+U
+//     reference:  ((O c + E c + N c + S c + D c + U c) - f h^6) / (6 c)   ==   (s6 - f h^2) / 6     (ours)
+// rounding for rounding (scaling by a power of two commutes with RN), and f h^2 is exact, so the subtraction is one
+// FMA; the quotient by 6 is the Markstein sequence of mg_exact.cuh: 9 fp64 instructions per update instead of 20.
+// The identity fails only if an intermediate of the reference underflows (or ours overflows): every value that enters
+// or leaves a stage is range-checked with 4 integer instructions (zero, or magnitude in [2^lo, 2^hi]); a violation
+// raises a flag in global memory and the host-enqueued fallback (mg3d_smooth_fused.cu with the literal arithmetic,
+// conditional on that flag) recomputes the pass from the untouched input buffer.  tests/test_smoother_pipe_gpu.py.
+// MG_ARITH_FAST (template ARITH = 1): pairwise sum and multiplication by 1/6, no range check -- 7 instructions, results
+// within 1e-10 (fp64) / 1e-5 (fp32) of the reference instead of identical.
+#include <type_traits>
+
+#include "mg3d_device.cuh"
+#include "mg_tma.cuh"
+
+using namespace mgx;
+using namespace mg3;
+using namespace mgtma;
+
+namespace {
+
+constexpr int LW = 32;               // sites per row of the tile = one warp
+constexpr int HXI = MGK3D_PP_HXI;    // halo in half-indices on each side (4 points)
+constexpr int HY = MGK3D_PP_HY;      // halo rows on each side
+constexpr int R = MGK3D_PP_R;        // rows per thread
+constexpr int NWARP = MGK3D_PP_NW;   // warps = thread rows
+constexpr int NT = 32 * NWARP;
+constexpr int TYT = R * NWARP;       // rows of the tile incl. halo
+constexpr int TXO = LW - 2 * HXI;    // output half-indices per tile
+constexpr int TYO = TYT - 2 * HY;    // output rows per tile
+constexpr int NRING = 6;             // slots per TMA ring (raw colour-1 v, f colour 0, f colour 1); steps are unrolled 6-fold
+constexpr int PF = 3;                // planes of prefetch: at step p the copies of raw(p+3), f0(p+2), f1(p+1) are issued
+constexpr int ZH = 4;                // z halo planes at each end of a chunk
+
+template <typename T> struct PBox {
+    static constexpr int PADL = MGK3D_PP_PADL(sizeof(T));  // columns left of lane 0 (keeps the TMA start 16-byte aligned)
+    static constexpr int W = MGK3D_PP_BOX_I(sizeof(T));    // row stride = TMA box width
+    static constexpr int SLOT = (W * TYT * (int)sizeof(T) + 127) / 128 * 128 / (int)sizeof(T);  // elements
+    // slot map (in slots): [0,6) raw v colour 1, [6,12) f colour 0, [12,18) f colour 1, [18,24) exchange r1, b1, r2 (2 each)
+    static constexpr int NSLOT = 3 * NRING + 6;
+    static constexpr int GUARD = 2 * W;  // addressable elements in front of slot 0 and behind the last slot (edge lanes / rows)
+};
+
+struct PipeMaps {
+    CUtensorMap vblack;  // colour-1 array of the input v, box (W, TYT, 1)
+    CUtensorMap f[2];    // colour arrays of f, same box
+};
+
+// range check of a value that enters a stage: +0, or lo <= |x| <= hi in exponent terms.  Everything else -- tiny, huge,
+// non-finite, and -0 (whose sign the FMA chain of the quotient would lose) -- leaves a nonzero mark in acc.
+__device__ __forceinline__ void guard(double x, unsigned lo, unsigned span, unsigned& acc)
+{
+    const unsigned h = (unsigned)__double2hiint(x);
+    if ((h & 0x7fffffffu) - lo > span) acc |= h | (unsigned)__double2loint(x);
+}
+__device__ __forceinline__ void guard(float x, unsigned lo, unsigned span, unsigned& acc)
+{
+    const unsigned h = __float_as_uint(x);
+    if ((h & 0x7fffffffu) - lo > span) acc |= h;
+}
+
+template <typename T, int ARITH>
+__device__ __forceinline__ T gs_update(T own, T nbx, T N, T S, T D, T U, T f, T h2, T y6)
+{
+    if (ARITH == 0) {
+        T s = add(own, nbx);  // O + E (commutative)
+        s = add(s, N);
+        s = add(s, S);
+        s = add(s, D);
+        s = add(s, U);
+        const T t = fma_(-f, h2, s);  // f*h2 is exact
+        if (sizeof(T) == 4) return div(t, T(6));
+        const T q = mul(t, y6);
+        const T r = fma_(T(-6), q, t);
+        return fma_(r, y6, q);
+    } else {
+        const T s = ((own + nbx) + (N + S)) + (D + U);
+        return fma_(-f, h2, s) * y6;
+    }
+}
+
+template <typename T, int ARITH>
+__global__ void __launch_bounds__(NT, 1)
+k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in, T* __restrict__ v_out, mg_geom3d g, T h2, T y6,
+              int zchunk, unsigned glo, unsigned gspan, unsigned int* __restrict__ flag)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int PADL = PBox<T>::PADL, W = PBox<T>::W, SLOT = PBox<T>::SLOT, NSLOT = PBox<T>::NSLOT, GUARD = PBox<T>::GUARD;
+    constexpr uint32_t SLOT_BYTES = W * TYT * sizeof(T);
+    // intermediates only need the range check where the exponent range is short (see guard_window): float
+    constexpr bool CHECK_MID = ARITH == 0 && sizeof(T) == 4;
+    constexpr int GUARD_AL = (GUARD * (int)sizeof(T) + 127) / 128 * 128 / (int)sizeof(T);
+    T* base = reinterpret_cast<T*>(smem_raw) + GUARD_AL;  // slot 0
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)NSLOT * SLOT + GUARD_AL);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = g.n, imax = (n - 1) / 2;
+    const int i0 = blockIdx.x * TXO, y0 = blockIdx.y * TYO;
+    const int zs = blockIdx.z * zchunk, ze = min(zs + zchunk, g.nzl);  // output planes [zs, ze)
+    const int pb = zs - ZH, nsteps = ze - zs + 2 * ZH;                  // raw planes pb .. pb+nsteps-1, one per step
+
+    if (tid == 0) {
+        prefetch_tensormap(&maps.vblack);
+        prefetch_tensormap(&maps.f[0]);
+        prefetch_tensormap(&maps.f[1]);
+        for (int s = 0; s < NRING; s++) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    // Everything starts as zero: edge lanes and rows read one element / row outside their slot (results that depend on it are
+    // never stored), the first steps read ring slots no copy has filled yet, and whatever the halo computes from that must
+    // stay finite and inside the guard window.
+    for (int k = tid; k < NSLOT * SLOT + 2 * GUARD_AL; k += NT) (base - GUARD_AL)[k] = T(0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order these generic-proxy writes before the TMA writes
+    __syncthreads();
+
+    const int bx0 = i0 - HXI - PADL, by0 = y0 - HY;  // box origin
+    // One group of copies per step, all first needed at the same later step, tracked by one mbarrier: issued at step m
+    // (raw plane pb+m arrives) for step m+PF: raw v colour 1 of plane p+PF, f colour 0 of plane p+PF-1 (R1), f colour 1 of
+    // plane p+PF-2 (B1).  Out-of-range coordinates zero-fill.
+    auto issue = [&](int slot, int pn) {  // slot = (step index of the consumer) % NRING, pn = its raw plane
+        mbar_arrive_expect_tx(&bars[slot], 3 * SLOT_BYTES);
+        tma_load_3d(base + (size_t)slot * SLOT, &maps.vblack, &bars[slot], bx0, by0, pn);
+        tma_load_3d(base + (size_t)(NRING + slot) * SLOT, &maps.f[0], &bars[slot], bx0, by0, pn - 1);
+        tma_load_3d(base + (size_t)(2 * NRING + slot) * SLOT, &maps.f[1], &bars[slot], bx0, by0, pn - 2);
+    };
+    if (tid == 0)
+        for (int k = 0; k < PF && k < nsteps; k++) issue(k, pb + k);
+
+    // ---- per-thread constants -------------------------------------------------------------------------------
+    // Site (lane, row r): half-index i, row y.  On plane z its colour-c point has x = 2i + ((c + y + z) & 1).  Steps are
+    // unrolled six-fold, so relative to the first plane every parity is a compile-time bit XOR s0 = (y_row0 + z0 + pb) & 1.
+    const int i = i0 - HXI + lane;
+    const int tr0 = R * warp, yr0 = y0 - HY + tr0;
+    const int s0 = (yr0 + g.z0 + pb) & 1;
+    const T* sb = base + tr0 * W + lane + PADL;   // own site of row 0 in slot 0; row r: + r*W; slot j: + j*SLOT
+    const T* sP = sb + (2 * s0 - 1);              // x-neighbour of row r when ((r & 1) ^ CV) == 0 ...
+    const T* sM = sb - (2 * s0 - 1);              // ... and when it is 1 (CV: see step())
+    T* sw = base + tr0 * W + lane + PADL;
+    // byte offset of the site inside a colour plane (Dirichlet loads and the stores; both are predicated on the point existing)
+    unsigned goff[R];
+    const long long pbytes = g.plane * (long long)sizeof(T);
+    // mA: the point of the site with x parity s_r = s0 ^ (r & 1); mB: the other one.  bit r: interior in (x, y);
+    // bit 8+r: exists and lies in the tile's output region (store predicate); bit 16+r: exists in the grid
+    unsigned mA = 0, mB = 0;
+    {
+        const bool ex0 = i >= 0 && i <= imax, ex1 = i >= 0 && 2 * i + 1 <= n - 1;      // x = 2i / 2i+1 exists
+        const bool in0 = i >= 1 && 2 * i <= n - 2, in1 = i >= 0 && 2 * i + 1 <= n - 2;   // ... is interior in x
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int tr = tr0 + r, y = yr0 + r;
+            goff[r] = (unsigned)((min(max(y, 0), n - 1) * g.hp + min(max(i, 0), imax)) * (int)sizeof(T));
+            const bool y_in = y >= 0 && y <= n - 1, y_int = y >= 1 && y <= n - 2;
+            const bool outr = tr >= HY && tr < HY + TYO && lane >= HXI && lane < HXI + TXO;
+            const int sr = s0 ^ (r & 1);
+            const bool exA = sr ? ex1 : ex0, exB = sr ? ex0 : ex1, inA = sr ? in1 : in0, inB = sr ? in0 : in1;
+            if (y_int && inA) mA |= 1u << r;
+            if (y_int && inB) mB |= 1u << r;
+            if (y_in && exA && outr) mA |= 1u << (8 + r);
+            if (y_in && exB && outr) mB |= 1u << (8 + r);
+            if (y_in && exA) mA |= 1u << (16 + r);
+            if (y_in && exB) mB |= 1u << (16 + r);
+        }
+    }
+    // uniform plane pointers, advanced by one plane per step
+    const char* va = (const char*)v_in + (long long)pb * pbytes;                 // input v colour 0 (Dirichlet points), plane p
+    char* oa = (char*)v_out + (long long)(pb - 4) * pbytes;                      // output colour 0, plane p-4
+    char* ob = (char*)(v_out + g.cstride) + (long long)(pb - 4) * pbytes;        // output colour 1, plane p-4
+
+    // ---- register state: z-windows (3 planes) of the raw colour-1 values and of the outputs of R1, B1, R2 -----
+    T wr[3][R], w1[3][R], w2[3][R], w3[3][R], rr_n[R];
+#pragma unroll
+    for (int s = 0; s < 3; s++)
+#pragma unroll
+        for (int r = 0; r < R; r++) wr[s][r] = w1[s][r] = w2[s][r] = w3[s][r] = T(0);
+#pragma unroll
+    for (int r = 0; r < R; r++) rr_n[r] = T(0);
+    unsigned bad = 0;
+    unsigned phase = 0;  // mbarrier parity of the ring: flips every NRING steps
+
+    // One step = raw plane p = pb + m arrives; J6 = m % 6 is a template constant, so ring slots, exchange slots,
+    // window rotation and parities are all compile-time.
+    // FAST (compile-time): the tile with its halo lies strictly inside the grid in x and y and the planes p-4 .. p are all
+    // interior and inside the chunk's pipeline steady state -- no Dirichlet points, no masks, no conditional copies.
+    auto step = [&](auto Jc, auto Fc, int p) {
+        constexpr int J6 = decltype(Jc)::value, J = J6 % 3, J1 = (J + 1) % 3, J2 = (J + 2) % 3;
+        constexpr bool FAST = decltype(Fc)::value;
+        constexpr int E = J6 & 1;          // exchange slot written for planes p-1 / p-3 (r1, r2) is E, for p-2 (b1) is E^1
+        constexpr int CV = (J6 + 1) & 1;   // the updated point of row r has x parity s_r ^ CV in ALL four stages of this step
+        const unsigned mU = CV ? mB : mA, mO = CV ? mA : mB;
+        // the Dirichlet values of colour 0 on plane p-1, loaded one step ago
+        T rkeep[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            rkeep[r] = FAST ? T(0) : rr_n[r];
+            if (ARITH == 0 && !FAST) guard(rr_n[r], glo, gspan, bad);
+        }
+        if (!FAST) {
+            const int zg = g.z0 + p;
+            // Dirichlet points of colour 0 on plane p (parity s_r ^ CV ^ 1): exist and are not interior
+            const unsigned mz = (p >= 0 && p < g.nzl) ? ((mO >> 16) & ~(((unsigned)(zg - 1) <= (unsigned)(n - 3)) ? mO : 0u)) : 0u;
+#pragma unroll
+            for (int r = 0; r < R; r++) rr_n[r] = ((mz >> r) & 1u) ? __ldg((const T*)(va + goff[r])) : T(0);
+        }
+        if (tid == 0 && (FAST || p - pb + PF < nsteps)) issue((J6 + PF) % NRING, p + PF);
+        mbar_wait(&bars[J6], phase);
+        constexpr int OFF_P = J6 * SLOT;                         // raw plane p
+        constexpr int OFF_C = ((J6 + NRING - 1) % NRING) * SLOT; // raw plane p-1
+        // the copy group of step m carries raw(p), f0(p-1), f1(p-2) in slot m % 6 of the three rings
+        constexpr int F0A = (NRING + J6) * SLOT;                            // f colour 0, plane p-1
+        constexpr int F0B = (NRING + (J6 + NRING - 2) % NRING) * SLOT;      // f colour 0, plane p-3 (group of step m-2)
+        constexpr int F1A = (2 * NRING + J6) * SLOT;                        // f colour 1, plane p-2
+        constexpr int F1B = (2 * NRING + (J6 + NRING - 2) % NRING) * SLOT;  // f colour 1, plane p-4 (group of step m-2)
+        constexpr int XB = 3 * NRING;
+        constexpr int X1W = (XB + 0 + E) * SLOT, X1R = (XB + 0 + (E ^ 1)) * SLOT;
+        constexpr int X2W = (XB + 2 + (E ^ 1)) * SLOT, X2R = (XB + 2 + E) * SLOT;
+        constexpr int X3W = (XB + 4 + E) * SLOT, X3R = (XB + 4 + (E ^ 1)) * SLOT;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            wr[J][r] = sb[OFF_P + r * W];
+            if (ARITH == 0) guard(wr[J][r], glo, gspan, bad);
+        }
+        // One half-sweep stage on plane z for the thread's R sites: the colour being updated reads the other colour's
+        // window (D, C, U = planes z-1, z, z+1 at the own sites), the neighbours on plane z in shared memory at OFF and
+        // f at FOFF.  GF: first use of these f values -> range-check them, where they are used (f of boundary points is
+        // never read by an update, and the reference problem has f = -0.0 on the faces x, y, z = 0).
+        auto stage = [&](int z, auto offc, auto foffc, auto gfc, const T (&wD)[R], const T (&wC)[R], const T (&wU)[R], const T (&keep)[R],
+                         T (&out)[R]) {
+            constexpr int OFF = decltype(offc)::value, FOFF = decltype(foffc)::value;
+            constexpr bool GF = decltype(gfc)::value;
+            const int zg = g.z0 + z;
+            const unsigned mz = FAST ? ~0u : ((unsigned)(zg - 1) <= (unsigned)(n - 3)) ? mU : 0u;
+            T nbx[R], ff[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                nbx[r] = (((r & 1) ^ CV) ? sM : sP)[OFF + r * W];
+                ff[r] = sb[FOFF + r * W];
+            }
+            const T nN = sb[OFF - W], nS = sb[OFF + R * W];
+            T o[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const T N = r == 0 ? nN : wC[r > 0 ? r - 1 : 0];
+                const T S = r == R - 1 ? nS : wC[r < R - 1 ? r + 1 : 0];
+                o[r] = gs_update<T, ARITH>(wC[r], nbx[r], N, S, wD[r], wU[r], ff[r], h2, y6);
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                out[r] = (FAST || ((mz >> r) & 1u)) ? o[r] : keep[r];
+                if (ARITH == 0 && GF && (FAST || ((mz >> r) & 1u))) guard(ff[r], glo, gspan, bad);
+                if (CHECK_MID) guard(out[r], glo, gspan, bad);
+            }
+        };
+        using std::integral_constant;
+        using GFY = integral_constant<bool, true>;
+        using GFN = integral_constant<bool, false>;
+        // R1 @ p-1: colour 0 from raw colour 1
+        stage(p - 1, integral_constant<int, OFF_C>{}, integral_constant<int, F0A>{}, GFY{}, wr[J1], wr[J2], wr[J], rkeep, w1[J2]);
+#pragma unroll
+        for (int r = 0; r < R; r++) sw[X1W + r * W] = w1[J2][r];
+        // B1 @ p-2: colour 1 from R1
+        stage(p - 2, integral_constant<int, X1R>{}, integral_constant<int, F1A>{}, GFY{}, w1[J], w1[J1], w1[J2], wr[J1], w2[J1]);
+#pragma unroll
+        for (int r = 0; r < R; r++) sw[X2W + r * W] = w2[J1][r];
+        // R2 @ p-3: colour 0 from B1
+        stage(p - 3, integral_constant<int, X2R>{}, integral_constant<int, F0B>{}, GFN{}, w2[J2], w2[J], w2[J1], w1[J], w3[J]);
+#pragma unroll
+        for (int r = 0; r < R; r++) sw[X3W + r * W] = w3[J][r];
+        // B2 @ p-4: colour 1 from R2; plane p-4 is final
+        T b2[R];
+        stage(p - 4, integral_constant<int, X3R>{}, integral_constant<int, F1B>{}, GFN{}, w3[J1], w3[J2], w3[J], w2[J2], b2);
+        const int zo = p - 4;
+        {
+            // colour 0 was updated by R2 on plane p-3 at parity s_r ^ CV, so on plane p-4 it sits at the other parity (mO),
+            // colour 1 at s_r ^ CV (mU); planes outside [zs, ze) belong to the z halo of the chunk
+            const bool zok = FAST || (zo >= zs && zo < ze);
+            const unsigned m0 = zok ? (mO >> 8) : 0u, m1 = zok ? (mU >> 8) : 0u;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if ((m0 >> r) & 1u) __stcs((T*)(oa + goff[r]), w3[J2][r]);
+                if ((m1 >> r) & 1u) __stcs((T*)(ob + goff[r]), b2[r]);
+            }
+        }
+        va += pbytes; oa += pbytes; ob += pbytes;
+        __syncthreads();
+    };
+
+    // steady-state steps m in [m_lo, m_hi]: planes p-4 .. p interior (global z in [1, n-2]) and stored (p-4 >= zs), the
+    // copy group issued for step m+PF exists; interior tile in x, y
+    const bool tile_fast = i0 - HXI >= 1 && 2 * (i0 - HXI + LW - 1) + 1 <= n - 2 && y0 - HY >= 1 && y0 - HY + TYT - 1 <= n - 2;
+    const int m_lo = max(2 * ZH, 5 - g.z0 - pb), m_hi = min(n - 2 - g.z0 - pb, nsteps - 1 - PF);
+    using std::integral_constant;
+    for (int m = 0; m < nsteps; m += 6) {
+        const int p = pb + m;
+        if (tile_fast && m >= m_lo && m + 5 <= m_hi) {
+            step(integral_constant<int, 0>{}, integral_constant<bool, true>{}, p);
+            step(integral_constant<int, 1>{}, integral_constant<bool, true>{}, p + 1);
+            step(integral_constant<int, 2>{}, integral_constant<bool, true>{}, p + 2);
+            step(integral_constant<int, 3>{}, integral_constant<bool, true>{}, p + 3);
+            step(integral_constant<int, 4>{}, integral_constant<bool, true>{}, p + 4);
+            step(integral_constant<int, 5>{}, integral_constant<bool, true>{}, p + 5);
+        } else {
+            step(integral_constant<int, 0>{}, integral_constant<bool, false>{}, p);
+            if (m + 1 < nsteps) step(integral_constant<int, 1>{}, integral_constant<bool, false>{}, p + 1);
+            if (m + 2 < nsteps) step(integral_constant<int, 2>{}, integral_constant<bool, false>{}, p + 2);
+            if (m + 3 < nsteps) step(integral_constant<int, 3>{}, integral_constant<bool, false>{}, p + 3);
+            if (m + 4 < nsteps) step(integral_constant<int, 4>{}, integral_constant<bool, false>{}, p + 4);
+            if (m + 5 < nsteps) step(integral_constant<int, 5>{}, integral_constant<bool, false>{}, p + 5);
+        }
+        phase ^= 1u;
+    }
+    if (ARITH == 0 && bad) atomicOr(flag, 1u);
+}
+
+template <typename T>
+size_t smem_bytes_t()
+{
+    const size_t guard_al = ((size_t)PBox<T>::GUARD * sizeof(T) + 127) / 128 * 128;
+    return (size_t)PBox<T>::NSLOT * PBox<T>::SLOT * sizeof(T) + 2 * guard_al + NRING * sizeof(uint64_t);
+}
+
+// Exponent window of the range check, h = 2^-k.  Where the scaled formula could differ from the reference:
+//   * a product of the reference (x*h^4, f*h^6) must not lose bits to underflow: x nonzero on the grid 2^(e-p)
+//     (p = significand bits - 1) needs e - p - 6k >= emin_subnormal;
+//   * double only checks what ENTERS the pass (raw v, f, Dirichlet values).  Each stage can lose at most p + 3 bits of
+//     magnitude to cancellation (a nonzero sum is a multiple of its inputs' grid, and f*h^2 sits 2k below f), so after four
+//     stages values are >= 2^(lo - 2k - 3(p+3)) on the grid 2^(lo - 2k - 3(p+3) - p): with lo >= -857 + 6k every product
+//     of the reference is still exact, and with lo >= -697 + 2k the Markstein residual stays normal (mg_exact.cuh);
+//   * float has no exponent range to spare for that argument: every stage output is checked as well and the quotient is
+//     the IEEE division, which leaves lo >= -126 + 6k for the products;
+//   * hi: four stages of sums of six can grow a value by less than 2^7.
+template <typename T> void guard_window(double h2, unsigned* glo, unsigned* gspan);
+template <> void guard_window<double>(double h2, unsigned* glo, unsigned* gspan)
+{
+    int e;
+    frexp(h2, &e);  // h2 = 2^(e-1) = 2^(-2k)
+    const int k = -(e - 1) / 2;
+    const int a = -857 + 6 * k, b = -697 + 2 * k;
+    const int lo = (a > b ? a : b) + 8, hi = 1010;
+    const unsigned L = (unsigned)(lo + 1023) << 20, H = (((unsigned)(hi + 1023 + 1)) << 20) - 1;
+    *glo = L;
+    *gspan = H - L;
+}
+template <> void guard_window<float>(double h2, unsigned* glo, unsigned* gspan)
+{
+    int e;
+    frexp(h2, &e);
+    const int k = -(e - 1) / 2;
+    const int lo = -126 + 6 * k + 4, hi = 115;
+    const unsigned L = (unsigned)(lo + 127) << 23, H = (((unsigned)(hi + 127 + 1)) << 23) - 1;
+    *glo = L;
+    *gspan = H - L;
+}
+
+template <typename T, int ARITH>
+int launch_k(cudaStream_t s, const PipeMaps& m, const T* v_in, const T* f, T* v_out, mg_geom3d g, mg_coef3d c, dim3 grid, int zchunk,
+             unsigned int* flag)
+{
+    MG_SET_SMEM_LIMIT((k_relax_pipe2<T, ARITH>), smem_bytes_t<T>());
+    unsigned glo, gspan;
+    guard_window<T>(c.hx2, &glo, &gspan);
+    const T y6 = T(1) / T(6);
+    (void)f;  // f only enters through its tensor maps
+    k_relax_pipe2<T, ARITH><<<grid, NT, smem_bytes_t<T>(), s>>>(m, v_in, v_out, g, (T)c.hx2, y6, zchunk, glo, gspan, flag);
+    return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
+}
+
+template <typename T>
+int launch(cudaStream_t s, const void* const maps3[3], const T* v_in, const T* f, T* v_out, mg_geom3d g, mg_coef3d c, int arith,
+           unsigned int* flag)
+{
+    PipeMaps m;
+    memcpy(&m.vblack, maps3[0], sizeof(CUtensorMap));
+    memcpy(&m.f[0], maps3[1], sizeof(CUtensorMap));
+    memcpy(&m.f[1], maps3[2], sizeof(CUtensorMap));
+    const int tx = ((g.n + 1) / 2 + TXO - 1) / TXO, ty = (g.n + TYO - 1) / TYO;
+    // z chunks: every chunk pays 2*ZH planes of warm-up plus the pipeline depth; more chunks balance the waves of one-CTA SMs
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms < 1) sms = 148;
+    }
+    int nchunk = 1;
+    double best = 1e30;
+    for (int k = 1; k <= 16; k++) {
+        const int zc = (g.nzl + k - 1) / k;
+        if (k > 1 && zc < 32) break;
+        const long long ctas = (long long)tx * ty * ((g.nzl + zc - 1) / zc);
+        const double cost = (double)((ctas + sms - 1) / sms) * (zc + 2 * ZH + 3);
+        if (cost < best) { best = cost; nchunk = k; }
+    }
+    const int zchunk = (g.nzl + nchunk - 1) / nchunk;
+    dim3 grid(tx, ty, (g.nzl + zchunk - 1) / zchunk);
+    if (arith) return launch_k<T, 1>(s, m, v_in, f, v_out, g, c, grid, zchunk, flag);
+    return launch_k<T, 0>(s, m, v_in, f, v_out, g, c, grid, zchunk, flag);
+}
+
+}  // namespace
+
+/* maps3: tensor maps of {v_in colour 1, f colour 0, f colour 1} with box (MGK3D_PP_BOX_I(esize), MGK3D_PP_BOX_Y, 1).
+   Requires c.fast_den and hx2 == hy2 == hz2 (checked by the caller).  arith 0: bit-exact, *flag is raised when a value
+   left the range in which the scaled formula is provably identical to the reference's (the caller enqueues the
+   conditional literal-arithmetic pass after this one); arith 1: MG_ARITH_FAST. */
+extern "C" int mgk3d_relax_pipe2(cudaStream_t s, int dtype, const void* const maps3[3], const void* v_in, const void* f, void* v_out,
+                                 mg_geom3d g, mg_coef3d c, int arith, unsigned int* flag)
+{
+    if (dtype == 0) return launch<float>(s, maps3, (const float*)v_in, (const float*)f, (float*)v_out, g, c, arith, flag);
+    return launch<double>(s, maps3, (const double*)v_in, (const double*)f, (double*)v_out, g, c, arith, flag);
+}

@@ -140,12 +140,10 @@ int launch(cudaStream_t s, const void* map_other, T* v_own, const T* f_own, mg_g
     CUtensorMap map;
     memcpy(&map, map_other, sizeof map);
     if (c.fast_den) {
-        static bool attr = (cudaFuncSetAttribute(k_relax_colour_tma<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(sizeof(T))), true);
-        (void)attr;
+        MG_SET_SMEM_LIMIT((k_relax_colour_tma<T, true>), smem_bytes(sizeof(T)));
         k_relax_colour_tma<T, true><<<grid, NT, smem, s>>>(map, v_own, f_own, g, narrow<T>(c), colour, zl_lo, zl_hi, zchunk);
     } else {
-        static bool attr = (cudaFuncSetAttribute(k_relax_colour_tma<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(sizeof(T))), true);
-        (void)attr;
+        MG_SET_SMEM_LIMIT((k_relax_colour_tma<T, false>), smem_bytes(sizeof(T)));
         k_relax_colour_tma<T, false><<<grid, NT, smem, s>>>(map, v_own, f_own, g, narrow<T>(c), colour, zl_lo, zl_hi, zchunk);
     }
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;

@@ -149,8 +149,7 @@ int launch(cudaStream_t s, int nlev, const mg_geom3d* g, const mg_coef3d* c, voi
     const size_t smem = elems * sizeof(T);
 #define MG_TAIL_LAUNCH(FD, FH)                                                                                          \
     do {                                                                                                                \
-        static bool attr = (cudaFuncSetAttribute(k_vcycle_tail<T, FD, FH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), true); \
-        (void)attr;                                                                                                     \
+        MG_SET_SMEM_LIMIT((k_vcycle_tail<T, FD, FH>), 200 * 1024);                                                      \
         k_vcycle_tail<T, FD, FH><<<1, NT, smem, s>>>(a);                                                                \
     } while (0)
     if (fast_den && fast_h) MG_TAIL_LAUNCH(true, true);

@@ -125,6 +125,12 @@ int mg_comm_allreduce_sum_max(mg_comm* c, double* buf2, cudaStream_t s)
     return MG_OK;
 }
 
+int mg_comm_allreduce_u64_sum(mg_comm* c, unsigned long long* buf1, cudaStream_t s)
+{
+    MG_NCCL(N.AllReduce(buf1, buf1, 1, ncclUint64, ncclSum, c->comm, s));
+    return MG_OK;
+}
+
 int mg_comm_allgather_inplace(mg_comm* c, void* recvbuf, size_t count, int dtype, cudaStream_t s)
 {
     const char* send = (const char*)recvbuf + (size_t)c->rank * count * mg_esize(dtype);

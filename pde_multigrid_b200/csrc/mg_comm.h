@@ -22,6 +22,8 @@ int mg_comm_send(mg_comm* c, const void* buf, size_t count, int dtype, int peer,
 int mg_comm_recv(mg_comm* c, void* buf, size_t count, int dtype, int peer, cudaStream_t s);
 /* in-place on device doubles: buf[0] summed, buf[1] maximised over the ranks */
 int mg_comm_allreduce_sum_max(mg_comm* c, double* buf2, cudaStream_t s);
+/* in-place on one device uint64: summed (mod 2^64) over the ranks */
+int mg_comm_allreduce_u64_sum(mg_comm* c, unsigned long long* buf1, cudaStream_t s);
 /* in-place all-gather: every rank contributes `count` elements located at recvbuf + rank*count */
 int mg_comm_allgather_inplace(mg_comm* c, void* recvbuf, size_t count, int dtype, cudaStream_t s);
 

@@ -23,16 +23,23 @@ __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf
 
 // Correctly rounded a/b from a correctly rounded reciprocal y = RN(1/b) computed once on the host
 // (Markstein 1990: q = RN(a*y); r = a - b*q exactly with one FMA; q' = RN(q + r*y) is the correctly
-// rounded quotient).  Three pipe operations instead of the ~20-instruction IEEE division sequence;
-// bit-identical to a/b whenever q is finite and no intermediate underflows.  Non-finite q (inf/NaN
-// input) is passed through so that overflowed REF_COMPAT runs still match the reference.
+// rounded quotient).  Three pipe operations instead of the ~20-instruction IEEE division sequence.
+// Bit-identical to a/b in every case:
+//   * r == 0: q is already the exact quotient (this also keeps the sign of a zero: the FMA chain would turn -0 into +0);
+//   * |a| below 2^(emin + 2p + 4) (p = significand bits): the residual r could be subnormal and lose bits, so the
+//     IEEE division is used there -- never reached by values of an actual solve, see tests/test_smoother_pipe_gpu.py;
+//   * non-finite q (inf/NaN input): passed through, so that overflowed REF_COMPAT runs still match the reference.
+__device__ __forceinline__ bool div_small(double a) { return fabs(a) < 0x1p-914; }
+__device__ __forceinline__ bool div_small(float a) { return fabsf(a) < 0x1p-76f; }
+
 template <typename T>
 __device__ __forceinline__ T div_by_const(T a, T b, T y)
 {
+    if (div_small(a)) return div(a, b);
     T q = mul(a, y);
     T r = fma_(-b, q, a);
     T q2 = fma_(r, y, q);
-    return (q - q == T(0)) ? q2 : q;  // q - q is NaN for inf/NaN
+    return (q - q == T(0) && r != T(0)) ? q2 : q;  // q - q is NaN for inf/NaN
 }
 
 }  // namespace mgx

@@ -71,7 +71,23 @@ int mgk3d_relax_colour_tma(cudaStream_t s, int dtype, const void* tmap_other, vo
 #define MGK3D_FU_TY 16
 #define MGK3D_FU_BOX_I(esize) (MGK3D_FU_TI + 2 * (16 / (int)(esize)))
 #define MGK3D_FU_BOX_Y (MGK3D_FU_TY + 8)
-int mgk3d_relax_fused2(cudaStream_t s, int dtype, const void* const maps4[4], void* v_out, mg_geom3d g, mg_coef3d c);
+/* cond: NULL = always run; otherwise {flag, done counter}: the pass runs only when *flag != 0 (raised by
+   mgk3d_relax_pipe2) and the last CTA to finish clears both words */
+int mgk3d_relax_fused2(cudaStream_t s, int dtype, const void* const maps4[4], void* v_out, mg_geom3d g, mg_coef3d c,
+                       unsigned int* cond);
+/* register-tiled temporally blocked smoother (mg3d_smooth_pipe.cu): TWO full RB sweeps per pass, out of place, 2.5*B*N
+   bytes.  maps3 = tensor maps of {v_in colour 1, f colour 0, f colour 1} with box (MGK3D_PP_BOX_I(esize), MGK3D_PP_BOX_Y, 1).
+   Needs c.fast_den and hx2 == hy2 == hz2.  arith 0: bit-exact (flag raised when the exactness range check fails: the
+   caller follows up with mgk3d_relax_fused2(..., cond = flag)); arith 1: MG_ARITH_FAST */
+#define MGK3D_PP_HXI 2
+#define MGK3D_PP_HY 4
+#define MGK3D_PP_R 2
+#define MGK3D_PP_NW 16
+#define MGK3D_PP_PADL(esize) ((int)(esize) == 8 ? 0 : 2)
+#define MGK3D_PP_BOX_I(esize) (32 + 2 * MGK3D_PP_PADL(esize))
+#define MGK3D_PP_BOX_Y (MGK3D_PP_R * MGK3D_PP_NW)
+int mgk3d_relax_pipe2(cudaStream_t s, int dtype, const void* const maps3[3], const void* v_in, const void* f, void* v_out,
+                      mg_geom3d g, mg_coef3d c, int arith, unsigned int* flag);
 /* the coarse tail of a V-cycle in one launch (mg3d_tail.cu): V(v1,v2) on the sub-hierarchy g[0..nlev-1], g[0].n <=
    MGK3D_TAIL_N, every level resident in one CTA's shared memory */
 #define MGK3D_TAIL_N 17
@@ -123,6 +139,12 @@ int mgk3d_set(cudaStream_t s, int dtype, void* a, mg_geom3d g, double value, int
    the host libm exactly like the reference: f = (T)(-3*PI*PI*sx*sy*sz), N3/Grid3D.cpp:92 */
 int mgk3d_init_f(cudaStream_t s, int dtype, void* f, mg_geom3d g, const double* sx, const double* sy,
                  const double* sz, int zl_lo, int zl_hi);
+
+/* diagnostics (mg3d_diag.cu): *out += position-keyed checksum of local planes [zl_lo, zl_hi);
+   {sum, max} of |sin(PI x)sin(PI y)sin(PI z) - v| from host-libm sine tables (N3/Grid3D.cpp:136-159) */
+int mgk3d_field_checksum(cudaStream_t s, int dtype, const void* a, mg_geom3d g, int zl_lo, int zl_hi, unsigned long long* out);
+int mgk3d_abs_error(cudaStream_t s, int dtype, const void* v, mg_geom3d g, const double* sx, const double* sy, const double* sz,
+                    int zl_lo, int zl_hi, double* scratch, double* out2);
 
 /* dense (reference layout, x fastest, zl_hi-zl_lo planes starting at `dense`) <-> colour-split field */
 int mgk3d_repack(cudaStream_t s, int dtype, void* split, mg_geom3d g, void* dense, int to_device, int zl_lo, int zl_hi);

@@ -213,8 +213,14 @@ class MultiGrid3D(_MultiGridBase):
 
         self.rank, self.nranks = int(rank), int(nranks)
 
-    def set_smoother(self, smoother, sweeps_per_pass=1):
+    def set_smoother(self, smoother, sweeps_per_pass=None):
+        if sweeps_per_pass is None:
+            sweeps_per_pass = 2 if smoother in (_lib.MG_SMOOTHER_FUSED, _lib.MG_SMOOTHER_PIPE) else 1
         self._call("set_smoother", ctypes.c_int(smoother), ctypes.c_int(sweeps_per_pass))
+
+    def set_arith(self, arith):
+        """MG_ARITH_EXACT (bit-identical to the reference, default) or MG_ARITH_FAST."""
+        self._call("set_arith", ctypes.c_int(arith))
 
     def set_jacobi_weight(self, omega):
         """Relaxation weight of MG_SMOOTHER_JACOBI (default 6/7)."""
@@ -233,6 +239,18 @@ class MultiGrid3D(_MultiGridBase):
     @property
     def halo_bytes(self):
         return self._fn("halo_bytes")(self._h)
+
+    def field_checksum(self, level=0, field=MG_FIELD_V):
+        """Position-keyed additive checksum of a whole level field (all ranks return the global value)."""
+        out = ctypes.c_ulonglong()
+        self._call("field_checksum", ctypes.c_int(level), ctypes.c_int(field), ctypes.byref(out))
+        return out.value
+
+    def abs_error(self, level=0):
+        """(mean, max) over all points of |sin(pi x)sin(pi y)sin(pi z) - v|: Grid3D::PrintDiff as a reduction."""
+        mean, mx = ctypes.c_double(), ctypes.c_double()
+        self._call("abs_error", ctypes.c_int(level), ctypes.byref(mean), ctypes.byref(mx))
+        return mean.value, mx.value
 
     @staticmethod
     def plan_level(n, nranks, rank):

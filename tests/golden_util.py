@@ -99,3 +99,34 @@ def compare(got, g, hist_rtol):
             assert np.all(np.abs(val - want) <= hist_rtol * np.abs(want)), (key, val, want)
         else:
             assert_bits_equal(val, want, key)
+
+
+_GOLD = np.uint64(0x9E3779B97F4A7C15)
+
+
+def field_checksum(a):
+    """Position-keyed additive checksum of a dense field (any dimension, C order = the reference's x-fastest layout):
+
+        sum over points i of mix64(bits(a[i]) + (i + 1) * 0x9E3779B97F4A7C15)   (mod 2^64)
+
+    with bits() the raw IEEE bit pattern zero-extended to 64 bits, i the linear index of the reference layout
+    (x + y*n + z*n*n) and mix64 the splitmix64 finaliser.  Addition commutes, so slabs (and GPUs) can be summed in
+    any order; the key makes it sensitive to where a value sits.  The engine computes the same number on the device
+    (mg3d_field_checksum, csrc/mg3d_kernels.cu)."""
+    a = np.ascontiguousarray(a)
+    flat = a.reshape(-1)
+    bits_t = np.uint32 if a.dtype == np.float32 else np.uint64
+    total = np.uint64(0)
+    step = 1 << 24
+    with np.errstate(over="ignore"):
+        for s0 in range(0, flat.size, step):
+            b = flat[s0:s0 + step].view(bits_t).astype(np.uint64)
+            idx = np.arange(s0 + 1, s0 + 1 + b.size, dtype=np.uint64)
+            z = b + idx * _GOLD
+            z ^= z >> np.uint64(30)
+            z *= np.uint64(0xBF58476D1CE4E5B9)
+            z ^= z >> np.uint64(27)
+            z *= np.uint64(0x94D049BB133111EB)
+            z ^= z >> np.uint64(31)
+            total += z.sum(dtype=np.uint64)
+    return int(total)

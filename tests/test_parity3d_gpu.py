@@ -288,7 +288,7 @@ def test_fused_smoother_is_bit_identical(mg, n, nu, dtype, rng_range):
     outs = []
     for smoother in (mg.MG_SMOOTHER_COLOUR, mg.MG_SMOOTHER_FUSED):
         eng = mg.MultiGrid3D(n, rng_range, dtype=dtype)
-        eng.set_smoother(smoother, 2)
+        eng.set_smoother(smoother)
         eng.set_v(0, v0)
         eng.set_f(0, f0)
         eng.Relax(0, nu)
