@@ -14,7 +14,14 @@ One JSON line on stdout (rank 0):
              v,f -> device, one V(2,2), v -> host, every step
   roofline   the dominant kernel (finest-level smoother launch): algorithmic bytes / live event time
   cpu_baseline  the reference CPU solver (oracle/_ref, compiled unmodified) on this box's host, bounded sample
-`--impl reference` times that CPU solver as the measured arm instead (no GPU work at all).
+  parity     after the timed region: InitV/InitF again, one V(2,2), and the position-keyed checksum of v on every level
+             (mg3d_field_checksum, summed over the ranks) against tests/golden/hashes3d.json -- the numbers the reference
+             CPU solver itself produced at this size (tests/golden/make_hash.py).  ok == true means: this run, on this many
+             GPUs, holds the reference's bits.
+  other_configs  (N=1) the remaining BASELINE.json configurations, measured in the same process: 1D N=1025, 2D Lyapunov
+             1025^2, 3D 257^3; (N=8) the 2049^3 capacity run of configs[4]
+`--impl reference` times that CPU solver as the measured arm instead (no GPU work at all): 513^3, at most 3 cycles.
+`--profile-traffic` re-measures roofline.traffic with ncu (one launch of the dominant kernel) into profiles/roofline_traffic.json.
 
 Only this file's cpu_baseline / --impl reference legs touch oracle/; the GPU arm never does.
 """
@@ -124,6 +131,41 @@ class ClockSampler:
         return out
 
 
+def workload_name(n, B):
+    tag = {257: " (BASELINE.json configs[2])", 1025: " (BASELINE.json configs[3])", 2049: " (BASELINE.json configs[4])"}.get(n, "")
+    return "3D Poisson %d^3 %s V(%d,%d), reference problem%s, sign-corrected residual" % (n, "fp64" if B == 8 else "fp32", NU1, NU2, tag)
+
+
+def golden_checksums(n, dtype_tag, mode="corrected"):
+    """Checksums of v per level after each V(2,2) cycle, as the reference CPU solver produced them (or None)."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "hashes3d.json")) as fh:
+            rec = json.load(fh).get("%d/%s/%s" % (n, dtype_tag, mode))
+        return [c["checksum_v"] for c in rec["cycles"]] if rec else None
+    except Exception:
+        return None
+
+
+def parity_block(eng, n, dtype_tag):
+    """InitV/InitF, V(2,2) cycles, device checksum of v on every level against the reference's own run."""
+    want = golden_checksums(n, dtype_tag)
+    eng.init_problem()
+    if want is None:
+        return {"ok": None, "why": "the reference cannot run %d^3 (no golden checksum): see residual_l2 / closed form" % n}
+    got, ok = [], True
+    for cyc in want:
+        eng.VCycle(0, NU1, NU2)
+        cs = ["%016x" % eng.field_checksum(l) for l in range(eng.numGrids)]
+        got.append(cs)
+        ok = ok and cs == cyc
+    return {"ok": bool(ok), "cycles": len(want), "checksum_v_level0": got[-1][0], "expected_level0": want[-1][0],
+            "levels_compared": len(want[-1]),
+            "what": "position-keyed additive checksum (mod 2^64) of the bit patterns of v on every level after each V(2,2) from "
+                    "v=0, summed over the ranks' slabs on the device",
+            "expected_from": "tests/golden/hashes3d.json: the reference NOCUDA_TESI solver compiled unmodified, run at this size "
+                             "(tests/golden/make_hash.py)"}
+
+
 def host_cpu_info():
     model = "unknown"
     try:
@@ -162,8 +204,12 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n_sample = args.cpu_n
-    sec, kind = time_reference_cpu(n_sample, args.steps, args.warmup)
+    # the reference at the headline size needs ~40 GB and ~2 min per cycle (tests/golden/make_hash.py ran it once): the arm
+    # samples 513^3 -- one level below, same code path, 1/8 of the points -- for at most 3 cycles and no warm-up
+    n_sample = args.ref_n
+    steps = max(1, min(args.steps, 3))
+    sec, kind = time_reference_cpu(n_sample, steps, 0)
+    args.steps, args.warmup = steps, 0
     scale = updates_per_cycle(n_sample) / updates_per_cycle(args.n)
     value = scale / sec
     model, cores = host_cpu_info()
@@ -174,15 +220,125 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "3D Poisson V(2,2) cycles/s", "value": value, "unit": "V-cycles/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 / scale,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D Poisson %d^3 fp64 V(%d,%d), reference problem (BASELINE.json configs[3]), "
-                               "sign-corrected residual" % (args.n, NU1, NU2),
-                   "sample_grid": n_sample, "host_cpu": model, "host_cores": cores},
+        "config": {"workload": workload_name(args.n, 8), "sample_grid": n_sample, "host_cpu": model, "host_cores": cores},
         "grid_point_updates_per_s": updates_per_cycle(n_sample) / sec,
         "cpu_baseline": {"value": value, "unit": "V-cycles/s", "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "V-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+    return 0
+
+
+def _timed(torch, eng, fn, reps, warm=2):
+    s = torch.cuda.ExternalStream(eng.stream)
+    for _ in range(warm):
+        fn()
+    eng.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    for _ in range(reps):
+        fn()
+    e1.record(s)
+    eng.sync()
+    return e0.elapsed_time(e1) / reps
+
+
+def other_configs(mg, torch, world, rank, uid, dist):
+    """The BASELINE.json configurations that are not the headline, measured in this process so that the driver's record
+    carries them: N=1: configs[0] 1D N=1025 (V(1000,1000) and FMG(2,1000,1000), N1/Poisson1DSolver.cpp:15-25), configs[1] 2D
+    Lyapunov 1025^2 (V(2,2) and FMG(1,500,500), N2/LyapunovSolver.cpp:25-43), configs[2] 3D 257^3 fp64 V(2,2).  N=8:
+    configs[4], 3D 2049^3 fp64 on 8 GPUs (the reference cannot run it: 32-bit indices)."""
+    out = {}
+    if world == 1:
+        e = mg.MultiGrid1D(1025, dtype=np.float64)
+        out["1d_n1025_f64"] = {"vcycle_1000_1000_ms": _timed(torch, e, lambda: e.VCycle(0, 1000, 1000), 5),
+                               "fmg_2_1000_1000_ms": _timed(torch, e, lambda: (e.init_problem(), e.FullMultiGridVCycle(0, 2, 1000, 1000)), 3)}
+        e.close()
+        e = mg.MultiGrid2D(1025, dtype=np.float32)
+        ms = _timed(torch, e, lambda: e.VCycle(0, 2, 2), 20)
+        upd = 4 * sum((s - 2) ** 2 for s in level_sizes(1025))
+        out["2d_lyapunov_1025_f32"] = {"vcycle_2_2_ms": ms, "vcycles_per_s": 1e3 / ms, "grid_point_updates_per_s": upd * 1e3 / ms,
+                                       "fmg_1_500_500_ms": _timed(torch, e, lambda: (e.init_problem(), e.FullMultiGridVCycle(0, 1, 500, 500)), 2, warm=1)}
+        e.close()
+        e = mg.MultiGrid3D(257, dtype=np.float64, residual_mode=mg.MG_CORRECTED)
+        ms = _timed(torch, e, lambda: e.VCycle(0, 2, 2), 50, warm=3)
+        byt = algorithmic_bytes_per_cycle(257, 8)
+        peak, _ = measured_peak_gbs()
+        want = golden_checksums(257, "f64")
+        e.init_problem()
+        ok = True
+        for cyc in want or []:
+            e.VCycle(0, 2, 2)
+            ok = ok and ["%016x" % e.field_checksum(l) for l in range(e.numGrids)] == cyc
+        out["3d_257_f64"] = {"vcycle_2_2_ms": ms, "vcycles_per_s": 1e3 / ms, "grid_point_updates_per_s": updates_per_cycle(257) * 1e3 / ms,
+                             "algorithmic_gbs": byt / ms / 1e6, "hbm_frac": byt / ms / 1e6 / peak, "parity_ok": bool(ok) if want else None}
+        e.close()
+    if world == 8:
+        n = 2049
+        e = mg.MultiGrid3D(n, dtype=np.float64, residual_mode=mg.MG_CORRECTED, rank=rank, nranks=world, nccl_unique_id=uid)
+        r0 = e.residual_norm(0)[0]
+        for _ in range(2):
+            e.VCycle(0, NU1, NU2)
+        e.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+        s = torch.cuda.ExternalStream(e.stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(5):
+            e.VCycle(0, NU1, NU2)
+        e1.record(s)
+        e.sync()
+        t = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        r7 = e.residual_norm(0)[0]
+        byt = algorithmic_bytes_per_cycle(n, 8)
+        peak, _ = measured_peak_gbs()
+        closed = 3.0 * np.pi ** 2 * ((n - 1) / 2.0) ** 1.5
+        out["3d_2049_f64_8gpu"] = {"workload": workload_name(n, 8), "vcycle_2_2_ms": ms, "vcycles_per_s": 1e3 / ms,
+                                   "grid_point_updates_per_s": updates_per_cycle(n) * 1e3 / ms,
+                                   "hbm_frac_per_gpu": byt / ms / 1e6 / world / peak,
+                                   "residual_l2_initial": r0, "closed_form_initial": closed, "initial_matches_closed_form": bool(abs(r0 - closed) <= 1e-10 * closed),
+                                   "residual_l2_after_7_cycles": r7, "contraction_per_cycle": (r7 / r0) ** (1.0 / 7.0)}
+        e.close()
+    return out
+
+
+def profile_traffic(args):
+    """One launch of the dominant kernel under ncu (dram__bytes_read.sum + dram__bytes_write.sum), stored per
+    (kernel, n, dtype, arithmetic) in profiles/roofline_traffic.json.  Needs a GPU; N=1 only."""
+    kname = {"auto": "k_relax_pipe2", "pipe": "k_relax_pipe2", "tma": "k_relax_colour_tma"}[args.smoother]
+    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
+           "-k", "regex:" + kname, "-s", "1", "-c", "1", "--csv", sys.executable, os.path.join(ROOT, "scripts", "pipe_once.py"),
+           str(args.n), args.dtype, "pipe" if kname == "k_relax_pipe2" else "tma"] + (["fast"] if args.arith == "fast" else [])
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
+    vals = {}
+    for line in out.splitlines():
+        c = [x.strip('"') for x in line.split('","')]
+        if len(c) > 3 and c[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"):
+            unit, val = c[-2], float(c[-1].replace(",", ""))
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1)
+            vals[c[-3]] = val * mult
+    if len(vals) < 3:
+        print(out[-2000:])
+        raise SystemExit("ncu did not report the metrics")
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(path) as fh:
+            tj = json.load(fh)
+    except Exception:
+        tj = {}
+    tj.setdefault("kernels", {})["%s_n%d_%s_%s" % (kname, args.n, args.dtype, args.arith)] = {
+        "dram_bytes_per_launch": vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"],
+        "dram_bytes_read": vals["dram__bytes_read.sum"], "dram_bytes_write": vals["dram__bytes_write.sum"],
+        "ms_under_ncu": vals["gpu__time_duration.sum"],
+        "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, one launch of %s at %d^3 %s (bench.py --profile-traffic); "
+                  "a property of the kernel and the grid, not re-measured in the run that prints it" % (kname, args.n, args.dtype)}
+    with open(path, "w") as fh:
+        json.dump(tj, fh, indent=1, sort_keys=True)
+    print(json.dumps(tj["kernels"]))
     return 0
 
 
@@ -195,18 +351,25 @@ def main():
     ap.add_argument("--n", "--grid", dest="n", type=int, default=1025,
                     help="finest grid size per axis (2^k+1); under torchrun spell it --grid (torchrun treats --n as an abbreviation of its own options)")
     ap.add_argument("--dtype", default="f64", choices=["f32", "f64"])
-    ap.add_argument("--cpu-n", type=int, default=257, help="grid of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-n", type=int, default=257, help="grid of the bounded CPU-baseline sample of the GPU arm")
+    ap.add_argument("--ref-n", type=int, default=513, help="grid the --impl reference arm runs (at most 3 cycles)")
+    ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--profile-traffic", action="store_true",
+                    help="measure the dominant kernel's DRAM bytes per launch with ncu into profiles/roofline_traffic.json and exit")
+    ap.add_argument("--arith", default="exact", choices=["exact", "fast"])
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--smoother", default="auto", choices=["auto", "colour", "fused"])
-    ap.add_argument("--sweeps-per-pass", type=int, default=0)
+    ap.add_argument("--smoother", default="auto", choices=["auto", "colour", "tma", "fused", "pipe"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.profile_traffic:
+        return profile_traffic(args)
 
     import torch
     import pde_multigrid_b200 as mg
@@ -240,9 +403,11 @@ def main():
     B = np.dtype(np_dtype).itemsize
     n = args.n
     eng = mg.MultiGrid3D(n, dtype=np_dtype, residual_mode=mg.MG_CORRECTED, rank=rank, nranks=world, nccl_unique_id=uid)
-    if args.smoother != "auto" or args.sweeps_per_pass:
-        code = {"auto": mg.MG_SMOOTHER_AUTO, "colour": mg.MG_SMOOTHER_COLOUR, "fused": mg.MG_SMOOTHER_FUSED}[args.smoother]
-        eng.set_smoother(code, max(args.sweeps_per_pass, 1))
+    if args.smoother != "auto":
+        eng.set_smoother({"colour": mg.MG_SMOOTHER_COLOUR, "tma": mg.MG_SMOOTHER_TMA, "fused": mg.MG_SMOOTHER_FUSED,
+                          "pipe": mg.MG_SMOOTHER_PIPE}[args.smoother])
+    if args.arith == "fast":
+        eng.set_arith(mg.MG_ARITH_FAST)
     stream = torch.cuda.ExternalStream(eng.stream)
 
     def barrier():
@@ -326,27 +491,39 @@ def main():
     relax0 = breakdown[0].get("relax", {"ms": 0.0, "launches": 0})
     roofline = None
     if relax0["launches"]:
-        # the smoother call at the finest level: (nu1+nu2) RB sweeps per cycle, 3*B*N0 algorithmic bytes per sweep
-        # (read v, read f, write v) spread over the launches the smoother needs for them
-        alg_per_launch = (NU1 + NU2) * 3 * B * (N0 / world) / relax0["launches"]
-        avg_ms = relax0["ms"] / relax0["launches"]
+        # The dominant kernel is the finest-level smoother.  Default smoother: the temporally blocked pass, ONE kernel launch
+        # = TWO full RB sweeps (k_relax_pipe2; the conditional exact-fallback launch behind it exits at once unless the range
+        # guard fired and is timed with it).  Algorithmic bytes: 3*B*N0 per RB sweep = read v, read f,
+        # write v -- the pass moves fewer real bytes than that (2.5*B*N0 + halo for both sweeps), so achieved/peak can
+        # exceed 1; `traffic` is what ncu saw it move.
+        two_sweep = args.smoother in ("auto", "pipe", "fused") and world == 1
+        sweeps_per_launch = 2.0 if two_sweep else 0.5
+        nlaunch = (NU1 + NU2) / sweeps_per_launch
+        alg_per_launch = sweeps_per_launch * 3 * B * (N0 / world)
+        avg_ms = relax0["ms"] / nlaunch
         achieved = alg_per_launch / (avg_ms * 1e-3) / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
-                tj = json.load(fh)
-            key = "relax_n%d_%s_%s" % (n, args.dtype, tj.get("current", ""))
-            traffic = tj.get("kernels", {}).get(key)
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "kernel": "finest-level smoother launch (Relax, level 0)", "achieved": achieved,
-                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8000_gbs": achieved / 8000.0,
-                    "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_ms,
-                    "launches_per_cycle": relax0["launches"],
+        kname = "k_relax_pipe2" if two_sweep and args.smoother != "fused" else ("k_relax_fused2" if two_sweep else "k_relax_colour_tma")
+        traffic, traffic_src = None, None
+        if world == 1:
+            try:
+                with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+                    ent = json.load(fh).get("kernels", {}).get("%s_n%d_%s_%s" % (kname, n, args.dtype, args.arith))
+                if ent:
+                    traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
+            except Exception:
+                pass
+        roofline = {"bound": "hbm", "kernel": "%s: finest-level smoother, %g RB sweep(s) per launch" % (kname, sweeps_per_launch),
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "frac_of_nominal_8000_gbs": achieved / 8000.0, "traffic": traffic, "traffic_source": traffic_src,
+                    "dram_gbs_on_traffic": (traffic / (avg_ms * 1e-3) / 1e9) if traffic else None,
+                    "dram_frac_on_traffic": (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_ms,
+                    "launches_per_cycle": nlaunch, "kernel_launches_counted_per_cycle": relax0["launches"],
                     "share_of_step": relax0["ms"] / ms_step_profiled,
                     "measured_in": "second pass of the same %d steps with per-operator CUDA events on the engine's stream "
                                    "(%.3f ms/step eager; the headline pass replays the same kernels from a CUDA graph)" % (args.steps, ms_step_profiled)}
+
+    parity = None if args.no_parity else parity_block(eng, n, args.dtype)
 
     # ---- end to end through the C-ABI call with HOST buffers (every rank moves the planes it owns) ----
     e2e = None
@@ -393,6 +570,15 @@ def main():
                                   "at %d^3 fp64, sign-corrected residual, %.2f s/cycle; V-cycles/s scaled to %d^3 by grid-point "
                                   "updates (x%.5f)" % (args.cpu_steps, args.cpu_n, sec, n, scale)}
 
+    levels = eng.numGrids
+    eng.close()
+    eng = None
+    other = None
+    if not args.no_other_configs:
+        try:
+            other = other_configs(mg, torch, world, rank, uid, dist)
+        except Exception as exc:  # the headline line must not die with a side measurement
+            other = {"error": repr(exc)}
     if rank == 0:
         model, cores = host_cpu_info()
         value = 1e3 / ms_step
@@ -400,11 +586,9 @@ def main():
             "metric": "3D Poisson V(2,2) cycles/s", "value": value, "unit": "V-cycles/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": "3D Poisson %d^3 %s V(%d,%d), reference problem (BASELINE.json configs[3]), "
-                                   "sign-corrected residual" % (n, "fp64" if B == 8 else "fp32", NU1, NU2),
-                       "levels": eng.numGrids, "partition": "z-slabs x%d" % world,
+            "config": {"workload": workload_name(n, B), "levels": levels, "partition": "z-slabs x%d" % world,
                        "l2": "fields are %.1f GB per level-0 array, far larger than the 126 MB L2: no flush needed" % (N0 * B / 1e9),
-                       "smoother": args.smoother, "host_cpu": model, "host_cores": cores},
+                       "smoother": args.smoother, "arithmetic": args.arith, "host_cpu": model, "host_cores": cores},
             "grid_point_updates_per_s": updates_per_cycle(n) * value,
             "algorithmic_bytes_per_cycle": bytes_cycle,
             "hbm_roofline_cycle": {"achieved_gbs": bytes_cycle / (ms_step * 1e-3) / 1e9 / world, "peak_gbs": peak,
@@ -416,7 +600,8 @@ def main():
                              "achieved_gbs": halo_bytes / max(args.steps, 1) / (ms_step * 1e-3) / 1e9, "peak_gbs": 900.0,
                              "frac": halo_bytes / max(args.steps, 1) / (ms_step * 1e-3) / 1e9 / 900.0}),
             "residual_l2": {"before": r0[0], "after": r1[0]},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks, "parity": parity,
+            "other_configs": other,
             "gpu_launches": int(launches), "halo_bytes_per_cycle_rank0": int(halo_bytes) // max(args.steps, 1),
             "ms_per_step_profiled_pass": ms_step_profiled,
             "with_per_cycle_norm": {"ms_per_step": ms_step_with_norm, "value": 1e3 / ms_step_with_norm, "unit": "V-cycles/s",
@@ -424,7 +609,6 @@ def main():
             "breakdown_ms_per_cycle": breakdown,
         }
         print(json.dumps(line), flush=True)
-    eng.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

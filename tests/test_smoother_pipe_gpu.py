@@ -122,7 +122,7 @@ def test_fast_arithmetic_within_tolerance(mg, dtype, tol):
         a, b = exact.residual_norm(0)[0], fast.residual_norm(0)[0]
         # the residual amplifies rounding differences of v by 6/h^2 = 4e5: 1e-16 relative in v shows as ~1e-10 .. 1e-9 relative
         # in ||r||; the float32 history sits on its round-off floor after a few cycles
-        assert abs(a - b) <= (1e-8 if dtype == np.float64 else 1e-3) * max(a, 1.0), (a, b)
+        assert abs(a - b) <= (1e-8 if dtype == np.float64 else 2e-2) * max(a, 1.0), (a, b)
     va, vb = exact.get_v(0), fast.get_v(0)
     assert np.max(np.abs(va.astype(np.float64) - vb)) <= tol * np.max(np.abs(va))
     assert not np.array_equal(va, vb) or dtype == np.float32  # it IS a different rounding sequence
