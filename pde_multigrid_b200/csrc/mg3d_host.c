@@ -10,8 +10,9 @@
  *
  * Multi-GPU (the reference has none; thesis p.75 names it as future work): one process per GPU, the
  * grid is cut into z-slabs.  Rank g of P owns the global planes [g*m, (g+1)*m), m = (n-1)/P, the last
- * rank also the Dirichlet plane n-1.  A slab stores 2 ghost planes below (the fused residual+restrict
- * needs v two planes under its first coarse plane) and 1 above.  A level is slab-distributed while
+ * rank also the Dirichlet plane n-1.  A slab stores 4 ghost planes below and above (two RB sweeps per pass of the
+ * temporally blocked smoother reach four planes; the fused residual+restrict needs v two planes under its first
+ * coarse plane).  A level is slab-distributed while
  * m >= 8 and n >= 257; coarser levels are agglomerated: every rank holds them whole (one all-gather of the
  * restricted right-hand side on the way down, nothing on the way up) and smooths them redundantly.
  * RB Gauss-Seidel only couples opposite colours, so exchanging the just-updated colour's boundary
@@ -26,8 +27,10 @@
 #include "mg_host_common.h"
 #include "mg_profile.h"
 
-#define MG_GHOST_LO 2
-#define MG_GHOST_HI 1
+/* ghost planes a slab stores below / above its own planes: the temporally blocked smoother consumes four planes of
+   colour 1 (and of f) on each side per pass; the fused residual+restrict reads v two planes below its first coarse plane */
+#define MG_GHOST_LO 4
+#define MG_GHOST_HI 4
 /* bytes of addressable slack in front of and behind the fields of the arena: the pipelined smoother (mg3d_smooth_pipe.cu)
    issues unclamped, masked loads for halo sites up to 4 rows outside a field */
 #define MG_ARENA_SLACK ((size_t)1 << 20)
@@ -53,6 +56,10 @@ typedef struct {
     unsigned char tmap_pp[2][128] __attribute__((aligned(64)));    /* pipelined smoother: colour-1 array of v, [buffer] */
     unsigned char tmap_pf[2][128] __attribute__((aligned(64)));    /* pipelined smoother: f (L2 prefetch), [colour] */
     int iso;        /* hx2 == hy2 == hz2 */
+    /* distributed levels: 1 = the ghost planes of v (both colours, 2 below / 1 above) hold the neighbours' current values.
+       Every operator leaves it 1 except the temporally blocked smoother, whose pass only writes the planes a rank owns;
+       whoever reads ghost planes of v calls ensure_v_ghosts() first. */
+    int vg_valid;
 } mg_level3d;
 
 /* direct NVLink halo path (mg_halo_p2p.cu): the neighbours' arenas and flag words mapped with CUDA IPC */
@@ -61,7 +68,7 @@ typedef struct {
     char* peer_arena[2];          /* [0] rank-1, [1] rank+1 */
     unsigned int* flags;          /* local words, one per 128-B line: [0] raised by rank-1, [32] by rank+1, [64] push counter, [96] wait error */
     unsigned int* peer_flags[2];
-    size_t* nb_off[2];            /* neighbour's byte offset of field fi of level l inside its arena: [2*l + fi] */
+    size_t* nb_off[2];            /* neighbour's byte offset of field fi (0: v buffer 0, 1: f, 2: v buffer 1) of level l inside its arena: [3*l + fi] */
     mg_geom3d* nb_geom[2];        /* neighbour's slab geometry per level */
     int* nb_own[2];               /* neighbour's own_lo, own_hi per level: [2*l], [2*l+1] */
 } mg_p2p;
@@ -73,6 +80,7 @@ typedef struct {
 typedef struct {
     int used, level, v1, v2, smoother, arith, calls;
     unsigned cur_start, cur_end; /* bit l = which v buffer level l works on when the graph starts / has finished */
+    unsigned vg_start, vg_end;   /* bit l = mg_level3d.vg_valid */
     cudaGraphExec_t exec;
     long long launches, halo_bytes;
 } mg_graph_slot;
@@ -192,8 +200,8 @@ static size_t field_bytes(const mg_level3d* L, int dtype)
 
 static int level_uses_tma(int n) { return (n - 1) / 2 >= MGK3D_TMA_IT && !getenv("MG_B200_NO_TMA"); }
 
-/* fields a level keeps in the arena: v, f and, where the fused smoother can run (large, not distributed), a second v */
-static int level_fields_for(int n, int dist) { return (level_uses_tma(n) && !dist) ? 3 : 2; }
+/* fields a level keeps in the arena: v, f and, where the temporally blocked smoothers can run (the large levels), a second v */
+static int level_fields_for(int n, int dist) { (void)dist; return level_uses_tma(n) ? 3 : 2; }
 static int level_fields(const mg_level3d* L) { return level_fields_for(L->g.n, L->dist); }
 
 static int check_level(const mg3d_t* mg, int level)
@@ -217,52 +225,56 @@ static char* plane_ptr(const mg3d_t* mg, const mg_level3d* L, void* field, int c
  *   down: my bottom owned plane (if `down` != 0) -> the upper ghost of rank-1
  * colour_mask: bit 0 = colour-0 array, bit 1 = colour-1 array.
  * ---------------------------------------------------------------------------------------------- */
-static int exchange_p2p(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int down, cudaStream_t xs)
+static int exchange_p2p(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int depth_down, cudaStream_t xs)
 {
     mg_level3d* L = &mg->lv[level];
     mg_p2p* q = &mg->p2p;
     const size_t es = mg_esize(mg->dtype), pb = (size_t)L->g.plane * es; /* bytes per colour plane */
-    const int r = mg->rank, P = mg->nranks, fi = field == L->v ? 0 : 1;
+    const int r = mg->rank, P = mg->nranks;
+    /* the neighbours run the same program: their current v buffer is the one with my index */
+    const int fi = field == L->f ? 1 : (field == L->vbuf[1] && L->vbuf[1] ? 2 : 0);
     const void* src[4] = {0, 0, 0, 0};
     void* dst[4] = {0, 0, 0, 0};
     unsigned long long bytes[4] = {0, 0, 0, 0};
     unsigned int* raise[2] = {0, 0};
     int nseg = 0;
-    const int send_up = r + 1 < P && depth_up > 0, send_down = r > 0 && down;
+    const int send_up = r + 1 < P && depth_up > 0, send_down = r > 0 && depth_down > 0;
     for (int col = 0; col < 2; col++) {
         if (!(colour_mask & (1 << col))) continue;
         if (send_up) { /* my top planes -> the lower ghosts of rank+1 */
             const mg_geom3d* ng = &q->nb_geom[1][level];
             src[nseg] = plane_ptr(mg, L, field, col, L->own_hi - depth_up);
-            dst[nseg] = q->peer_arena[1] + q->nb_off[1][2 * level + fi] +
+            dst[nseg] = q->peer_arena[1] + q->nb_off[1][3 * level + fi] +
                         ((size_t)col * (size_t)ng->cstride + (size_t)(q->nb_own[1][2 * level] - depth_up) * (size_t)ng->plane) * es;
             bytes[nseg++] = pb * depth_up;
             mg->halo_bytes += (long long)(pb * depth_up);
         }
-        if (send_down) { /* my bottom plane -> the upper ghost of rank-1 */
+        if (send_down) { /* my bottom planes -> the upper ghosts of rank-1 */
             const mg_geom3d* ng = &q->nb_geom[0][level];
             src[nseg] = plane_ptr(mg, L, field, col, L->own_lo);
-            dst[nseg] = q->peer_arena[0] + q->nb_off[0][2 * level + fi] +
+            dst[nseg] = q->peer_arena[0] + q->nb_off[0][3 * level + fi] +
                         ((size_t)col * (size_t)ng->cstride + (size_t)q->nb_own[0][2 * level + 1] * (size_t)ng->plane) * es;
-            bytes[nseg++] = pb;
-            mg->halo_bytes += (long long)pb;
+            bytes[nseg++] = pb * depth_down;
+            mg->halo_bytes += (long long)(pb * depth_down);
         }
     }
     if (send_up) raise[1] = q->peer_flags[1] + 0;    /* its "from below" word */
     if (send_down) raise[0] = q->peer_flags[0] + 32; /* its "from above" word */
-    const int recv_below = r > 0 && depth_up > 0, recv_above = r + 1 < P && down;
+    const int recv_below = r > 0 && depth_up > 0, recv_above = r + 1 < P && depth_down > 0;
     if (xs == mg->stream) PROF_BEGIN(mg, level, MG_OP_OTHER);
     MG_LAUNCH(mg->launches, mgk_halo_exchange(xs, src, dst, bytes, raise, recv_below, recv_above, q->flags));
     if (xs == mg->stream) PROF_END(mg);
     return MG_OK;
 }
 
-static int exchange_on(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int down, cudaStream_t xs)
+/* depth_up / depth_down planes (<= MG_GHOST_LO / MG_GHOST_HI; 0 = nothing travels in that direction) */
+static int exchange_on(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int depth_down, cudaStream_t xs)
 {
     mg_level3d* L = &mg->lv[level];
     if (!L->dist) return MG_OK;
-    /* the direct NVLink path addresses the neighbour's v and f inside its arena; anything else (the Jacobi scratch) goes through NCCL */
-    if (mg->p2p.enabled && (field == L->v || field == L->f)) return exchange_p2p(mg, level, field, colour_mask, depth_up, down, xs);
+    /* the direct NVLink path addresses the neighbour's v buffers and f inside its arena; anything else (the Jacobi scratch) goes through NCCL */
+    if (mg->p2p.enabled && (field == L->vbuf[0] || field == L->vbuf[1] || field == L->f))
+        return exchange_p2p(mg, level, field, colour_mask, depth_up, depth_down, xs);
     const size_t pe = (size_t)L->g.plane; /* elements per colour plane */
     const int r = mg->rank, P = mg->nranks;
     int st;
@@ -275,12 +287,12 @@ static int exchange_on(mg3d_t* mg, int level, void* field, int colour_mask, int 
                 st = mg_comm_send(mg->comm, plane_ptr(mg, L, field, col, L->own_hi - depth_up), pe * depth_up, mg->dtype, r + 1, xs);
                 mg->halo_bytes += (long long)(pe * depth_up * mg_esize(mg->dtype));
             }
-            if (!st && down) st = mg_comm_recv(mg->comm, plane_ptr(mg, L, field, col, L->own_hi), pe, mg->dtype, r + 1, xs);
+            if (!st && depth_down > 0) st = mg_comm_recv(mg->comm, plane_ptr(mg, L, field, col, L->own_hi), pe * depth_down, mg->dtype, r + 1, xs);
         }
         if (!st && r > 0) {
-            if (down) {
-                st = mg_comm_send(mg->comm, plane_ptr(mg, L, field, col, L->own_lo), pe, mg->dtype, r - 1, xs);
-                mg->halo_bytes += (long long)(pe * mg_esize(mg->dtype));
+            if (depth_down > 0) {
+                st = mg_comm_send(mg->comm, plane_ptr(mg, L, field, col, L->own_lo), pe * depth_down, mg->dtype, r - 1, xs);
+                mg->halo_bytes += (long long)(pe * depth_down * mg_esize(mg->dtype));
             }
             if (!st && depth_up > 0)
                 st = mg_comm_recv(mg->comm, plane_ptr(mg, L, field, col, L->own_lo - depth_up), pe * depth_up, mg->dtype, r - 1, xs);
@@ -292,9 +304,40 @@ static int exchange_on(mg3d_t* mg, int level, void* field, int colour_mask, int 
     return st ? st : st2;
 }
 
-static int exchange(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int down)
+static int exchange(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int depth_down)
 {
-    return exchange_on(mg, level, field, colour_mask, depth_up, down, mg->stream);
+    return exchange_on(mg, level, field, colour_mask, depth_up, depth_down, mg->stream);
+}
+
+/* The temporally blocked smoother writes the planes a rank owns into the OTHER v buffer and reads, of that buffer's ghost
+   planes, nothing -- but a later pass out of it reads the Dirichlet points of colour 0 on its ghost planes (the exchange in
+   front of a pass only moves colour 1).  Dirichlet values never change, so it is enough that whoever defines v on every stored
+   plane (InitV, set_field, setToValue) gives the ghost planes of the other buffer the same values. */
+static int mirror_v_ghosts(mg3d_t* mg, int level)
+{
+    mg_level3d* L = &mg->lv[level];
+    if (!L->dist || !L->vbuf[1]) return MG_OK;
+    void* other = L->vbuf[L->cur ^ 1];
+    const size_t pb = (size_t)L->g.plane * mg_esize(mg->dtype);
+    for (int col = 0; col < 2; col++) {
+        if (L->own_lo > 0)
+            MG_CUDA(cudaMemcpyAsync(plane_ptr(mg, L, other, col, 0), plane_ptr(mg, L, L->v, col, 0), pb * (size_t)L->own_lo, cudaMemcpyDeviceToDevice, mg->stream));
+        if (L->g.nzl > L->own_hi)
+            MG_CUDA(cudaMemcpyAsync(plane_ptr(mg, L, other, col, L->own_hi), plane_ptr(mg, L, L->v, col, L->own_hi),
+                                    pb * (size_t)(L->g.nzl - L->own_hi), cudaMemcpyDeviceToDevice, mg->stream));
+    }
+    return MG_OK;
+}
+
+/* ghost planes of v as the colour-per-launch kernels, the fused residual+restrict and the prolongation expect them
+   (2 below, 1 above, both colours): refreshed here if the temporally blocked smoother left them behind */
+static int ensure_v_ghosts(mg3d_t* mg, int level)
+{
+    mg_level3d* L = &mg->lv[level];
+    if (!L->dist || L->vg_valid) return MG_OK;
+    int st = exchange(mg, level, L->v, 3, 2, 1);
+    if (!st) L->vg_valid = 1;
+    return st;
 }
 
 /* first agglomerated level below a distributed one: every rank computed the coarse planes under its own
@@ -342,7 +385,7 @@ static int p2p_setup(mg3d_t* mg, size_t arena_bytes)
     for (int k = 0; k < 2; k++) {
         const int nr = k == 0 ? r - 1 : r + 1;
         if (nr < 0 || nr >= P) continue;
-        q->nb_off[k] = (size_t*)calloc(2 * (size_t)mg->nlevels, sizeof(size_t));
+        q->nb_off[k] = (size_t*)calloc(3 * (size_t)mg->nlevels, sizeof(size_t));
         q->nb_geom[k] = (mg_geom3d*)calloc((size_t)mg->nlevels, sizeof(mg_geom3d));
         q->nb_own[k] = (int*)calloc(2 * (size_t)mg->nlevels, sizeof(int));
         if (!q->nb_off[k] || !q->nb_geom[k] || !q->nb_own[k]) return mg_fail(MG_ERR_NOMEM, "host allocation failed");
@@ -354,8 +397,9 @@ static int p2p_setup(mg3d_t* mg, size_t arena_bytes)
             q->nb_own[k][2 * l] = plan[3];
             q->nb_own[k][2 * l + 1] = plan[4];
             const size_t fb = mg_align256(2 * (size_t)q->nb_geom[k][l].cstride * mg_esize(mg->dtype));
-            q->nb_off[k][2 * l] = off; off += fb;
-            q->nb_off[k][2 * l + 1] = off; off += fb;
+            q->nb_off[k][3 * l] = off; off += fb;
+            q->nb_off[k][3 * l + 1] = off; off += fb;
+            q->nb_off[k][3 * l + 2] = off;
             if (level_fields_for(mg->lv[l].g.n, plan[0]) == 3) off += fb;
         }
     }
@@ -486,6 +530,7 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
         set_geom(&L->g, nl, dtype, plan[1], plan[2]);
         L->own_lo = plan[3];
         L->own_hi = plan[4];
+        L->vg_valid = 1;
         level_coefs(dtype, nl, range, L->h, &L->c);
         total += (size_t)level_fields(L) * field_bytes(L, dtype);
         nl = (nl - 1) / 2 + 1; /* N3/MultiGrid3D.cpp:40-42 */
@@ -718,8 +763,12 @@ int mg3d_set_field(mg3d_t* mg, int level, int field, const void* host_dense)
     if (!host_dense || (field != MG_FIELD_V && field != MG_FIELD_F)) return mg_fail(MG_ERR_ARG, "bad field/pointer");
     mg_level3d* L = &mg->lv[level];
     st = copy_in(mg, field_ptr(L, field), &L->g, host_dense, L->own_lo, L->own_hi);
-    if (!st) st = exchange(mg, level, field_ptr(L, field), 3, MG_GHOST_LO, 1);
+    if (!st) st = exchange(mg, level, field_ptr(L, field), 3, MG_GHOST_LO, MG_GHOST_HI);
     if (st) return st;
+    if (field == MG_FIELD_V) {
+        L->vg_valid = 1;
+        if ((st = mirror_v_ghosts(mg, level))) return st;
+    }
     MG_CUDA(cudaStreamSynchronize(mg->stream)); /* host buffer may be reused by the caller */
     return MG_OK;
 }
@@ -782,9 +831,11 @@ int mg3d_init_problem(mg3d_t* mg)
        exchange per distributed level is the handshake that orders the two (and it is cheap). */
     for (int l = 0; l < mg->nlevels; l++) {
         mg_level3d* L = &mg->lv[l];
-        int st = exchange(mg, l, L->v, 3, MG_GHOST_LO, 1);
-        if (!st) st = exchange(mg, l, L->f, 3, MG_GHOST_LO, 1);
+        int st = exchange(mg, l, L->v, 3, MG_GHOST_LO, MG_GHOST_HI);
+        if (!st) st = exchange(mg, l, L->f, 3, MG_GHOST_LO, MG_GHOST_HI);
+        if (!st) st = mirror_v_ghosts(mg, l);
         if (st) return st;
+        L->vg_valid = 1;
     }
     return MG_OK;
 }
@@ -811,12 +862,19 @@ static int relax_launch(mg3d_t* mg, mg_level3d* L, int colour, int lo, int hi, i
 
 /* 1 when relax_level(level, n > 0) takes the overlapped path: the boundary planes of the slab and their halo exchange
    run on the side stream while the interior planes are swept; every half-sweep ends with a join */
+static int level_takes_pipe(const mg3d_t* mg, const mg_level3d* L)
+{
+    return (mg->smoother == MG_SMOOTHER_PIPE || (mg->smoother == MG_SMOOTHER_AUTO && !mg->no_pipe)) && L->has_tma && L->vbuf[1] &&
+           L->c.fast_den && L->iso && (!L->dist || L->own_hi - L->own_lo >= 8);
+}
+
 static int relax_overlaps(const mg3d_t* mg, int level)
 {
     const mg_level3d* L = &mg->lv[level];
     int lo, hi;
     interior_range(L, &lo, &hi);
-    return L->dist && mg->overlap && !mg->prof.enabled && hi - lo >= 4 && mg->smoother != MG_SMOOTHER_JACOBI;
+    /* (a level the temporally blocked smoother handles exchanges once per pass, in front of it, on the main stream) */
+    return L->dist && mg->overlap && !mg->prof.enabled && hi - lo >= 4 && mg->smoother != MG_SMOOTHER_JACOBI && !level_takes_pipe(mg, L);
 }
 
 /* A halo exchange whose ghost planes are first read by the boundary-plane kernel of the smoothing call that follows
@@ -843,6 +901,7 @@ static int relax_jacobi_level(mg3d_t* mg, int level, int ncycles)
         MG_CUDA(cudaMalloc(&L->jscratch, cbytes));
         MG_CUDA(cudaMemsetAsync(L->jscratch, 0, cbytes, mg->stream));
     }
+    if ((st = ensure_v_ghosts(mg, level))) return st;
     char *red = (char*)L->v, *black = red + cbytes, *cur = red;
     const char *f_red = (const char*)L->f, *f_black = f_red + cbytes;
     for (int k = 0; k < ncycles; k++) {
@@ -881,30 +940,34 @@ static int relax_level(mg3d_t* mg, int level, int ncycles)
     /* register-tiled temporally blocked smoother (the default where it applies): two full sweeps per pass, out of place.
        Bit-exact mode: the pass range-checks everything it touches; the conditional literal-arithmetic pass behind it only
        runs (and then recomputes the same output buffer from the untouched input) if that check failed. */
-    if ((mg->smoother == MG_SMOOTHER_PIPE || (mg->smoother == MG_SMOOTHER_AUTO && !mg->no_pipe)) && L->has_tma && L->vbuf[1] && !L->dist &&
-        L->c.fast_den && L->iso) {
+    if (level_takes_pipe(mg, L)) {
         while (ncycles >= 2) {
             const void* maps3[3] = {L->tmap_pp[L->cur], L->tmap_pf[0], L->tmap_pf[1]};
             const void* maps4[4] = {L->tmap_fu[L->cur][0], L->tmap_fu[L->cur][1], L->tmap_ff[0], L->tmap_ff[1]};
+            /* slab: four planes of colour 1 from each neighbour -- all the pass reads of v beyond the planes it owns (one
+               exchange per two sweeps instead of four; the halo planes are swept redundantly, bit-identical on both sides) */
+            if (L->dist && (st = exchange(mg, level, L->v, 2, MG_GHOST_LO, MG_GHOST_HI))) return st;
             PROF_BEGIN(mg, level, MG_OP_RELAX);
             MG_LAUNCH(mg->launches, mgk3d_relax_pipe2(mg->stream, mg->dtype, maps3, L->vbuf[L->cur], L->f, L->vbuf[L->cur ^ 1], L->g, L->c,
-                                                      mg->arith == MG_ARITH_FAST, mg->d_flag));
-            if (mg->arith != MG_ARITH_FAST)
-                MG_LAUNCH(mg->launches, mgk3d_relax_fused2(mg->stream, mg->dtype, maps4, L->vbuf[L->cur ^ 1], L->g, L->c, mg->d_flag));
+                                                      L->own_lo, L->own_hi, mg->arith == MG_ARITH_FAST, mg->d_flag));
+            if (mg->arith != MG_ARITH_FAST) /* conditional on the range guard; reads the same input planes, no exchange of its own */
+                MG_LAUNCH(mg->launches, mgk3d_relax_fused2(mg->stream, mg->dtype, maps4, L->vbuf[L->cur ^ 1], L->g, L->c, L->own_lo, L->own_hi, mg->d_flag));
             PROF_END(mg);
             L->cur ^= 1;
             L->v = L->vbuf[L->cur];
+            L->vg_valid = 0; /* only the owned planes of the new buffer were written */
             ncycles -= 2;
         }
         if (ncycles <= 0) return MG_OK;
     }
+    if ((st = ensure_v_ghosts(mg, level))) return st;
     /* the shared-memory version of the same idea (literal arithmetic; slower than four colour launches, kept as the
        exact fallback above and selectable for tests) */
     if (mg->smoother == MG_SMOOTHER_FUSED && L->has_tma && L->vbuf[1] && !L->dist) {
         while (ncycles >= 2) {
             const void* maps4[4] = {L->tmap_fu[L->cur][0], L->tmap_fu[L->cur][1], L->tmap_ff[0], L->tmap_ff[1]};
             PROF_BEGIN(mg, level, MG_OP_RELAX);
-            MG_LAUNCH(mg->launches, mgk3d_relax_fused2(mg->stream, mg->dtype, maps4, L->vbuf[L->cur ^ 1], L->g, L->c, NULL));
+            MG_LAUNCH(mg->launches, mgk3d_relax_fused2(mg->stream, mg->dtype, maps4, L->vbuf[L->cur ^ 1], L->g, L->c, L->own_lo, L->own_hi, NULL));
             PROF_END(mg);
             L->cur ^= 1;
             L->v = L->vbuf[L->cur];
@@ -952,6 +1015,7 @@ int mg3d_residual(mg3d_t* mg, int level, void* host_out)
     if (st) return st;
     if (!host_out) return mg_fail(MG_ERR_ARG, "null output");
     mg_level3d* L = &mg->lv[level];
+    if ((st = ensure_v_ghosts(mg, level))) return st;
     void* r = NULL;
     MG_CUDA(cudaMalloc(&r, field_bytes(L, mg->dtype)));
     int k = mgk3d_residual(mg->stream, mg->dtype, L->v, L->f, r, L->g, L->c, mg->mode == MG_CORRECTED, L->own_lo, L->own_hi);
@@ -969,6 +1033,7 @@ int mg3d_residual_norm(mg3d_t* mg, int level, double* l2, double* linf)
     int st = check_level(mg, level);
     if (st) return st;
     mg_level3d* L = &mg->lv[level];
+    if ((st = ensure_v_ghosts(mg, level))) return st;
     double* out2 = mg->d_scratch + 2 * MGK_NORM_MAX_PARTS;
     int k = -2;
     if (L->has_tma && mg->smoother != MG_SMOOTHER_COLOUR && level + 1 < mg->nlevels) {
@@ -1050,8 +1115,8 @@ int mg3d_abs_error(mg3d_t* mg, int level, double* mean_abs, double* max_abs)
 static int after_restrict(mg3d_t* mg, int fine_level, void* coarse_field, int defer)
 {
     const mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
-    if (C->dist && defer) return exchange_deferred(mg, fine_level + 1, coarse_field, 3, MG_GHOST_LO, 1);
-    if (C->dist) return exchange(mg, fine_level + 1, coarse_field, 3, MG_GHOST_LO, 1);
+    if (C->dist && defer) return exchange_deferred(mg, fine_level + 1, coarse_field, 3, MG_GHOST_LO, MG_GHOST_HI);
+    if (C->dist) return exchange(mg, fine_level + 1, coarse_field, 3, MG_GHOST_LO, MG_GHOST_HI);
     if (F->dist) return gather_level(mg, fine_level + 1, coarse_field, 1);
     return MG_OK;
 }
@@ -1065,10 +1130,13 @@ int mg3d_restrict(mg3d_t* mg, int fine_level, int field)
     mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
     int lo, hi;
     coarse_share(mg, fine_level, &lo, &hi);
+    if (field == MG_FIELD_V && (st = ensure_v_ghosts(mg, fine_level))) return st;
     PROF_BEGIN(mg, fine_level, MG_OP_OTHER);
     MG_LAUNCH(mg->launches, mgk3d_restrict(mg->stream, mg->dtype, field_ptr(F, field), F->g, field_ptr(C, field), C->g, lo, hi));
     PROF_END(mg);
-    return after_restrict(mg, fine_level, field_ptr(C, field), 0);
+    st = after_restrict(mg, fine_level, field_ptr(C, field), 0);
+    if (!st && field == MG_FIELD_V) C->vg_valid = 1;
+    return st;
 }
 
 /* defer_f_halo: the coarse f ghosts are not read before the coarse level's residual (the smoother reads f at its own
@@ -1079,7 +1147,10 @@ static int residual_restrict_level(mg3d_t* mg, int fine_level, int defer_f_halo)
     int lo, hi, st;
     coarse_share(mg, fine_level, &lo, &hi);
     /* the fused kernel reads v two planes below the slab: only plane a-2 is stale after the smoother's exchanges */
-    if (F->dist && (st = exchange(mg, fine_level, F->v, 3, MG_GHOST_LO, 0))) return st;
+    if (F->dist) {
+        if ((st = exchange(mg, fine_level, F->v, 3, 2, F->vg_valid ? 0 : 1))) return st;
+        F->vg_valid = 1;
+    }
     PROF_BEGIN(mg, fine_level, MG_OP_RESIDUAL_RESTRICT);
     if (F->has_tma && mg->smoother != MG_SMOOTHER_COLOUR)
         MG_LAUNCH(mg->launches, mgk3d_residual_restrict_tma(mg->stream, mg->dtype, F->tmap_rr[F->cur][0], F->tmap_rr[F->cur][1], F->f, F->g, F->c,
@@ -1087,8 +1158,12 @@ static int residual_restrict_level(mg3d_t* mg, int fine_level, int defer_f_halo)
     else
         MG_LAUNCH(mg->launches, mgk3d_residual_restrict(mg->stream, mg->dtype, F->v, F->f, F->g, F->c, mg->mode == MG_CORRECTED,
                                                         C->f, C->v, C->g, lo, hi));
-    if (F->dist) /* coarse v = 0 everywhere this rank stores it (ghost planes, or the whole agglomerated level) */
+    if (F->dist) { /* coarse v = 0 everywhere this rank stores it (ghost planes, or the whole agglomerated level) */
         MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, C->v, C->g, 0.0, 1, 0, C->g.nzl));
+        if (C->dist && C->vbuf[1]) /* ... and on the ghost planes of its other buffer: see mirror_v_ghosts */
+            MG_LAUNCH(mg->launches, mgk3d_set_ghosts(mg->stream, mg->dtype, C->vbuf[C->cur ^ 1], C->g, 0.0, C->own_lo, C->own_hi));
+    }
+    C->vg_valid = 1;
     PROF_END(mg);
     return after_restrict(mg, fine_level, C->f, defer_f_halo);
 }
@@ -1108,12 +1183,22 @@ int mg3d_residual_restrict(mg3d_t* mg, int fine_level)
 static int interpolate_level(mg3d_t* mg, int fine_level, int add, int colour_mask, int defer_halo)
 {
     mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
-    int lo, hi;
+    int lo, hi, st;
     interior_range(F, &lo, &hi);
+    if ((st = ensure_v_ghosts(mg, fine_level + 1))) return st; /* the last fine plane of a slab reads the coarse plane above */
     PROF_BEGIN(mg, fine_level, MG_OP_INTERPOLATE);
     MG_LAUNCH(mg->launches, mgk3d_interpolate(mg->stream, mg->dtype, F->v, F->g, C->v, C->g, add, colour_mask, lo, hi));
     PROF_END(mg);
-    if (defer_halo && F->dist) return exchange_deferred(mg, fine_level, F->v, colour_mask, 1, 1);
+    if (!F->dist) return MG_OK;
+    /* a level the temporally blocked smoother takes next fetches its (deeper) ghost planes itself */
+    /* The owned planes of the fine v changed: the neighbours' ghost copies are stale.  A level the temporally blocked
+       smoother takes next fetches its (deeper) ghost planes itself, and whoever else reads ghost planes refreshes them
+       first (ensure_v_ghosts); otherwise the colour that changed travels now. */
+    if (level_takes_pipe(mg, F) || !F->vg_valid) {
+        F->vg_valid = 0;
+        return MG_OK;
+    }
+    if (defer_halo) return exchange_deferred(mg, fine_level, F->v, colour_mask, 1, 1);
     return exchange(mg, fine_level, F->v, colour_mask, 1, 1);
 }
 
@@ -1141,7 +1226,12 @@ int mg3d_set_to_value(mg3d_t* mg, int level, int field, double value, int modify
     mg_level3d* L = &mg->lv[level];
     /* ghost planes take the same constant; the exchange is the neighbour handshake (see mg3d_init_problem) */
     MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, field_ptr(L, field), L->g, value, modify_boundaries, 0, L->g.nzl));
-    return exchange(mg, level, field_ptr(L, field), 3, MG_GHOST_LO, 1);
+    st = exchange(mg, level, field_ptr(L, field), 3, MG_GHOST_LO, MG_GHOST_HI);
+    if (!st && field == MG_FIELD_V) {
+        L->vg_valid = 1;
+        st = mirror_v_ghosts(mg, level);
+    }
+    return st;
 }
 
 /* VCycle, N3/MultiGrid3D.cpp:623-647.  CalculateResidual + Restrict + setToValue(coarse v, 0, true)
@@ -1193,12 +1283,16 @@ int mg3d_vcycle(mg3d_t* mg, int level, int v1, int v2)
     /* a captured graph bakes in which of its two v buffers every level works on (the temporally blocked smoothers
        ping-pong), so that state is part of the key; a cycle with an odd number of passes ends on the other buffers and
        the next call finds (or captures) the graph that starts there */
-    unsigned cur_now = 0;
-    for (int l = 0; l < mg->nlevels && l < 32; l++) cur_now |= (unsigned)mg->lv[l].cur << l;
+    unsigned cur_now = 0, vg_now = 0;
+    for (int l = 0; l < mg->nlevels && l < 32; l++) {
+        cur_now |= (unsigned)mg->lv[l].cur << l;
+        vg_now |= (unsigned)(mg->lv[l].vg_valid != 0) << l;
+    }
     mg_graph_slot* g = NULL;
     for (int i = 0; i < MG_GRAPH_SLOTS && !g; i++)
         if (mg->graphs[i].used && mg->graphs[i].level == level && mg->graphs[i].v1 == v1 && mg->graphs[i].v2 == v2 &&
-            mg->graphs[i].smoother == mg->smoother && mg->graphs[i].arith == mg->arith && mg->graphs[i].cur_start == cur_now)
+            mg->graphs[i].smoother == mg->smoother && mg->graphs[i].arith == mg->arith && mg->graphs[i].cur_start == cur_now &&
+            mg->graphs[i].vg_start == vg_now)
             g = &mg->graphs[i];
     if (!g) {
         for (int i = 0; i < MG_GRAPH_SLOTS && !g; i++)
@@ -1207,6 +1301,7 @@ int mg3d_vcycle(mg3d_t* mg, int level, int v1, int v2)
         memset(g, 0, sizeof *g);
         g->used = 1; g->level = level; g->v1 = v1; g->v2 = v2; g->smoother = mg->smoother; g->arith = mg->arith;
         g->cur_start = cur_now;
+        g->vg_start = vg_now;
     }
     g->calls++;
     if (g->calls == 1) return vcycle_rec(mg, level, v1, v2);
@@ -1216,11 +1311,13 @@ int mg3d_vcycle(mg3d_t* mg, int level, int v1, int v2)
         MG_CUDA(cudaStreamBeginCapture(mg->stream, cudaStreamCaptureModeThreadLocal));
         st = vcycle_rec(mg, level, v1, v2);
         cudaError_t e = cudaStreamEndCapture(mg->stream, &graph);
-        g->cur_end = 0;
-        for (int l = 0; l < mg->nlevels; l++) { /* nothing ran during the capture: undo the host-side buffer flips */
+        g->cur_end = g->vg_end = 0;
+        for (int l = 0; l < mg->nlevels; l++) { /* nothing ran during the capture: undo the host-side state changes */
             if (l < 32) g->cur_end |= (unsigned)mg->lv[l].cur << l;
+            if (l < 32) g->vg_end |= (unsigned)(mg->lv[l].vg_valid != 0) << l;
             mg->lv[l].cur = (int)((cur_now >> l) & 1u);
             mg->lv[l].v = mg->lv[l].vbuf[mg->lv[l].cur];
+            mg->lv[l].vg_valid = (int)((vg_now >> l) & 1u);
         }
         g->launches = mg->launches - l0;
         g->halo_bytes = mg->halo_bytes - h0;
@@ -1242,9 +1339,10 @@ int mg3d_vcycle(mg3d_t* mg, int level, int v1, int v2)
         }
     }
     MG_CUDA(cudaGraphLaunch(g->exec, mg->stream));
-    for (int l = 0; l < mg->nlevels && l < 32; l++) { /* the replay leaves every level on the buffer the capture ended on */
+    for (int l = 0; l < mg->nlevels && l < 32; l++) { /* the replay leaves every level in the state the capture ended in */
         mg->lv[l].cur = (int)((g->cur_end >> l) & 1u);
         mg->lv[l].v = mg->lv[l].vbuf[mg->lv[l].cur];
+        mg->lv[l].vg_valid = (int)((g->vg_end >> l) & 1u);
     }
     mg->launches += g->launches;
     mg->halo_bytes += g->halo_bytes;
@@ -1392,9 +1490,11 @@ int mg3d_vcycle_host(mg3d_t* mg, void* v_host, const void* f_host, int v1, int v
     if (v1 < 0 || v2 < 0 || cycles < 0) return mg_fail(MG_ERR_ARG, "negative count");
     mg_level3d* L = &mg->lv[0];
     int st = copy_in(mg, L->v, &L->g, v_host, L->own_lo, L->own_hi);
-    if (!st) st = exchange(mg, 0, L->v, 3, MG_GHOST_LO, 1);
+    if (!st) st = exchange(mg, 0, L->v, 3, MG_GHOST_LO, MG_GHOST_HI);
+    if (!st) L->vg_valid = 1;
+    if (!st) st = mirror_v_ghosts(mg, 0);
     if (!st) st = copy_in(mg, L->f, &L->g, f_host, L->own_lo, L->own_hi);
-    if (!st) st = exchange(mg, 0, L->f, 3, MG_GHOST_LO, 1);
+    if (!st) st = exchange(mg, 0, L->f, 3, MG_GHOST_LO, MG_GHOST_HI);
     for (int i = 0; i < cycles && !st; i++) st = vcycle_rec(mg, 0, v1, v2);
     if (!st) st = copy_out(mg, v_host, L->v, &L->g, L->own_lo, L->own_hi);
     return st;

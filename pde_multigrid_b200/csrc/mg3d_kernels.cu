@@ -295,12 +295,14 @@ __global__ void k_apply_correction(T* __restrict__ fine, const T* __restrict__ e
     fine[i] = add(fine[i], err[i]);
 }
 
+// zl_skip_lo < zl_skip_hi: the planes [zl_skip_lo, zl_skip_hi) are left out (a slab's own planes: only its ghost planes are set)
 template <typename T>
-__global__ void k_set(T* __restrict__ a, mg_geom3d g, T value, int modify_boundaries, int zl_lo)
+__global__ void k_set(T* __restrict__ a, mg_geom3d g, T value, int modify_boundaries, int zl_lo, int zl_skip_lo, int zl_skip_hi)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int zl = zl_lo + blockIdx.z;
+    int zl = zl_lo + blockIdx.z;
+    if (zl >= zl_skip_lo) zl += zl_skip_hi - zl_skip_lo;
     const int z = g.z0 + zl;
     if (x >= g.n || y >= g.n) return;
     if (!modify_boundaries && (x == 0 || x == g.n - 1 || y == 0 || y == g.n - 1 || z == 0 || z == g.n - 1)) return;
@@ -527,9 +529,22 @@ int mgk3d_set(cudaStream_t s, int dtype, void* a, mg_geom3d g, double value, int
     if (zl_hi <= zl_lo) return 0;
     dim3 block = block2d(g.n), grid((g.n + block.x - 1) / block.x, (g.n + block.y - 1) / block.y, zl_hi - zl_lo);
     if (dtype == 0)
-        k_set<float><<<grid, block, 0, s>>>((float*)a, g, (float)value, modify_boundaries, zl_lo);
+        k_set<float><<<grid, block, 0, s>>>((float*)a, g, (float)value, modify_boundaries, zl_lo, 0, 0);
     else
-        k_set<double><<<grid, block, 0, s>>>((double*)a, g, value, modify_boundaries, zl_lo);
+        k_set<double><<<grid, block, 0, s>>>((double*)a, g, value, modify_boundaries, zl_lo, 0, 0);
+    return launch_ok();
+}
+
+/* every stored plane EXCEPT [own_lo, own_hi): the ghost planes of a slab */
+int mgk3d_set_ghosts(cudaStream_t s, int dtype, void* a, mg_geom3d g, double value, int own_lo, int own_hi)
+{
+    const int nz = g.nzl - (own_hi - own_lo);
+    if (nz <= 0) return 0;
+    dim3 block = block2d(g.n), grid((g.n + block.x - 1) / block.x, (g.n + block.y - 1) / block.y, nz);
+    if (dtype == 0)
+        k_set<float><<<grid, block, 0, s>>>((float*)a, g, (float)value, 1, 0, own_lo, own_hi);
+    else
+        k_set<double><<<grid, block, 0, s>>>((double*)a, g, value, 1, 0, own_lo, own_hi);
     return launch_ok();
 }
 

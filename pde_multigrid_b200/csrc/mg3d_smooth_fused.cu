@@ -58,7 +58,8 @@ struct FusedMaps {
 
 template <typename T, bool FAST>
 __global__ void __launch_bounds__(NT, 1)
-k_relax_fused2(const __grid_constant__ FusedMaps maps, T* __restrict__ v_out, mg_geom3d g, Coef3<T> c, int zchunk, unsigned int* cond)
+k_relax_fused2(const __grid_constant__ FusedMaps maps, T* __restrict__ v_out, mg_geom3d g, Coef3<T> c, int zchunk, int zlo, int zhi,
+               unsigned int* cond)
 {
     // conditional launch (the exact fallback of mg3d_smooth_pipe.cu): nothing to do unless the flag was raised.  Nobody
     // changes the flag while this grid runs (the last CTA to finish clears it), so every CTA takes the same branch.
@@ -72,7 +73,7 @@ k_relax_fused2(const __grid_constant__ FusedMaps maps, T* __restrict__ v_out, mg
     const int tid = threadIdx.x;
     const int i0 = blockIdx.x * TI, X0 = 2 * i0;
     const int y0 = blockIdx.y * TY;
-    const int zs = blockIdx.z * zchunk, ze = min(zs + zchunk, g.nzl);  // output planes [zs, ze)
+    const int zs = zlo + blockIdx.z * zchunk, ze = min(zs + zchunk, zhi);  // output planes [zs, ze), local indices
     const int n = g.n;
 
     if (tid == 0) {
@@ -178,8 +179,8 @@ k_relax_fused2(const __grid_constant__ FusedMaps maps, T* __restrict__ v_out, mg
         int sb[7];  // element offset of the slot of plane p-j
 #pragma unroll
         for (int j = 0; j < 7; j++) sb[j] = ((p - j - pb) & (NS - 1)) * SLOT;
-        const unsigned zpar = (unsigned)p & 1u;
-        auto plane_on = [&](int q, int e) { return q >= 1 && q <= n - 2 && q >= zs - e && q < ze + e; };
+        const unsigned zpar = (unsigned)p & 1u;  // (the slab's z0 is folded into the per-slot parity bit above)
+        auto plane_on = [&](int q, int e) { return g.z0 + q >= 1 && g.z0 + q <= n - 2 && q >= zs - e && q < ze + e; };
         // phase A: red of sweep 1 on plane p-1, red of sweep 2 on plane p-4
         stage(0, 1, 0, plane_on(p - 1, 3), sb, zpar);
         stage(2, 4, 0, plane_on(p - 4, 1), sb, zpar);
@@ -211,16 +212,18 @@ template <typename T>
 size_t smem_bytes_t() { return (size_t)NS * FBox<T>::SLOT * sizeof(T) + NS * sizeof(uint64_t); }
 
 template <typename T, bool FAST>
-int launch_k(cudaStream_t s, const FusedMaps& m, T* v_out, mg_geom3d g, mg_coef3d c, dim3 grid, int zchunk, unsigned int* cond)
+int launch_k(cudaStream_t s, const FusedMaps& m, T* v_out, mg_geom3d g, mg_coef3d c, dim3 grid, int zchunk, int zlo, int zhi, unsigned int* cond)
 {
     MG_SET_SMEM_LIMIT((k_relax_fused2<T, FAST>), smem_bytes_t<T>());
-    k_relax_fused2<T, FAST><<<grid, NT, smem_bytes_t<T>(), s>>>(m, v_out, g, narrow<T>(c), zchunk, cond);
+    k_relax_fused2<T, FAST><<<grid, NT, smem_bytes_t<T>(), s>>>(m, v_out, g, narrow<T>(c), zchunk, zlo, zhi, cond);
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 
 template <typename T>
-int launch(cudaStream_t s, const void* const maps4[4], T* v_out, mg_geom3d g, mg_coef3d c, unsigned int* cond)
+int launch(cudaStream_t s, const void* const maps4[4], T* v_out, mg_geom3d g, mg_coef3d c, int zlo, int zhi, unsigned int* cond)
 {
+    if (zhi <= zlo) return 0;
+    const int nz = zhi - zlo;
     FusedMaps m;
     memcpy(&m.v[0], maps4[0], sizeof(CUtensorMap));
     memcpy(&m.v[1], maps4[1], sizeof(CUtensorMap));
@@ -231,16 +234,16 @@ int launch(cudaStream_t s, const void* const maps4[4], T* v_out, mg_geom3d g, mg
     int nchunk = 1;
     double best = 1e30;
     for (int k = 1; k <= 8; k *= 2) {
-        const int zc = (g.nzl + k - 1) / k;
+        const int zc = (nz + k - 1) / k;
         if (k > 1 && zc < 64) break;
         const long long ctas = (long long)tx * ty * k;
         const double cost = (double)((ctas + 147) / 148) * (zc + 2 * HALO + 2);
         if (cost < best) { best = cost; nchunk = k; }
     }
-    const int zchunk = (g.nzl + nchunk - 1) / nchunk;
-    dim3 grid(tx, ty, (g.nzl + zchunk - 1) / zchunk);
-    if (c.fast_den) return launch_k<T, true>(s, m, v_out, g, c, grid, zchunk, cond);
-    return launch_k<T, false>(s, m, v_out, g, c, grid, zchunk, cond);
+    const int zchunk = (nz + nchunk - 1) / nchunk;
+    dim3 grid(tx, ty, (nz + zchunk - 1) / zchunk);
+    if (c.fast_den) return launch_k<T, true>(s, m, v_out, g, c, grid, zchunk, zlo, zhi, cond);
+    return launch_k<T, false>(s, m, v_out, g, c, grid, zchunk, zlo, zhi, cond);
 }
 
 }  // namespace
@@ -248,8 +251,8 @@ int launch(cudaStream_t s, const void* const maps4[4], T* v_out, mg_geom3d g, mg
 /* maps4: tensor maps of {v_in colour 0, v_in colour 1, f colour 0, f colour 1} with box
    (MGK3D_FU_BOX_I(esize), MGK3D_FU_BOX_Y, 1); v_out: the other v buffer of the level (all planes are written) */
 extern "C" int mgk3d_relax_fused2(cudaStream_t s, int dtype, const void* const maps4[4], void* v_out, mg_geom3d g, mg_coef3d c,
-                                  unsigned int* cond)
+                                  int zl_lo, int zl_hi, unsigned int* cond)
 {
-    if (dtype == 0) return launch<float>(s, maps4, (float*)v_out, g, c, cond);
-    return launch<double>(s, maps4, (double*)v_out, g, c, cond);
+    if (dtype == 0) return launch<float>(s, maps4, (float*)v_out, g, c, zl_lo, zl_hi, cond);
+    return launch<double>(s, maps4, (double*)v_out, g, c, zl_lo, zl_hi, cond);
 }

@@ -106,7 +106,7 @@ __device__ __forceinline__ T gs_update(T own, T nbx, T N, T S, T D, T U, T f, T 
 template <typename T, int ARITH>
 __global__ void __launch_bounds__(NT, 1)
 k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in, T* __restrict__ v_out, mg_geom3d g, T h2, T y6,
-              int zchunk, unsigned glo, unsigned gspan, unsigned int* __restrict__ flag)
+              int zchunk, int zlo, int zhi, unsigned glo, unsigned gspan, unsigned int* __restrict__ flag)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int PADL = PBox<T>::PADL, W = PBox<T>::W, SLOT = PBox<T>::SLOT, NSLOT = PBox<T>::NSLOT, GUARD = PBox<T>::GUARD;
@@ -120,7 +120,7 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = g.n, imax = (n - 1) / 2;
     const int i0 = blockIdx.x * TXO, y0 = blockIdx.y * TYO;
-    const int zs = blockIdx.z * zchunk, ze = min(zs + zchunk, g.nzl);  // output planes [zs, ze)
+    const int zs = zlo + blockIdx.z * zchunk, ze = min(zs + zchunk, zhi);  // output planes [zs, ze), local indices
     const int pb = zs - ZH, nsteps = ze - zs + 2 * ZH;                  // raw planes pb .. pb+nsteps-1, one per step
 
     if (tid == 0) {
@@ -377,21 +377,23 @@ template <> void guard_window<float>(double h2, unsigned* glo, unsigned* gspan)
 
 template <typename T, int ARITH>
 int launch_k(cudaStream_t s, const PipeMaps& m, const T* v_in, const T* f, T* v_out, mg_geom3d g, mg_coef3d c, dim3 grid, int zchunk,
-             unsigned int* flag)
+             int zlo, int zhi, unsigned int* flag)
 {
     MG_SET_SMEM_LIMIT((k_relax_pipe2<T, ARITH>), smem_bytes_t<T>());
     unsigned glo, gspan;
     guard_window<T>(c.hx2, &glo, &gspan);
     const T y6 = T(1) / T(6);
     (void)f;  // f only enters through its tensor maps
-    k_relax_pipe2<T, ARITH><<<grid, NT, smem_bytes_t<T>(), s>>>(m, v_in, v_out, g, (T)c.hx2, y6, zchunk, glo, gspan, flag);
+    k_relax_pipe2<T, ARITH><<<grid, NT, smem_bytes_t<T>(), s>>>(m, v_in, v_out, g, (T)c.hx2, y6, zchunk, zlo, zhi, glo, gspan, flag);
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 
 template <typename T>
-int launch(cudaStream_t s, const void* const maps3[3], const T* v_in, const T* f, T* v_out, mg_geom3d g, mg_coef3d c, int arith,
-           unsigned int* flag)
+int launch(cudaStream_t s, const void* const maps3[3], const T* v_in, const T* f, T* v_out, mg_geom3d g, mg_coef3d c, int zlo, int zhi,
+           int arith, unsigned int* flag)
 {
+    if (zhi <= zlo) return 0;
+    const int nz = zhi - zlo;
     PipeMaps m;
     memcpy(&m.vblack, maps3[0], sizeof(CUtensorMap));
     memcpy(&m.f[0], maps3[1], sizeof(CUtensorMap));
@@ -408,27 +410,28 @@ int launch(cudaStream_t s, const void* const maps3[3], const T* v_in, const T* f
     int nchunk = 1;
     double best = 1e30;
     for (int k = 1; k <= 16; k++) {
-        const int zc = (g.nzl + k - 1) / k;
+        const int zc = (nz + k - 1) / k;
         if (k > 1 && zc < 32) break;
-        const long long ctas = (long long)tx * ty * ((g.nzl + zc - 1) / zc);
+        const long long ctas = (long long)tx * ty * ((nz + zc - 1) / zc);
         const double cost = (double)((ctas + sms - 1) / sms) * (zc + 2 * ZH + 3);
         if (cost < best) { best = cost; nchunk = k; }
     }
-    const int zchunk = (g.nzl + nchunk - 1) / nchunk;
-    dim3 grid(tx, ty, (g.nzl + zchunk - 1) / zchunk);
-    if (arith) return launch_k<T, 1>(s, m, v_in, f, v_out, g, c, grid, zchunk, flag);
-    return launch_k<T, 0>(s, m, v_in, f, v_out, g, c, grid, zchunk, flag);
+    const int zchunk = (nz + nchunk - 1) / nchunk;
+    dim3 grid(tx, ty, (nz + zchunk - 1) / zchunk);
+    if (arith) return launch_k<T, 1>(s, m, v_in, f, v_out, g, c, grid, zchunk, zlo, zhi, flag);
+    return launch_k<T, 0>(s, m, v_in, f, v_out, g, c, grid, zchunk, zlo, zhi, flag);
 }
 
 }  // namespace
 
-/* maps3: tensor maps of {v_in colour 1, f colour 0, f colour 1} with box (MGK3D_PP_BOX_I(esize), MGK3D_PP_BOX_Y, 1).
+/* Local planes [zl_lo, zl_hi) of v_out are written (a slab: the planes it owns; v_in colour 1 and f need four valid planes
+   on each side of them).  maps3: tensor maps of {v_in colour 1, f colour 0, f colour 1} with box (MGK3D_PP_BOX_I(esize), MGK3D_PP_BOX_Y, 1).
    Requires c.fast_den and hx2 == hy2 == hz2 (checked by the caller).  arith 0: bit-exact, *flag is raised when a value
    left the range in which the scaled formula is provably identical to the reference's (the caller enqueues the
    conditional literal-arithmetic pass after this one); arith 1: MG_ARITH_FAST. */
 extern "C" int mgk3d_relax_pipe2(cudaStream_t s, int dtype, const void* const maps3[3], const void* v_in, const void* f, void* v_out,
-                                 mg_geom3d g, mg_coef3d c, int arith, unsigned int* flag)
+                                 mg_geom3d g, mg_coef3d c, int zl_lo, int zl_hi, int arith, unsigned int* flag)
 {
-    if (dtype == 0) return launch<float>(s, maps3, (const float*)v_in, (const float*)f, (float*)v_out, g, c, arith, flag);
-    return launch<double>(s, maps3, (const double*)v_in, (const double*)f, (double*)v_out, g, c, arith, flag);
+    if (dtype == 0) return launch<float>(s, maps3, (const float*)v_in, (const float*)f, (float*)v_out, g, c, zl_lo, zl_hi, arith, flag);
+    return launch<double>(s, maps3, (const double*)v_in, (const double*)f, (double*)v_out, g, c, zl_lo, zl_hi, arith, flag);
 }

@@ -66,7 +66,8 @@ int mgk3d_relax_colour_tma(cudaStream_t s, int dtype, const void* tmap_other, vo
                            mg_coef3d c, int colour, int zl_lo, int zl_hi);
 /* temporally blocked smoother (mg3d_smooth_fused.cu): TWO full RB sweeps in one pass over HBM, out of place.
    maps4 = tensor maps of {v_in colour 0, v_in colour 1, f colour 0, f colour 1} with box
-   (MGK3D_FU_BOX_I(esize), MGK3D_FU_BOX_Y, 1); every plane of v_out is written */
+   (MGK3D_FU_BOX_I(esize), MGK3D_FU_BOX_Y, 1); local planes [zl_lo, zl_hi) of v_out are written (a slab: the planes it owns;
+   the input needs four valid planes of colour 1 on each side of them) */
 #define MGK3D_FU_TI 32
 #define MGK3D_FU_TY 16
 #define MGK3D_FU_BOX_I(esize) (MGK3D_FU_TI + 2 * (16 / (int)(esize)))
@@ -74,7 +75,7 @@ int mgk3d_relax_colour_tma(cudaStream_t s, int dtype, const void* tmap_other, vo
 /* cond: NULL = always run; otherwise {flag, done counter}: the pass runs only when *flag != 0 (raised by
    mgk3d_relax_pipe2) and the last CTA to finish clears both words */
 int mgk3d_relax_fused2(cudaStream_t s, int dtype, const void* const maps4[4], void* v_out, mg_geom3d g, mg_coef3d c,
-                       unsigned int* cond);
+                       int zl_lo, int zl_hi, unsigned int* cond);
 /* register-tiled temporally blocked smoother (mg3d_smooth_pipe.cu): TWO full RB sweeps per pass, out of place, 2.5*B*N
    bytes.  maps3 = tensor maps of {v_in colour 1, f colour 0, f colour 1} with box (MGK3D_PP_BOX_I(esize), MGK3D_PP_BOX_Y, 1).
    Needs c.fast_den and hx2 == hy2 == hz2.  arith 0: bit-exact (flag raised when the exactness range check fails: the
@@ -87,7 +88,7 @@ int mgk3d_relax_fused2(cudaStream_t s, int dtype, const void* const maps4[4], vo
 #define MGK3D_PP_BOX_I(esize) (32 + 2 * MGK3D_PP_PADL(esize))
 #define MGK3D_PP_BOX_Y (MGK3D_PP_R * MGK3D_PP_NW)
 int mgk3d_relax_pipe2(cudaStream_t s, int dtype, const void* const maps3[3], const void* v_in, const void* f, void* v_out,
-                      mg_geom3d g, mg_coef3d c, int arith, unsigned int* flag);
+                      mg_geom3d g, mg_coef3d c, int zl_lo, int zl_hi, int arith, unsigned int* flag);
 /* the coarse tail of a V-cycle in one launch (mg3d_tail.cu): V(v1,v2) on the sub-hierarchy g[0..nlev-1], g[0].n <=
    MGK3D_TAIL_N, every level resident in one CTA's shared memory */
 #define MGK3D_TAIL_N 17
@@ -135,6 +136,8 @@ int mgk3d_apply_correction(cudaStream_t s, int dtype, void* fine, const void* er
 /* setToValue */
 int mgk3d_set(cudaStream_t s, int dtype, void* a, mg_geom3d g, double value, int modify_boundaries, int zl_lo,
               int zl_hi);
+/* the same on every stored plane except [own_lo, own_hi): the ghost planes of a slab, boundary points included */
+int mgk3d_set_ghosts(cudaStream_t s, int dtype, void* a, mg_geom3d g, double value, int own_lo, int own_hi);
 /* Grid3D::InitF from per-axis tables sx,sy,sz (device doubles, n each) = sin(PI*coord) computed with
    the host libm exactly like the reference: f = (T)(-3*PI*PI*sx*sy*sz), N3/Grid3D.cpp:92 */
 int mgk3d_init_f(cudaStream_t s, int dtype, void* f, mg_geom3d g, const double* sx, const double* sy,

@@ -74,6 +74,21 @@ def main():
                     dn, sn = d.residual_norm(0), s.residual_norm(0)
                     if not (abs(dn[0] - sn[0]) <= 1e-12 * abs(sn[0]) and dn[1] == sn[1]):
                         failures.append("%s: norms %r vs %r" % (tag, dn, sn))
+                    if d.field_checksum(0) != s.field_checksum(0) or d.field_checksum(1, mg.MG_FIELD_F) != s.field_checksum(1, mg.MG_FIELD_F):
+                        failures.append("%s: field checksums (summed over the ranks) differ from the single-GPU ones" % tag)
+                # pure two-sweep passes (temporally blocked smoother on the slabs), eager, captured, replayed
+                for step in range(3):
+                    d.VCycle(0, 2, 2)
+                    s.VCycle(0, 2, 2)
+                for l in range(d.numGrids):
+                    zb, zc = d.owned_range(l)
+                    if not same(d.get_v(l), s.get_v(l)[zb:zb + zc]):
+                        failures.append("%s: v level %d differs after three V(2,2) on rank %d" % (tag, l, rank))
+                d.Relax(0, 4)
+                s.Relax(0, 4)
+                zb, zc = d.owned_range(0)
+                if not same(d.get_v(0), s.get_v(0)[zb:zb + zc]):
+                    failures.append("%s: Relax(0, 4) differs on rank %d" % (tag, rank))
                 zb, zc = d.owned_range(0)
                 if not same(d.CalculateResidual(0), s.CalculateResidual(0)[zb:zb + zc]):
                     failures.append("%s: CalculateResidual differs on rank %d" % (tag, rank))

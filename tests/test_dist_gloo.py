@@ -13,6 +13,11 @@ kernels, restricted to the planes a rank owns, and exchange planes over gloo exa
 The weighted-Jacobi option runs through the same test with its own slab schedule (new colour 0 into a scratch array whose
 roles alternate with v, colour 1 in place, per-colour exchanges of whichever array holds the new values, copy back of the
 owned planes and the nearest ghosts after an odd number of sweeps) against the whole-grid definition of the sweep.
+The temporally blocked smoother (smoother "pipe", the default on the large levels) has its own schedule: ONE exchange of four
+planes of colour 1 in each direction in front of every two-sweep pass, the halo planes swept redundantly (R1 on [a-3, b+3),
+B1 on [a-2, b+2), R2 on [a-1, b+1), B2 on [a, b)), only the owned planes written (to the other v buffer, whose remaining planes
+are NaN here), ghost planes of v refreshed lazily by whoever reads them next (residual+restrict: two planes up, one down;
+prolongation: the coarse level), coarse f exchanged four planes deep.
 If a ghost depth or an exchange were missing, a NaN (or a stale value) would reach an owned plane.  The owned planes
 must equal the same cycles run sequentially on the whole grid WITH THE FULL CORRECTION, bit for bit (RB Gauss-Seidel
 is partition-invariant, and the colour-0 half of the correction is dead)."""
@@ -28,6 +33,8 @@ import torch.multiprocessing as mp
 N = 65
 NU = 2
 NU_J = 3  # odd: every Jacobi smoothing call ends on the scratch array and copies back
+NU_P = 3  # temporally blocked smoother: one two-sweep pass plus a colour-by-colour remainder sweep
+PIPE_MIN_N = 33  # levels the emulated temporally blocked smoother takes (the engine: levels with tensor maps, n >= 257)
 CYCLES = 2
 
 
@@ -115,25 +122,34 @@ class Level:
         self.a, self.b = plan["z0"] + plan["own_lo"], plan["z0"] + plan["own_hi"]  # owned global planes
         self.v = np.full((n, n, n), np.nan)
         self.f = np.full((n, n, n), np.nan)
+        self.vg_valid = True
+        self.v_other = np.full((n, n, n), np.nan)  # second v buffer of the temporally blocked smoother
+
+    def mirror_v_ghosts(self):
+        """mg3d_host.c::mirror_v_ghosts: the ghost planes of the other buffer get the values of the current one"""
+        for z in list(range(max(self.z0, 0), self.a)) + list(range(self.b, min(self.z0 + self.nzl, self.n))):
+            self.v_other[z] = self.v[z]
 
     def interior(self):
         return max(self.a, 1), min(self.b, self.n - 1)
 
 
 def exchange(L, arr, rank, world, depth_up, down, colour=None):
-    """colour None: whole planes; otherwise only that colour's points of the ghost planes are overwritten."""
+    """depth_up planes travel up, `down` planes travel down.  colour None: whole planes; otherwise only that colour's points of
+    the ghost planes are overwritten."""
     if not L.dist:
         return
+    down = int(down)
     reqs = []
     if rank + 1 < world:
         if depth_up:
             reqs.append(dist.isend(torch.from_numpy(arr[L.b - depth_up:L.b].copy()), rank + 1))
         if down:
-            up_ghost = torch.empty((1, L.n, L.n), dtype=torch.float64)
+            up_ghost = torch.empty((down, L.n, L.n), dtype=torch.float64)
             reqs.append(dist.irecv(up_ghost, rank + 1))
     if rank > 0:
         if down:
-            reqs.append(dist.isend(torch.from_numpy(arr[L.a:L.a + 1].copy()), rank - 1))
+            reqs.append(dist.isend(torch.from_numpy(arr[L.a:L.a + down].copy()), rank - 1))
         if depth_up:
             lo_ghost = torch.empty((depth_up, L.n, L.n), dtype=torch.float64)
             reqs.append(dist.irecv(lo_ghost, rank - 1))
@@ -148,10 +164,39 @@ def exchange(L, arr, rank, world, depth_up, down, colour=None):
             arr[z][m] = plane[m]
 
     if rank + 1 < world and down:
-        put(L.b, up_ghost.numpy()[0])
+        for k in range(down):
+            put(L.b + k, up_ghost.numpy()[k])
     if rank > 0 and depth_up:
         for k in range(depth_up):
             put(L.a - depth_up + k, lo_ghost.numpy()[k])
+
+
+def ensure_v_ghosts(L, rank, world):
+    """mg3d_host.c::ensure_v_ghosts"""
+    if L.dist and not L.vg_valid:
+        exchange(L, L.v, rank, world, 2, 1)
+        L.vg_valid = True
+
+
+def relax_pipe(L, rank, world, nu):
+    """mg3d_host.c::relax_level on a level the temporally blocked smoother takes: pairs of sweeps per pass, a remaining
+    single sweep colour by colour."""
+    n = L.n
+    while nu >= 2:
+        exchange(L, L.v, rank, world, 4, 4, 1)
+        w = L.v.copy()
+        for colour, e in ((0, 3), (1, 2), (0, 1), (1, 0)):  # R1, B1, R2, B2 on the owned planes grown by e
+            lo, hi = max(L.a - e, 1), min(L.b + e, n - 1)
+            relax_colour(w, L.f, colour, lo, hi)
+        out = L.v_other                  # the other buffer: only the owned planes are written; of its ghost planes the
+        out[L.a:L.b] = w[L.a:L.b]        # next pass will read the Dirichlet points (mirror_v_ghosts)
+        L.v_other = L.v
+        L.v = out
+        L.vg_valid = not L.dist
+        nu -= 2
+    if nu:
+        ensure_v_ghosts(L, rank, world)
+        relax(L, rank, world, nu)
 
 
 def relax(L, rank, world, nu):
@@ -223,16 +268,27 @@ def vcycle(levels, l, rank, world, engine_schedule=True, smoother="gs"):
     full ApplyCorrection, used for the sequential run the slabs are compared with.  smoother "jacobi": the weighted
     Jacobi option (full correction, both colours exchanged); the sequential run uses the whole-grid definition."""
     L = levels[l]
+    pipe = smoother == "pipe" and engine_schedule and L.n >= PIPE_MIN_N
     if smoother == "jacobi":
         smooth = (lambda: relax_jacobi(L, rank, world, NU_J)) if engine_schedule else (lambda: relax_jacobi_whole(L, NU_J))
         engine_colour = None
+    elif pipe:
+        smooth = lambda: relax_pipe(L, rank, world, NU_P)
+        engine_colour = 1
+    elif smoother == "pipe":
+        smooth = lambda: (ensure_v_ghosts(L, rank, world), relax(L, rank, world, NU_P))
+        engine_colour = 1 if engine_schedule else None
     else:
         smooth = lambda: relax(L, rank, world, NU)
         engine_colour = 1 if engine_schedule else None
     smooth()
     if l + 1 < len(levels):
         C = levels[l + 1]
-        exchange(L, L.v, rank, world, 2, 0)                       # plane a-2 for the fused residual+restrict
+        if smoother == "pipe":                                    # two planes up; one down as well if the ghosts are stale
+            exchange(L, L.v, rank, world, 2, 0 if L.vg_valid else 1)
+            L.vg_valid = True
+        else:
+            exchange(L, L.v, rank, world, 2, 0)                   # plane a-2 for the fused residual+restrict
         if C.dist or not L.dist:
             clo, chi = C.a, C.b
         else:                                                     # first agglomerated level: planes under my slab
@@ -240,8 +296,10 @@ def vcycle(levels, l, rank, world, engine_schedule=True, smoother="gs"):
         residual_restrict(L.v, L.f, C.f, C.v, clo, chi)
         if L.dist:
             C.v[max(C.z0, 0):C.z0 + C.nzl] = 0.0                  # coarse v = 0 wherever this rank stores it
+            C.mirror_v_ghosts()
+        C.vg_valid = True
         if C.dist:
-            exchange(C, C.f, rank, world, 2, 1)
+            exchange(C, C.f, rank, world, 4, 4)
         elif L.dist:                                              # all-gather of the equal shares + top plane from the last rank
             m = (C.n - 1) // world
             parts = [torch.empty((m, C.n, C.n), dtype=torch.float64) for _ in range(world)]
@@ -253,8 +311,13 @@ def vcycle(levels, l, rank, world, engine_schedule=True, smoother="gs"):
             C.f[C.n - 1] = top.numpy()[0]
         vcycle(levels, l + 1, rank, world, engine_schedule, smoother)
         lo, hi = L.interior()
+        if smoother == "pipe":
+            ensure_v_ghosts(C, rank, world)
         interpolate_add(L.v, C.v, lo, hi, engine_colour)
-        exchange(L, L.v, rank, world, 1, 1, engine_colour)
+        if smoother == "pipe" and L.dist and (pipe or not L.vg_valid):
+            L.vg_valid = False                                    # lazily: the next pass (or reader) fetches what it needs
+        else:
+            exchange(L, L.v, rank, world, 1, 1, engine_colour)
     smooth()
 
 
@@ -264,7 +327,7 @@ def problem(n):
     return np.zeros((n, n, n)), f
 
 
-def worker(rank, world, port, plans, out_queue, smoother="gs"):
+def worker(rank, world, port, plans, out_queue, smoother="gs", N=N):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -273,6 +336,7 @@ def worker(rank, world, port, plans, out_queue, smoother="gs"):
     L0 = levels[0]
     sl = slice(L0.z0, L0.z0 + L0.nzl)
     L0.v[sl], L0.f[sl] = v0[sl], f0[sl]
+    L0.mirror_v_ghosts()
     for _ in range(CYCLES):
         vcycle(levels, 0, rank, world, True, smoother)
     out_queue.put((rank, L0.a, L0.b, L0.v[L0.a:L0.b].copy()))
@@ -286,10 +350,11 @@ def free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("smoother", ["gs", "jacobi"])
+@pytest.mark.parametrize("smoother", ["gs", "jacobi", "pipe"])
 def test_slab_schedule_world2_gloo(mg, monkeypatch, smoother):
     world = 2
-    monkeypatch.setenv("MG_B200_DIST_MIN_N", "65")  # distribute the small test grid too (default threshold: n >= 257)
+    N = 129 if smoother == "pipe" else 65  # pipe: two distributed levels (129, 65), the coarse one fed by exchanged f ghosts
+    monkeypatch.setenv("MG_B200_DIST_MIN_N", "65")  # distribute the small test grids too (default threshold: n >= 257)
     plans = {(n, r): mg.MultiGrid3D.plan_level(n, world, r) for n in sizes(N) for r in range(world)}
     assert plans[(65, 0)]["dist"] == 1 and plans[(33, 0)]["dist"] == 0
     # sequential reference: the same stand-in kernels on the whole grid in one process
@@ -304,7 +369,7 @@ def test_slab_schedule_world2_gloo(mg, monkeypatch, smoother):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = free_port()
-    procs = [ctx.Process(target=worker, args=(r, world, port, plans, q, smoother)) for r in range(world)]
+    procs = [ctx.Process(target=worker, args=(r, world, port, plans, q, smoother, N)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=240) for _ in range(world)]

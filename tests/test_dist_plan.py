@@ -27,8 +27,8 @@ def test_slabs_tile_and_nest(mg, n, P):
             for r, p in enumerate(plans):
                 a, b = p["z0"] + p["own_lo"], p["z0"] + p["own_hi"]
                 owned.append((a, b))
-                assert p["own_lo"] == (2 if r > 0 else 0)              # two ghost planes below
-                assert p["nzl"] - p["own_hi"] == (1 if r < P - 1 else 0)  # one above
+                assert p["own_lo"] == (4 if r > 0 else 0)              # four ghost planes below ...
+                assert p["nzl"] - p["own_hi"] == (4 if r < P - 1 else 0)  # ... and above (two RB sweeps per smoother pass)
                 assert b - a >= 8
             assert owned[0][0] == 0 and owned[-1][1] == nl
             assert all(owned[r][1] == owned[r + 1][0] for r in range(P - 1))
