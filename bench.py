@@ -166,6 +166,31 @@ def parity_block(eng, n, dtype_tag):
                              "(tests/golden/make_hash.py)"}
 
 
+def bind_to_gpu_numa_node(torch, device_index):
+    """Host-side plumbing of the end-to-end leg: run this process (and therefore first-touch and pin its host buffers) on the
+    NUMA node the GPU hangs off, so that eight ranks do not pull their PCIe traffic across the socket interconnect.
+    Returns (node, n_cpus) or (None, 0) when the topology cannot be read."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None, 0
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None, 0
+        os.sched_setaffinity(0, cpus)
+        return node, len(cpus)
+    except Exception:
+        return None, 0
+
+
 def host_cpu_info():
     model = "unknown"
     try:
@@ -276,6 +301,14 @@ def other_configs(mg, torch, world, rank, uid, dist):
         e.close()
     if world == 8:
         n = 2049
+        import ctypes
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")  # a second communicator needs its own NCCL id
+        if rank == 0:
+            raw = (ctypes.c_ubyte * 128)()
+            mg._lib.check(mg.lib().mg_comm_unique_id(raw))
+            buf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().tolist())
         e = mg.MultiGrid3D(n, dtype=np.float64, residual_mode=mg.MG_CORRECTED, rank=rank, nranks=world, nccl_unique_id=uid)
         r0 = e.residual_norm(0)[0]
         for _ in range(2):
@@ -530,6 +563,7 @@ def main():
     if not args.no_e2e:
         zb, zc = eng.owned_range(0)
         cnt = zc * n * n
+        numa_node, numa_cpus = bind_to_gpu_numa_node(torch, local_rank)
         hv = torch.zeros(cnt, dtype=torch.float64 if B == 8 else torch.float32).pin_memory()
         hf = torch.empty(cnt, dtype=hv.dtype).pin_memory()
         hf_np = hf.numpy().reshape(zc, n, n)
@@ -548,7 +582,9 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": 1.0 / dt, "unit": "V-cycles/s", "h2d_bytes_per_step": 2 * N0 * B, "d2h_bytes_per_step": N0 * B,
-               "steps": args.e2e_steps, "ms_per_step": dt * 1e3,
+               "steps": args.e2e_steps, "ms_per_step": dt * 1e3, "pcie_gbs_per_gpu": 3 * N0 * B / world / dt / 1e9,
+               "host_buffers": "pinned, allocated on the GPU's NUMA node %s (%d CPUs bound)" % (numa_node, numa_cpus) if numa_node is not None
+                               else "pinned (NUMA topology not readable: no binding)",
                "call": "mg3d_vcycle_host (pinned host v,f -> device, VCycle(0,2,2), v -> host; every rank moves its own z-slab)",
                "timer": "host wall clock around the synchronous C-ABI call, barrier on both sides, max over ranks"}
         del hv, hf

@@ -94,6 +94,9 @@ int mg3d_plan_level(int n, int nranks, int rank, int out5[5]);
 /* global planes [z_begin, z_begin + z_count) this rank owns on `level` (the whole level when it is not distributed);
    set_field / get_field / residual / vcycle_host move exactly these planes */
 int mg3d_owned_range(const mg3d_t* mg, int level, int* z_begin, int* z_count);
+/* diagnostic: `reps` halo exchanges (colour_mask bit c = colour c; depth_up planes to rank+1, depth_down planes to rank-1)
+   of the current v of `level`, enqueued back to back: times the NVLink transport (scripts/bench_halo.py) */
+int mg3d_halo_benchmark(mg3d_t* mg, int level, int colour_mask, int depth_up, int depth_down, int reps);
 long long mg3d_halo_bytes(const mg3d_t* mg); /* bytes this rank has sent in halo exchanges and gathers so far */
 int mg3d_destroy(mg3d_t* mg); /* ~MultiGrid3D */
 int mg3d_num_levels(const mg3d_t* mg);         /* MultiGrid3D::numGrids */

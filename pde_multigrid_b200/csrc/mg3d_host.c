@@ -60,6 +60,9 @@ typedef struct {
        Every operator leaves it 1 except the temporally blocked smoother, whose pass only writes the planes a rank owns;
        whoever reads ghost planes of v calls ensure_v_ghosts() first. */
     int vg_valid;
+    /* 1 = the colour-1 ghost planes of v are valid to the full depth (InitV, set_field, setToValue, and the coarse v that
+       residual+restrict has just zeroed everywhere): the pass that comes next needs no exchange in front of it */
+    int vg_deep;
 } mg_level3d;
 
 /* direct NVLink halo path (mg_halo_p2p.cu): the neighbours' arenas and flag words mapped with CUDA IPC */
@@ -80,7 +83,7 @@ typedef struct {
 typedef struct {
     int used, level, v1, v2, smoother, arith, calls;
     unsigned cur_start, cur_end; /* bit l = which v buffer level l works on when the graph starts / has finished */
-    unsigned vg_start, vg_end;   /* bit l = mg_level3d.vg_valid */
+    unsigned vg_start, vg_end;   /* bits 2l, 2l+1 = mg_level3d.vg_valid, vg_deep */
     cudaGraphExec_t exec;
     long long launches, halo_bytes;
 } mg_graph_slot;
@@ -102,8 +105,10 @@ struct mg3d_s {
     double* d_scratch; /* 2*MGK_NORM_MAX_PARTS partials + 2 outputs */
     double* d_tables;  /* 3*n0 doubles: sin tables of InitF */
     double* h_out2;    /* pinned */
-    void* staging;     /* dense device staging buffer for host<->device field copies */
+    void* staging;     /* two dense device staging slots for host<->device field copies */
     size_t staging_bytes;
+    cudaStream_t xstream; /* copy stream of copy_in / copy_out */
+    cudaEvent_t ev_copied[2], ev_packed[2];
     long long launches;
     long long halo_bytes; /* bytes sent by this rank in halo exchanges / gathers */
     mg_prof prof;
@@ -531,6 +536,7 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
         L->own_lo = plan[3];
         L->own_hi = plan[4];
         L->vg_valid = 1;
+        L->vg_deep = 1;
         level_coefs(dtype, nl, range, L->h, &L->c);
         total += (size_t)level_fields(L) * field_bytes(L, dtype);
         nl = (nl - 1) / 2 + 1; /* N3/MultiGrid3D.cpp:40-42 */
@@ -634,6 +640,11 @@ int mg3d_destroy(mg3d_t* mg)
     if (mg->d_tables) cudaFree(mg->d_tables);
     if (mg->d_flag) cudaFree(mg->d_flag);
     if (mg->h_out2) cudaFreeHost(mg->h_out2);
+    if (mg->xstream) {
+        cudaStreamSynchronize(mg->xstream);
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(mg->ev_copied[i]); cudaEventDestroy(mg->ev_packed[i]); }
+        cudaStreamDestroy(mg->xstream);
+    }
     if (mg->staging) cudaFree(mg->staging);
     mg_prof_free(&mg->prof);
     for (int l = 0; mg->lv && l < mg->nlevels; l++)
@@ -722,37 +733,76 @@ int mg3d_sync(mg3d_t* mg)
     return halo_error_check(mg);
 }
 
-/* dense host array (x fastest, idx = x + y*n + z*n*n) <-> colour-split device field: one linear copy
-   between the host array and a dense device staging buffer, plus a repack kernel.  Local planes
-   [zl_lo, zl_hi) of the field correspond to the start of the host array. */
-static int staging_reserve(mg3d_t* mg, size_t bytes)
+/* dense host array (x fastest, idx = x + y*n + z*n*n) <-> colour-split device field, local planes [zl_lo, zl_hi) of the
+   field <-> the start of the host array.  Chunks of planes travel through two dense staging slots on a copy stream while
+   the repack kernel of the previous chunk runs on the handle's stream: the PCIe link never waits for a kernel, v and f
+   uploads follow each other without a gap, and the staging memory is two chunks instead of a whole field. */
+#define MG_XFER_CHUNK_BYTES ((size_t)96 << 20)
+
+static int xfer_reserve(mg3d_t* mg, size_t plane_bytes, int* planes_per_chunk)
 {
-    if (mg->staging_bytes >= bytes) return MG_OK;
-    if (mg->staging) { MG_CUDA(cudaStreamSynchronize(mg->stream)); cudaFree(mg->staging); mg->staging = NULL; mg->staging_bytes = 0; }
-    MG_CUDA(cudaMalloc(&mg->staging, bytes));
-    mg->staging_bytes = bytes;
+    int ppc = (int)(MG_XFER_CHUNK_BYTES / plane_bytes);
+    if (ppc < 1) ppc = 1;
+    const size_t need = 2 * (size_t)ppc * plane_bytes;
+    if (mg->staging_bytes < need) {
+        if (mg->staging) { MG_CUDA(cudaStreamSynchronize(mg->stream)); cudaFree(mg->staging); mg->staging = NULL; mg->staging_bytes = 0; }
+        MG_CUDA(cudaMalloc(&mg->staging, need));
+        mg->staging_bytes = need;
+    }
+    if (!mg->xstream) {
+        MG_CUDA(cudaStreamCreateWithFlags(&mg->xstream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            MG_CUDA(cudaEventCreateWithFlags(&mg->ev_copied[i], cudaEventDisableTiming));
+            MG_CUDA(cudaEventCreateWithFlags(&mg->ev_packed[i], cudaEventDisableTiming));
+        }
+    }
+    *planes_per_chunk = ppc;
     return MG_OK;
 }
 
 static int copy_in(mg3d_t* mg, void* dev, const mg_geom3d* g, const void* host, int zl_lo, int zl_hi)
 {
-    size_t dense = (size_t)g->n * g->n * (size_t)(zl_hi - zl_lo) * mg_esize(mg->dtype);
-    int st = staging_reserve(mg, dense);
+    const size_t pbytes = (size_t)g->n * g->n * mg_esize(mg->dtype);
+    int ppc, st = xfer_reserve(mg, pbytes, &ppc);
     if (st) return st;
-    MG_CUDA(cudaMemcpyAsync(mg->staging, host, dense, cudaMemcpyHostToDevice, mg->stream));
-    MG_LAUNCH(mg->launches, mgk3d_repack(mg->stream, mg->dtype, dev, *g, mg->staging, 1, zl_lo, zl_hi));
+    /* the copy stream starts after whatever the handle's stream has queued that may still read the staging slots */
+    MG_CUDA(cudaEventRecord(mg->ev_packed[0], mg->stream));
+    MG_CUDA(cudaEventRecord(mg->ev_packed[1], mg->stream));
+    int k = 0;
+    for (int z = zl_lo; z < zl_hi; z += ppc, k++) {
+        const int nz = zl_hi - z < ppc ? zl_hi - z : ppc, slot = k & 1;
+        char* stg = (char*)mg->staging + (size_t)slot * ppc * pbytes;
+        MG_CUDA(cudaStreamWaitEvent(mg->xstream, mg->ev_packed[slot], 0)); /* the slot's previous chunk has been repacked */
+        MG_CUDA(cudaMemcpyAsync(stg, (const char*)host + (size_t)(z - zl_lo) * pbytes, (size_t)nz * pbytes, cudaMemcpyHostToDevice, mg->xstream));
+        MG_CUDA(cudaEventRecord(mg->ev_copied[slot], mg->xstream));
+        MG_CUDA(cudaStreamWaitEvent(mg->stream, mg->ev_copied[slot], 0));
+        MG_LAUNCH(mg->launches, mgk3d_repack(mg->stream, mg->dtype, dev, *g, stg, 1, z, z + nz));
+        MG_CUDA(cudaEventRecord(mg->ev_packed[slot], mg->stream));
+    }
     return MG_OK;
 }
 
 static int copy_out(mg3d_t* mg, void* host, const void* dev, const mg_geom3d* g, int zl_lo, int zl_hi)
 {
-    size_t dense = (size_t)g->n * g->n * (size_t)(zl_hi - zl_lo) * mg_esize(mg->dtype);
-    int st = staging_reserve(mg, dense);
+    const size_t pbytes = (size_t)g->n * g->n * mg_esize(mg->dtype);
+    int ppc, st = xfer_reserve(mg, pbytes, &ppc);
     if (st) return st;
-    MG_LAUNCH(mg->launches, mgk3d_repack(mg->stream, mg->dtype, (void*)dev, *g, mg->staging, 0, zl_lo, zl_hi));
-    MG_CUDA(cudaMemcpyAsync(host, mg->staging, dense, cudaMemcpyDeviceToHost, mg->stream));
+    MG_CUDA(cudaEventRecord(mg->ev_copied[0], mg->xstream));
+    MG_CUDA(cudaEventRecord(mg->ev_copied[1], mg->xstream));
+    int k = 0;
+    for (int z = zl_lo; z < zl_hi; z += ppc, k++) {
+        const int nz = zl_hi - z < ppc ? zl_hi - z : ppc, slot = k & 1;
+        char* stg = (char*)mg->staging + (size_t)slot * ppc * pbytes;
+        MG_CUDA(cudaStreamWaitEvent(mg->stream, mg->ev_copied[slot], 0)); /* the slot's previous chunk is on its way to the host */
+        MG_LAUNCH(mg->launches, mgk3d_repack(mg->stream, mg->dtype, (void*)dev, *g, stg, 0, z, z + nz));
+        MG_CUDA(cudaEventRecord(mg->ev_packed[slot], mg->stream));
+        MG_CUDA(cudaStreamWaitEvent(mg->xstream, mg->ev_packed[slot], 0));
+        MG_CUDA(cudaMemcpyAsync((char*)host + (size_t)(z - zl_lo) * pbytes, stg, (size_t)nz * pbytes, cudaMemcpyDeviceToHost, mg->xstream));
+        MG_CUDA(cudaEventRecord(mg->ev_copied[slot], mg->xstream));
+    }
+    MG_CUDA(cudaStreamSynchronize(mg->xstream));
     MG_CUDA(cudaStreamSynchronize(mg->stream));
-    return MG_OK;
+    return halo_error_check(mg); /* data computed from ghost planes a neighbour never delivered must not look like a result */
 }
 
 /* host_dense holds the planes this rank owns (mg3d_owned_range): the whole grid on one GPU */
@@ -766,7 +816,7 @@ int mg3d_set_field(mg3d_t* mg, int level, int field, const void* host_dense)
     if (!st) st = exchange(mg, level, field_ptr(L, field), 3, MG_GHOST_LO, MG_GHOST_HI);
     if (st) return st;
     if (field == MG_FIELD_V) {
-        L->vg_valid = 1;
+        L->vg_valid = L->vg_deep = 1;
         if ((st = mirror_v_ghosts(mg, level))) return st;
     }
     MG_CUDA(cudaStreamSynchronize(mg->stream)); /* host buffer may be reused by the caller */
@@ -835,7 +885,7 @@ int mg3d_init_problem(mg3d_t* mg)
         if (!st) st = exchange(mg, l, L->f, 3, MG_GHOST_LO, MG_GHOST_HI);
         if (!st) st = mirror_v_ghosts(mg, l);
         if (st) return st;
-        L->vg_valid = 1;
+        L->vg_valid = L->vg_deep = 1;
     }
     return MG_OK;
 }
@@ -902,6 +952,7 @@ static int relax_jacobi_level(mg3d_t* mg, int level, int ncycles)
         MG_CUDA(cudaMemsetAsync(L->jscratch, 0, cbytes, mg->stream));
     }
     if ((st = ensure_v_ghosts(mg, level))) return st;
+    L->vg_deep = 0;
     char *red = (char*)L->v, *black = red + cbytes, *cur = red;
     const char *f_red = (const char*)L->f, *f_black = f_red + cbytes;
     for (int k = 0; k < ncycles; k++) {
@@ -946,7 +997,7 @@ static int relax_level(mg3d_t* mg, int level, int ncycles)
             const void* maps4[4] = {L->tmap_fu[L->cur][0], L->tmap_fu[L->cur][1], L->tmap_ff[0], L->tmap_ff[1]};
             /* slab: four planes of colour 1 from each neighbour -- all the pass reads of v beyond the planes it owns (one
                exchange per two sweeps instead of four; the halo planes are swept redundantly, bit-identical on both sides) */
-            if (L->dist && (st = exchange(mg, level, L->v, 2, MG_GHOST_LO, MG_GHOST_HI))) return st;
+            if (L->dist && !L->vg_deep && (st = exchange(mg, level, L->v, 2, MG_GHOST_LO, MG_GHOST_HI))) return st;
             PROF_BEGIN(mg, level, MG_OP_RELAX);
             MG_LAUNCH(mg->launches, mgk3d_relax_pipe2(mg->stream, mg->dtype, maps3, L->vbuf[L->cur], L->f, L->vbuf[L->cur ^ 1], L->g, L->c,
                                                       L->own_lo, L->own_hi, mg->arith == MG_ARITH_FAST, mg->d_flag));
@@ -955,12 +1006,13 @@ static int relax_level(mg3d_t* mg, int level, int ncycles)
             PROF_END(mg);
             L->cur ^= 1;
             L->v = L->vbuf[L->cur];
-            L->vg_valid = 0; /* only the owned planes of the new buffer were written */
+            L->vg_valid = L->vg_deep = 0; /* only the owned planes of the new buffer were written */
             ncycles -= 2;
         }
         if (ncycles <= 0) return MG_OK;
     }
     if ((st = ensure_v_ghosts(mg, level))) return st;
+    L->vg_deep = 0; /* the sweeps below refresh one ghost plane per side only */
     /* the shared-memory version of the same idea (literal arithmetic; slower than four colour launches, kept as the
        exact fallback above and selectable for tests) */
     if (mg->smoother == MG_SMOOTHER_FUSED && L->has_tma && L->vbuf[1] && !L->dist) {
@@ -1111,6 +1163,18 @@ int mg3d_abs_error(mg3d_t* mg, int level, double* mean_abs, double* max_abs)
     return halo_error_check(mg);
 }
 
+/* diagnostic: `reps` halo exchanges of (colour_mask, depth_up, depth_down) on the current v of `level`, back to back on the
+   handle's stream -- for timing the transport (scripts/bench_halo.py); the data it moves is what the ghosts hold anyway */
+int mg3d_halo_benchmark(mg3d_t* mg, int level, int colour_mask, int depth_up, int depth_down, int reps)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (depth_up < 0 || depth_up > MG_GHOST_LO || depth_down < 0 || depth_down > MG_GHOST_HI || reps < 0 || !(colour_mask & 3))
+        return mg_fail(MG_ERR_ARG, "bad halo benchmark arguments");
+    for (int i = 0; i < reps && !st; i++) st = exchange(mg, level, mg->lv[level].v, colour_mask & 3, depth_up, depth_down);
+    return st;
+}
+
 /* what follows a restriction onto level+1: refresh ghosts (distributed) or gather (first agglomerated level) */
 static int after_restrict(mg3d_t* mg, int fine_level, void* coarse_field, int defer)
 {
@@ -1135,7 +1199,7 @@ int mg3d_restrict(mg3d_t* mg, int fine_level, int field)
     MG_LAUNCH(mg->launches, mgk3d_restrict(mg->stream, mg->dtype, field_ptr(F, field), F->g, field_ptr(C, field), C->g, lo, hi));
     PROF_END(mg);
     st = after_restrict(mg, fine_level, field_ptr(C, field), 0);
-    if (!st && field == MG_FIELD_V) C->vg_valid = 1;
+    if (!st && field == MG_FIELD_V) C->vg_valid = C->vg_deep = 1;
     return st;
 }
 
@@ -1163,7 +1227,7 @@ static int residual_restrict_level(mg3d_t* mg, int fine_level, int defer_f_halo)
         if (C->dist && C->vbuf[1]) /* ... and on the ghost planes of its other buffer: see mirror_v_ghosts */
             MG_LAUNCH(mg->launches, mgk3d_set_ghosts(mg->stream, mg->dtype, C->vbuf[C->cur ^ 1], C->g, 0.0, C->own_lo, C->own_hi));
     }
-    C->vg_valid = 1;
+    C->vg_valid = C->vg_deep = 1;
     PROF_END(mg);
     return after_restrict(mg, fine_level, C->f, defer_f_halo);
 }
@@ -1194,6 +1258,7 @@ static int interpolate_level(mg3d_t* mg, int fine_level, int add, int colour_mas
     /* The owned planes of the fine v changed: the neighbours' ghost copies are stale.  A level the temporally blocked
        smoother takes next fetches its (deeper) ghost planes itself, and whoever else reads ghost planes refreshes them
        first (ensure_v_ghosts); otherwise the colour that changed travels now. */
+    F->vg_deep = 0;
     if (level_takes_pipe(mg, F) || !F->vg_valid) {
         F->vg_valid = 0;
         return MG_OK;
@@ -1228,7 +1293,7 @@ int mg3d_set_to_value(mg3d_t* mg, int level, int field, double value, int modify
     MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, field_ptr(L, field), L->g, value, modify_boundaries, 0, L->g.nzl));
     st = exchange(mg, level, field_ptr(L, field), 3, MG_GHOST_LO, MG_GHOST_HI);
     if (!st && field == MG_FIELD_V) {
-        L->vg_valid = 1;
+        L->vg_valid = L->vg_deep = 1;
         st = mirror_v_ghosts(mg, level);
     }
     return st;
@@ -1286,7 +1351,7 @@ int mg3d_vcycle(mg3d_t* mg, int level, int v1, int v2)
     unsigned cur_now = 0, vg_now = 0;
     for (int l = 0; l < mg->nlevels && l < 32; l++) {
         cur_now |= (unsigned)mg->lv[l].cur << l;
-        vg_now |= (unsigned)(mg->lv[l].vg_valid != 0) << l;
+        if (l < 16) vg_now |= ((unsigned)(mg->lv[l].vg_valid != 0) | ((unsigned)(mg->lv[l].vg_deep != 0) << 1)) << (2 * l);
     }
     mg_graph_slot* g = NULL;
     for (int i = 0; i < MG_GRAPH_SLOTS && !g; i++)
@@ -1314,10 +1379,11 @@ int mg3d_vcycle(mg3d_t* mg, int level, int v1, int v2)
         g->cur_end = g->vg_end = 0;
         for (int l = 0; l < mg->nlevels; l++) { /* nothing ran during the capture: undo the host-side state changes */
             if (l < 32) g->cur_end |= (unsigned)mg->lv[l].cur << l;
-            if (l < 32) g->vg_end |= (unsigned)(mg->lv[l].vg_valid != 0) << l;
+            if (l < 16) g->vg_end |= ((unsigned)(mg->lv[l].vg_valid != 0) | ((unsigned)(mg->lv[l].vg_deep != 0) << 1)) << (2 * l);
             mg->lv[l].cur = (int)((cur_now >> l) & 1u);
             mg->lv[l].v = mg->lv[l].vbuf[mg->lv[l].cur];
-            mg->lv[l].vg_valid = (int)((vg_now >> l) & 1u);
+            mg->lv[l].vg_valid = l < 16 ? (int)((vg_now >> (2 * l)) & 1u) : 1;
+            mg->lv[l].vg_deep = l < 16 ? (int)((vg_now >> (2 * l + 1)) & 1u) : 0;
         }
         g->launches = mg->launches - l0;
         g->halo_bytes = mg->halo_bytes - h0;
@@ -1342,7 +1408,8 @@ int mg3d_vcycle(mg3d_t* mg, int level, int v1, int v2)
     for (int l = 0; l < mg->nlevels && l < 32; l++) { /* the replay leaves every level in the state the capture ended in */
         mg->lv[l].cur = (int)((g->cur_end >> l) & 1u);
         mg->lv[l].v = mg->lv[l].vbuf[mg->lv[l].cur];
-        mg->lv[l].vg_valid = (int)((g->vg_end >> l) & 1u);
+        mg->lv[l].vg_valid = l < 16 ? (int)((g->vg_end >> (2 * l)) & 1u) : 1;
+        mg->lv[l].vg_deep = l < 16 ? (int)((g->vg_end >> (2 * l + 1)) & 1u) : 0;
     }
     mg->launches += g->launches;
     mg->halo_bytes += g->halo_bytes;
@@ -1491,7 +1558,7 @@ int mg3d_vcycle_host(mg3d_t* mg, void* v_host, const void* f_host, int v1, int v
     mg_level3d* L = &mg->lv[0];
     int st = copy_in(mg, L->v, &L->g, v_host, L->own_lo, L->own_hi);
     if (!st) st = exchange(mg, 0, L->v, 3, MG_GHOST_LO, MG_GHOST_HI);
-    if (!st) L->vg_valid = 1;
+    if (!st) L->vg_valid = L->vg_deep = 1;
     if (!st) st = mirror_v_ghosts(mg, 0);
     if (!st) st = copy_in(mg, L->f, &L->g, f_host, L->own_lo, L->own_hi);
     if (!st) st = exchange(mg, 0, L->f, 3, MG_GHOST_LO, MG_GHOST_HI);

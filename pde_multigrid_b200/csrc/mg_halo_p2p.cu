@@ -10,6 +10,7 @@
 // levels need.  Write-after-read safety comes from the SPMD schedule: every rank alternates compute and
 // bidirectional exchanges, so a neighbour cannot run ahead by more than one exchange.
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "mg_launch.h"
 
@@ -41,9 +42,9 @@ __global__ void __launch_bounds__(256) k_halo_exchange(XArgs a)
         const size_t n16 = a.bytes[s] / 16;
         for (size_t i = tid; i < n16; i += nth) dst[i] = src[i];
     }
-    __threadfence_system();  // my stores are visible to the peer before the flag
     __syncthreads();
     if (threadIdx.x != 0) return;
+    __threadfence_system();  // (cumulative over the CTA barrier) this CTA's stores are visible to the peer before the flag
     unsigned int* blk = a.block;
     const unsigned int prev = atomicAdd(blk + 64, 1u);
     if (prev != gridDim.x - 1) return;
@@ -55,20 +56,24 @@ __global__ void __launch_bounds__(256) k_halo_exchange(XArgs a)
             const unsigned int v = ++blk[128 + 32 * k];
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flag[k]), "r"(v) : "memory");
         }
-    // then wait for the neighbours' pushes of this same exchange (bounded: never hang the GPU)
+    // then wait for the neighbours' pushes of this same exchange.  Bounded (a GPU must never hang): on expiry the sticky
+    // error word is set -- every API call that hands data back checks it -- and BOTH expected counters have already
+    // advanced, so later exchanges stay in step.  max_cycles <= 0: wait for ever.
     const long long t0 = clock64();
     const int waits[2] = {a.wait_below, a.wait_above};
+    unsigned int want[2] = {0, 0};
+    for (int k = 0; k < 2; k++)
+        if (waits[k]) want[k] = ++blk[192 + 32 * k];
     for (int k = 0; k < 2; k++) {
         if (!waits[k]) continue;
-        const unsigned int want = ++blk[192 + 32 * k];
         const unsigned int* fl = blk + 32 * k;
         while (true) {
             unsigned int cur;
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(fl) : "memory");
-            if ((int)(cur - want) >= 0) break;
-            if (clock64() - t0 > a.max_cycles) {
+            if ((int)(cur - want[k]) >= 0) break;
+            if (a.max_cycles > 0 && clock64() - t0 > a.max_cycles) {
                 blk[96] = 1;
-                return;
+                break;
             }
         }
     }
@@ -97,7 +102,15 @@ int mgk_halo_exchange(cudaStream_t s, const void* const src[4], void* const dst[
     a.wait_below = wait_below;
     a.wait_above = wait_above;
     a.block = flag_block;
-    a.max_cycles = 6000000000LL; /* ~3 s */
+    /* ordinary rank skew (a neighbour busy with host work between two calls) must not become an error: five minutes by
+       default, MG_B200_HALO_TIMEOUT_S seconds if set (0 = no limit) */
+    static long long max_cycles = -2;
+    if (max_cycles == -2) {
+        const char* env = getenv("MG_B200_HALO_TIMEOUT_S");
+        const double sec = env ? atof(env) : 300.0;
+        max_cycles = sec > 0 ? (long long)(sec * 2.0e9) : 0;
+    }
+    a.max_cycles = max_cycles;
     if (!total && !peer_flag[0] && !peer_flag[1] && !wait_below && !wait_above) return 0;
     unsigned long long want = (total / 16 + 256 * 8 - 1) / (256 * 8);  // ~8 x 16 B per thread
     int grid = (int)(want < 1 ? 1 : (want > 296 ? 296 : want));

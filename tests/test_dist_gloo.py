@@ -123,6 +123,7 @@ class Level:
         self.v = np.full((n, n, n), np.nan)
         self.f = np.full((n, n, n), np.nan)
         self.vg_valid = True
+        self.vg_deep = True
         self.v_other = np.full((n, n, n), np.nan)  # second v buffer of the temporally blocked smoother
 
     def mirror_v_ghosts(self):
@@ -183,7 +184,8 @@ def relax_pipe(L, rank, world, nu):
     single sweep colour by colour."""
     n = L.n
     while nu >= 2:
-        exchange(L, L.v, rank, world, 4, 4, 1)
+        if not L.vg_deep:  # InitV / the zeroed coarse v left valid ghosts of full depth
+            exchange(L, L.v, rank, world, 4, 4, 1)
         w = L.v.copy()
         for colour, e in ((0, 3), (1, 2), (0, 1), (1, 0)):  # R1, B1, R2, B2 on the owned planes grown by e
             lo, hi = max(L.a - e, 1), min(L.b + e, n - 1)
@@ -193,9 +195,11 @@ def relax_pipe(L, rank, world, nu):
         L.v_other = L.v
         L.v = out
         L.vg_valid = not L.dist
+        L.vg_deep = False
         nu -= 2
     if nu:
         ensure_v_ghosts(L, rank, world)
+        L.vg_deep = False
         relax(L, rank, world, nu)
 
 
@@ -276,7 +280,7 @@ def vcycle(levels, l, rank, world, engine_schedule=True, smoother="gs"):
         smooth = lambda: relax_pipe(L, rank, world, NU_P)
         engine_colour = 1
     elif smoother == "pipe":
-        smooth = lambda: (ensure_v_ghosts(L, rank, world), relax(L, rank, world, NU_P))
+        smooth = lambda: (ensure_v_ghosts(L, rank, world), setattr(L, "vg_deep", False), relax(L, rank, world, NU_P))
         engine_colour = 1 if engine_schedule else None
     else:
         smooth = lambda: relax(L, rank, world, NU)
@@ -297,7 +301,7 @@ def vcycle(levels, l, rank, world, engine_schedule=True, smoother="gs"):
         if L.dist:
             C.v[max(C.z0, 0):C.z0 + C.nzl] = 0.0                  # coarse v = 0 wherever this rank stores it
             C.mirror_v_ghosts()
-        C.vg_valid = True
+        C.vg_valid = C.vg_deep = True
         if C.dist:
             exchange(C, C.f, rank, world, 4, 4)
         elif L.dist:                                              # all-gather of the equal shares + top plane from the last rank
@@ -314,6 +318,7 @@ def vcycle(levels, l, rank, world, engine_schedule=True, smoother="gs"):
         if smoother == "pipe":
             ensure_v_ghosts(C, rank, world)
         interpolate_add(L.v, C.v, lo, hi, engine_colour)
+        L.vg_deep = False
         if smoother == "pipe" and L.dist and (pipe or not L.vg_valid):
             L.vg_valid = False                                    # lazily: the next pass (or reader) fetches what it needs
         else:

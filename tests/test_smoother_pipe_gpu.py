@@ -116,13 +116,17 @@ def test_fast_arithmetic_within_tolerance(mg, dtype, tol):
     exact = mg.MultiGrid3D(n, UNIT, dtype=dtype, residual_mode=mg.MG_CORRECTED)
     fast = mg.MultiGrid3D(n, UNIT, dtype=dtype, residual_mode=mg.MG_CORRECTED)
     fast.set_arith(mg.MG_ARITH_FAST)
-    for _ in range(3):
+    for cyc in range(3):
         exact.VCycle(0, 2, 2)
         fast.VCycle(0, 2, 2)
         a, b = exact.residual_norm(0)[0], fast.residual_norm(0)[0]
         # the residual amplifies rounding differences of v by 6/h^2 = 4e5: 1e-16 relative in v shows as ~1e-10 .. 1e-9 relative
-        # in ||r||; the float32 history sits on its round-off floor after a few cycles
-        assert abs(a - b) <= (1e-8 if dtype == np.float64 else 2e-2) * max(a, 1.0), (a, b)
+        # in ||r||.  In float32 the residual sits on its round-off floor from the second cycle on (pure rounding noise in both
+        # runs): only the first cycle is compared there.
+        if dtype == np.float64:
+            assert abs(a - b) <= 1e-8 * a, (cyc, a, b)
+        elif cyc == 0:
+            assert abs(a - b) <= 2e-2 * a, (cyc, a, b)
     va, vb = exact.get_v(0), fast.get_v(0)
     assert np.max(np.abs(va.astype(np.float64) - vb)) <= tol * np.max(np.abs(va))
     assert not np.array_equal(va, vb) or dtype == np.float32  # it IS a different rounding sequence
