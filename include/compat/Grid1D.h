@@ -17,8 +17,15 @@ class Grid1D
 		float x_a;
 		float x_b;
 
+#ifdef MG_COMPAT_CUDA_TESI
+		/* CUDA_TESI face (CUDA_TESI/CUDA 1D/Grid1D.h:15-18): the two fields as DEVICE arrays -- the engine's own storage of the
+		   level.  NULL for a Grid1D constructed on its own. */
+		float* d_v;
+		float* d_f;
+#endif
+
 		Grid1D(int sizeX_, float range[]) { setup(sizeX_, range); InitV(); InitF(); }
-		Grid1D(int sizeX_, float range[], mg1d_t* mg, int level) { setup(sizeX_, range); pull(mg, level); }
+		Grid1D(int sizeX_, float range[], mg1d_t* mg, int level) { setup(sizeX_, range); attach(mg, level); pull(mg, level); }
 		~Grid1D() { free(h_v); free(h_f); }
 
 		void InitV() { fetch(MG_FIELD_V); }
@@ -31,8 +38,23 @@ class Grid1D
 		}
 		void push(mg1d_t* mg, int level) const
 		{
+#ifndef MG_COMPAT_CUDA_TESI /* (CUDA_TESI face: the device arrays are the engine's own, the host arrays only feed the dumps) */
 			MG_CHECK(mg1d_set_field(mg, level, MG_FIELD_V, h_v));
 			MG_CHECK(mg1d_set_field(mg, level, MG_FIELD_F, h_f));
+#else
+			(void)mg; (void)level;
+#endif
+		}
+		void attach(mg1d_t* mg, int level)
+		{
+#ifdef MG_COMPAT_CUDA_TESI
+			void *pv = 0, *pf = 0;
+			MG_CHECK(mg1d_level_device_ptr(mg, level, MG_FIELD_V, &pv));
+			MG_CHECK(mg1d_level_device_ptr(mg, level, MG_FIELD_F, &pf));
+			d_v = (float*)pv; d_f = (float*)pf;
+#else
+			(void)mg; (void)level;
+#endif
 		}
 
 		void PrintDiffApproxReal(int diff_fd)
@@ -68,6 +90,9 @@ class Grid1D
 			h_x = (x_b - x_a) / (float)(sizeX - 1);
 			h_v = (float*)malloc((size_t)n * sizeof(float));
 			h_f = (float*)malloc((size_t)n * sizeof(float));
+#ifdef MG_COMPAT_CUDA_TESI
+			d_v = d_f = 0;
+#endif
 		}
 		void fetch(int field)
 		{

@@ -23,8 +23,19 @@ class Grid2D
 		float y_a;
 		float y_b;
 
+#ifdef MG_COMPAT_CUDA_TESI
+		/* CUDA_TESI face (CUDA_TESI/CUDA Lyapunov 2D/Grid2D.h:7,19-22): scalar size and the two fields as pitched DEVICE arrays.
+		   They ARE the engine's storage of the level (its 2D layout is pitched too): nothing is mirrored, a caller may hand
+		   them to the operators or write into them.  NULL for a Grid2D constructed on its own. */
+		int size;
+		float* d_v;
+		float* d_f;
+		size_t d_pitchByte;
+		int d_pitch;
+#endif
+
 		Grid2D(int sizeXY_[], float range[]) { setup(sizeXY_, range); InitV(); InitF(); }
-		Grid2D(int sizeXY_[], float range[], mg2d_t* mg, int level) { setup(sizeXY_, range); pull(mg, level); }
+		Grid2D(int sizeXY_[], float range[], mg2d_t* mg, int level) { setup(sizeXY_, range); attach(mg, level); pull(mg, level); }
 		~Grid2D() { free(h_v); free(h_f); free(sizeXY); }
 
 		void InitV() { fetch(MG_FIELD_V); }
@@ -37,8 +48,24 @@ class Grid2D
 		}
 		void push(mg2d_t* mg, int level) const
 		{
+#ifndef MG_COMPAT_CUDA_TESI /* (CUDA_TESI face: the device arrays are the engine's own, the host arrays only feed the dumps) */
 			MG_CHECK(mg2d_set_field(mg, level, MG_FIELD_V, h_v));
 			MG_CHECK(mg2d_set_field(mg, level, MG_FIELD_F, h_f));
+#else
+			(void)mg; (void)level;
+#endif
+		}
+		void attach(mg2d_t* mg, int level)
+		{
+#ifdef MG_COMPAT_CUDA_TESI
+			void *pv = 0, *pf = 0;
+			MG_CHECK(mg2d_level_device_ptr(mg, level, MG_FIELD_V, &pv, &d_pitch));
+			MG_CHECK(mg2d_level_device_ptr(mg, level, MG_FIELD_F, &pf, &d_pitch));
+			d_v = (float*)pv; d_f = (float*)pf;
+			d_pitchByte = (size_t)d_pitch * sizeof(float);
+#else
+			(void)mg; (void)level;
+#endif
 		}
 
 		void PrintDiffApproxReal(int diff_fd)
@@ -83,6 +110,9 @@ class Grid2D
 			h_y = (y_b - y_a) / (float)(sizeY - 1);
 			h_v = (float*)malloc((size_t)sizeX * sizeY * sizeof(float));
 			h_f = (float*)malloc((size_t)sizeX * sizeY * sizeof(float));
+#ifdef MG_COMPAT_CUDA_TESI
+			size = sizeX; d_v = d_f = 0; d_pitchByte = 0; d_pitch = 0;
+#endif
 		}
 		void fetch(int field)
 		{

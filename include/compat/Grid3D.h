@@ -27,25 +27,53 @@ class Grid3D
 		float z_a;
 		float z_b;
 
+#ifdef MG_COMPAT_CUDA_TESI
+		/* CUDA_TESI face (CUDA_TESI/CUDA Poisson 3D/Grid3D.h:11,26-27): the size triplet and the two fields as DEVICE arrays in
+		   the reference's dense layout.  They are mirrors of the engine's (colour-split) level, refreshed by pull() after every
+		   MultiGrid3D call and read back by push() before it -- a caller may hand them to the operators or modify them. */
+		int* d_sizeXYZ;
+		float* d_v;
+		float* d_f;
+		void PrintDiffApproxReal(int diff_fd) { PrintDiff(diff_fd); } /* C3/Grid3D.h:34 */
+#endif
+
 		/* standalone construction, as in the reference: the fields are initialised by the engine
 		   (InitV / InitF run on the device) */
-		Grid3D(int sizeXYZ_[], float range[]) { setup(sizeXYZ_, range); InitV(); InitF(); }
+		Grid3D(int sizeXYZ_[], float range[]) { setup(sizeXYZ_, range); InitV(); InitF(); upload(); }
 		/* used by MultiGrid3D: wraps level `level` of an existing engine handle */
 		Grid3D(int sizeXYZ_[], float range[], mg3d_t* mg, int level) { setup(sizeXYZ_, range); pull(mg, level); }
-		~Grid3D() { free(h_v); free(h_f); free(sizeXYZ); }
+		~Grid3D()
+		{
+			free(h_v); free(h_f); free(sizeXYZ);
+#ifdef MG_COMPAT_CUDA_TESI
+			cudaFree(d_v); cudaFree(d_f); cudaFree(d_sizeXYZ);
+#endif
+		}
 
 		void InitV() { fetch(MG_FIELD_V); }
 		void InitF() { fetch(MG_FIELD_F); }
 
 		void pull(mg3d_t* mg, int level)
 		{
+#ifdef MG_COMPAT_CUDA_TESI
+			MG_CHECK(mg3d_get_field_device(mg, level, MG_FIELD_V, d_v));
+			MG_CHECK(mg3d_get_field_device(mg, level, MG_FIELD_F, d_f));
+			MG_CUDA_CHECK(cudaMemcpy(h_v, d_v, bytes(), cudaMemcpyDeviceToHost)); /* host mirrors: only the Print* dumps read them */
+			MG_CUDA_CHECK(cudaMemcpy(h_f, d_f, bytes(), cudaMemcpyDeviceToHost));
+#else
 			MG_CHECK(mg3d_get_field(mg, level, MG_FIELD_V, h_v));
 			MG_CHECK(mg3d_get_field(mg, level, MG_FIELD_F, h_f));
+#endif
 		}
 		void push(mg3d_t* mg, int level) const
 		{
+#ifdef MG_COMPAT_CUDA_TESI
+			MG_CHECK(mg3d_set_field_device(mg, level, MG_FIELD_V, d_v));
+			MG_CHECK(mg3d_set_field_device(mg, level, MG_FIELD_F, d_f));
+#else
 			MG_CHECK(mg3d_set_field(mg, level, MG_FIELD_V, h_v));
 			MG_CHECK(mg3d_set_field(mg, level, MG_FIELD_F, h_f));
+#endif
 		}
 
 		void PrintGrid_v(int logfd) { dump(logfd, h_v, "value"); }
@@ -93,6 +121,20 @@ class Grid3D
 			size_t tot = (size_t)sizeX * sizeY * sizeZ;
 			h_v = (float*)malloc(tot * sizeof(float));
 			h_f = (float*)malloc(tot * sizeof(float));
+#ifdef MG_COMPAT_CUDA_TESI
+			MG_CUDA_CHECK(cudaMalloc((void**)&d_v, tot * sizeof(float)));
+			MG_CUDA_CHECK(cudaMalloc((void**)&d_f, tot * sizeof(float)));
+			MG_CUDA_CHECK(cudaMalloc((void**)&d_sizeXYZ, 3 * sizeof(int)));
+			MG_CUDA_CHECK(cudaMemcpy(d_sizeXYZ, sizeXYZ, 3 * sizeof(int), cudaMemcpyHostToDevice));
+#endif
+		}
+		size_t bytes() const { return (size_t)sizeX * sizeY * sizeZ * sizeof(float); }
+		void upload()
+		{
+#ifdef MG_COMPAT_CUDA_TESI
+			MG_CUDA_CHECK(cudaMemcpy(d_v, h_v, bytes(), cudaMemcpyHostToDevice));
+			MG_CUDA_CHECK(cudaMemcpy(d_f, h_f, bytes(), cudaMemcpyHostToDevice));
+#endif
 		}
 		void fetch(int field)
 		{

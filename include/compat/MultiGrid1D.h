@@ -28,8 +28,6 @@ class MultiGrid1D
 			for (int l = 0; l < numGrids; l++) grids1D[l] = new Grid1D(mg1d_level_size(engine, l), range, engine, l);
 		}
 
-		void Restrict(float* fine, int fsize, float* coarse, int csize) { MG_CHECK(mg1d_restrict_host(engine, fine, fsize, coarse, csize)); }
-		void Interpolate(float* fine, int fsize, float* coarse, int csize) { MG_CHECK(mg1d_interpolate_host(engine, fine, fsize, coarse, csize)); }
 		void Relax(Grid1D* curGrid, int ncycles)
 		{
 			int l = level_of(curGrid);
@@ -37,6 +35,23 @@ class MultiGrid1D
 			MG_CHECK(mg1d_relax(engine, l, ncycles));
 			curGrid->pull(engine, l);
 		}
+#ifdef MG_COMPAT_CUDA_TESI
+		/* CUDA_TESI face (C1/MultiGrid1D.h:16-23): the operands are DEVICE arrays */
+		void Restrict(float* fine, int fsize, float* coarse, int csize) { MG_CHECK(mg1d_restrict_device(engine, fine, fsize, coarse, csize)); }
+		void Interpolate(float* fine, int fsize, float* coarse, int csize) { MG_CHECK(mg1d_interpolate_device(engine, fine, fsize, coarse, csize)); }
+		void ApplyCorrection(float* fine, int fineSize, float* error, int errorSize) { MG_CHECK(mg1d_apply_correction_device(engine, fine, fineSize, error, errorSize)); }
+		void Set(float* d_v, int sizeX, float value, bool modifyBoundaries) { MG_CHECK(mg1d_set_device(engine, d_v, sizeX, value, modifyBoundaries)); }
+		float* CalculateResidual(Grid1D* fine) // caller-owned DEVICE array (C1/MultiGrid1D.cu:86-104)
+		{
+			int l = level_of(fine);
+			float* d_r = 0;
+			MG_CUDA_CHECK(cudaMalloc((void**)&d_r, (size_t)fine->sizeX * sizeof(float)));
+			MG_CHECK(mg1d_residual_device(engine, l, d_r));
+			return d_r;
+		}
+#else
+		void Restrict(float* fine, int fsize, float* coarse, int csize) { MG_CHECK(mg1d_restrict_host(engine, fine, fsize, coarse, csize)); }
+		void Interpolate(float* fine, int fsize, float* coarse, int csize) { MG_CHECK(mg1d_interpolate_host(engine, fine, fsize, coarse, csize)); }
 		float* CalculateResidual(Grid1D* fine)
 		{
 			int l = level_of(fine);
@@ -46,6 +61,7 @@ class MultiGrid1D
 			return r;
 		}
 		void ApplyCorrection(float* fine, int fineSize, float* error, int errorSize) { MG_CHECK(mg1d_apply_correction_host(engine, fine, fineSize, error, errorSize)); }
+#endif
 		void setToValue(float* grid, int sizeX, float value, bool modifyBoundaries) { MG_CHECK(mg1d_set_to_value_host(engine, grid, sizeX, value, modifyBoundaries)); }
 
 		void VCycle(int gridID, int v1, int v2)

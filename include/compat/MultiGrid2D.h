@@ -15,6 +15,10 @@ class MultiGrid2D
 		int sizeA;
 		int alfa;
 		mg2d_t* engine;
+#ifdef MG_COMPAT_CUDA_TESI
+		float* d_matrixA; /* CUDA_TESI face (C2/MultiGrid2D.h:12-13): A on the device */
+		int sizeX_A;
+#endif
 
 		MultiGrid2D(int finestGridSizeXY[], float range[], float* _A, int A_size, int alfa_)
 		{
@@ -33,6 +37,9 @@ class MultiGrid2D
 			for (int i = 0; i < numGrids; i++) delete grids2D[i];
 			free(grids2D);
 			free(matrixA);
+#ifdef MG_COMPAT_CUDA_TESI
+			cudaFree(d_matrixA);
+#endif
 			mg2d_destroy(engine);
 		}
 		void InitA(float* _A, int A_size, int alfa_)
@@ -41,6 +48,11 @@ class MultiGrid2D
 			sizeA = A_size;
 			matrixA = (float*)malloc((size_t)A_size * A_size * sizeof(float)); // the reference allocates A_size floats and overflows (App. B7)
 			for (int i = 0; i < A_size * A_size; i++) matrixA[i] = _A[i];
+#ifdef MG_COMPAT_CUDA_TESI
+			sizeX_A = A_size;
+			MG_CUDA_CHECK(cudaMalloc((void**)&d_matrixA, (size_t)A_size * A_size * sizeof(float)));
+			MG_CUDA_CHECK(cudaMemcpy(d_matrixA, matrixA, (size_t)A_size * A_size * sizeof(float), cudaMemcpyHostToDevice));
+#endif
 		}
 		void InitGrids(int finestGridSizeXY[], float range[])
 		{
@@ -65,6 +77,22 @@ class MultiGrid2D
 			MG_CHECK(mg2d_relax(engine, l, ncycles));
 			curGrid->pull(engine, l);
 		}
+#ifdef MG_COMPAT_CUDA_TESI
+		/* CUDA_TESI face (C2/MultiGrid2D.h:20-25): pitched device arrays as (pointer, size, pitch in elements) */
+		void Restrict(float* fine, int fsize, int f_pitch, float* coarse, int csize, int c_pitch) { MG_CHECK(mg2d_restrict_device(engine, fine, fsize, f_pitch, coarse, csize, c_pitch)); }
+		void Interpolate(float* fine, int fsize, int f_pitch, float* coarse, int csize, int c_pitch) { MG_CHECK(mg2d_interpolate_device(engine, fine, fsize, f_pitch, coarse, csize, c_pitch)); }
+		void ApplyCorrection(float* fine, int fineSize, int f_pitch, float* error, int errorSize, int e_pitch) { MG_CHECK(mg2d_apply_correction_device(engine, fine, fineSize, f_pitch, error, errorSize, e_pitch)); }
+		void Set(float* v, int size, int pitch, float value, bool modifyBorder) { MG_CHECK(mg2d_set_device(engine, v, size, pitch, value, modifyBorder)); }
+		float* CalculateResidual(Grid2D* fine) // caller-owned pitched DEVICE array with the level's pitch (C2/MultiGrid2D.cu:105-127)
+		{
+			int l = level_of(fine);
+			float* d_r = 0;
+			MG_CUDA_CHECK(cudaMalloc((void**)&d_r, (size_t)fine->d_pitch * fine->size * sizeof(float)));
+			MG_CUDA_CHECK(cudaMemset(d_r, 0, (size_t)fine->d_pitch * fine->size * sizeof(float)));
+			MG_CHECK(mg2d_residual_device(engine, l, d_r));
+			return d_r;
+		}
+#else
 		float* CalculateResidual(Grid2D* fine)
 		{
 			int l = level_of(fine);
@@ -73,6 +101,7 @@ class MultiGrid2D
 			MG_CHECK(mg2d_residual(engine, l, r));
 			return r;
 		}
+#endif
 		void ApplyCorrection(float* fine, int fsizeXY[], float* error, int esizeXY[]) { MG_CHECK(mg2d_apply_correction_host(engine, fine, fsizeXY, error, esizeXY)); }
 		void setToValue(float* grid, int sizeXY[], float value, bool modifyBoundaries) { MG_CHECK(mg2d_set_to_value_host(engine, grid, sizeXY, value, modifyBoundaries)); }
 

@@ -35,8 +35,6 @@ class MultiGrid3D
 			}
 		}
 
-		void Restrict(float* fine, int fsizeXYZ[], float* coarse, int csizeXYZ[]) { MG_CHECK(mg3d_restrict_host(engine, fine, fsizeXYZ, coarse, csizeXYZ)); }
-		void Interpolate(float* fine, int fsizeXYZ[], float* coarse, int csizeXYZ[]) { MG_CHECK(mg3d_interpolate_host(engine, fine, fsizeXYZ, coarse, csizeXYZ)); }
 		void Relax(Grid3D* curGrid, int ncycles)
 		{
 			int l = level_of(curGrid);
@@ -44,6 +42,58 @@ class MultiGrid3D
 			MG_CHECK(mg3d_relax(engine, l, ncycles));
 			curGrid->pull(engine, l);
 		}
+#ifdef MG_COMPAT_CUDA_TESI
+		/* CUDA_TESI face (C3/MultiGrid3D.h:16-24): the arrays AND the size triplets are device pointers; like the reference's own
+		   wrappers (C3/MultiGrid3D.cu:68-72) the triplets are copied back before the launch */
+		void Restrict(float* d_fine, int d_fsizeXYZ[], float* d_coarse, int d_csizeXYZ[])
+		{
+			int fs[3], cs[3];
+			dsize(d_fsizeXYZ, fs); dsize(d_csizeXYZ, cs);
+			MG_CHECK(mg3d_restrict_device(engine, d_fine, fs, d_coarse, cs));
+		}
+		void Interpolate(float* d_fine, int d_fsizeXYZ[], float* d_coarse, int d_csizeXYZ[])
+		{
+			int fs[3], cs[3];
+			dsize(d_fsizeXYZ, fs); dsize(d_csizeXYZ, cs);
+			MG_CHECK(mg3d_interpolate_device(engine, d_fine, fs, d_coarse, cs));
+		}
+		void ApplyCorrection(float* d_fine, int d_fsizeXYZ[], float* d_error, int d_esizeXYZ[])
+		{
+			int fs[3], es[3];
+			dsize(d_fsizeXYZ, fs); dsize(d_esizeXYZ, es);
+			MG_CHECK(mg3d_apply_correction_device(engine, d_fine, fs, d_error, es));
+		}
+		void Set(float* d_v, int d_sizeXYZ[], float value, bool modifyBorder)
+		{
+			int s[3];
+			dsize(d_sizeXYZ, s);
+			MG_CHECK(mg3d_set_device(engine, d_v, s, value, modifyBorder));
+		}
+		/* the index-map probe of the twin (C3/MultiGrid3D.cu:101-118,702-720): v(x,y,z) = x + y + z */
+		void SetTESTTEST(float* d_v, int d_sizeXYZ[], float, bool)
+		{
+			int s[3];
+			dsize(d_sizeXYZ, s);
+			size_t tot = (size_t)s[0] * s[1] * s[2];
+			float* h = (float*)malloc(tot * sizeof(float));
+			for (int z = 0; z < s[2]; z++)
+				for (int y = 0; y < s[1]; y++)
+					for (int x = 0; x < s[0]; x++) h[x + (size_t)y * s[0] + (size_t)z * s[0] * s[1]] = (float)(x + y + z);
+			MG_CUDA_CHECK(cudaMemcpy(d_v, h, tot * sizeof(float), cudaMemcpyHostToDevice));
+			free(h);
+		}
+		float* CalculateResidual(Grid3D* curGrid) // caller owns the returned DEVICE buffer, as in the twin (C3/MultiGrid3D.cu:220-222)
+		{
+			int l = level_of(curGrid);
+			curGrid->push(engine, l);
+			float* d_r = 0;
+			MG_CUDA_CHECK(cudaMalloc((void**)&d_r, (size_t)curGrid->sizeX * curGrid->sizeY * curGrid->sizeZ * sizeof(float)));
+			MG_CHECK(mg3d_residual_device(engine, l, d_r));
+			return d_r;
+		}
+#else
+		void Restrict(float* fine, int fsizeXYZ[], float* coarse, int csizeXYZ[]) { MG_CHECK(mg3d_restrict_host(engine, fine, fsizeXYZ, coarse, csizeXYZ)); }
+		void Interpolate(float* fine, int fsizeXYZ[], float* coarse, int csizeXYZ[]) { MG_CHECK(mg3d_interpolate_host(engine, fine, fsizeXYZ, coarse, csizeXYZ)); }
 		void setToValue(float* grid, int sizeXYZ[], float value, bool modifyBoundaries) { MG_CHECK(mg3d_set_to_value_host(engine, grid, sizeXYZ, value, modifyBoundaries)); }
 		float* CalculateResidual(Grid3D* fine) // caller owns the returned buffer, as in the reference
 		{
@@ -54,6 +104,7 @@ class MultiGrid3D
 			return r;
 		}
 		void ApplyCorrection(float* fine, int fsizeXYZ[], float* error, int esizeXYZ[]) { MG_CHECK(mg3d_apply_correction_host(engine, fine, fsizeXYZ, error, esizeXYZ)); }
+#endif
 
 		void VCycle(int gridID, int v1, int v2)
 		{
@@ -74,6 +125,9 @@ class MultiGrid3D
 		void PrintDiff() { grids3D[0]->PrintDiff(mg_compat_open_log("log/diff.txt")); }
 
 	private:
+#ifdef MG_COMPAT_CUDA_TESI
+		static void dsize(const int* d_size, int out[3]) { MG_CUDA_CHECK(cudaMemcpy(out, d_size, 3 * sizeof(int), cudaMemcpyDeviceToHost)); }
+#endif
 		int level_of(Grid3D* g)
 		{
 			for (int l = 0; l < numGrids; l++) if (grids3D[l] == g) return l;

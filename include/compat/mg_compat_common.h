@@ -21,6 +21,22 @@
 
 #include "mg_b200.h"
 
+/* -DMG_COMPAT_CUDA_TESI selects the faces of the reference's GPU twin (CUDA_TESI/...): grids carry DEVICE arrays
+   (d_v, d_f, 3D: d_sizeXYZ; 2D: d_pitch) and the operators take device pointers -- the methods have the same C++
+   signatures as the host ones, so the interpretation is a compile-time choice, exactly as it is between the reference's
+   two source trees.  Needs the CUDA runtime headers and -lcudart. */
+#ifdef MG_COMPAT_CUDA_TESI
+#include <cuda_runtime_api.h>
+#define MG_CUDA_CHECK(call)                                                                     \
+    do {                                                                                        \
+        cudaError_t mg_e_ = (call);                                                             \
+        if (mg_e_ != cudaSuccess) {                                                             \
+            fprintf(stderr, "%s failed: %s\n", #call, cudaGetErrorString(mg_e_));               \
+            abort();                                                                            \
+        }                                                                                       \
+    } while (0)
+#endif
+
 #define MG_CHECK(call)                                                                          \
     do {                                                                                        \
         int mg_st_ = (call);                                                                    \

@@ -146,6 +146,17 @@ int mg3d_restrict_host(mg3d_t* mg, const void* fine, const int fsize_xyz[3], voi
 int mg3d_interpolate_host(mg3d_t* mg, void* fine, const int fsize_xyz[3], const void* coarse, const int csize_xyz[3]);
 int mg3d_apply_correction_host(mg3d_t* mg, void* fine, const int fsize_xyz[3], const void* error, const int esize_xyz[3]);
 int mg3d_set_to_value_host(mg3d_t* mg, void* grid, const int size_xyz[3], double value, int modify_boundaries);
+/* The CUDA_TESI faces of the same operators: operands are DEVICE arrays in the reference's dense layout
+   (CUDA_TESI/CUDA Poisson 3D/MultiGrid3D.h:16-24: d_fine / d_coarse / d_v; Grid3D.h:26-27: d_v, d_f).  The reference
+   passes the size triplets as device arrays too (Grid3D.h:11 d_sizeXYZ) and copies them back in every wrapper
+   (MultiGrid3D.cu:68-72); here they are host ints -- the shim of include/compat/ does that copy. */
+int mg3d_set_field_device(mg3d_t* mg, int level, int field, const void* dev_dense); /* grids3D[level]->d_v|d_f -> engine */
+int mg3d_get_field_device(mg3d_t* mg, int level, int field, void* dev_dense);       /* engine -> grids3D[level]->d_v|d_f */
+int mg3d_residual_device(mg3d_t* mg, int level, void* dev_dense_out);               /* CalculateResidual -> caller-owned device array */
+int mg3d_restrict_device(mg3d_t* mg, const void* d_fine, const int fsize_xyz[3], void* d_coarse, const int csize_xyz[3]);
+int mg3d_interpolate_device(mg3d_t* mg, void* d_fine, const int fsize_xyz[3], const void* d_coarse, const int csize_xyz[3]);
+int mg3d_apply_correction_device(mg3d_t* mg, void* d_fine, const int fsize_xyz[3], const void* d_error, const int esize_xyz[3]);
+int mg3d_set_device(mg3d_t* mg, void* d_v, const int size_xyz[3], double value, int modify_border); /* Set(d_v, d_sizeXYZ, value, modifyBorder) */
 /* end-to-end: upload finest v,f -> `cycles` x VCycle(0,v1,v2) -> download finest v */
 int mg3d_vcycle_host(mg3d_t* mg, void* v_host, const void* f_host, int v1, int v2, int cycles);
 
@@ -182,6 +193,15 @@ int mg2d_interpolate_host(mg2d_t* mg, void* fine, const int fsize_xy[2], const v
 int mg2d_apply_correction_host(mg2d_t* mg, void* fine, const int fsize_xy[2], const void* error, const int esize_xy[2]);
 int mg2d_set_to_value_host(mg2d_t* mg, void* grid, const int size_xy[2], double value, int modify_boundaries);
 int mg2d_vcycle_host(mg2d_t* mg, void* v_host, const void* f_host, int v1, int v2, int cycles);
+/* the CUDA_TESI faces (CUDA_TESI/CUDA Lyapunov 2D/MultiGrid2D.h:20-25, Grid2D.h:19-22): pitched DEVICE arrays given as
+   (pointer, size, pitch in elements); the kernels run on the caller's arrays in place.  mg2d_level_device_ptr hands out
+   a level's own field (what the twin's Grid2D::d_v / d_f / d_pitch are). */
+int mg2d_level_device_ptr(mg2d_t* mg, int level, int field, void** ptr, int* pitch_elems);
+int mg2d_restrict_device(mg2d_t* mg, const void* fine, int fsize, int f_pitch, void* coarse, int csize, int c_pitch);
+int mg2d_interpolate_device(mg2d_t* mg, void* fine, int fsize, int f_pitch, const void* coarse, int csize, int c_pitch);
+int mg2d_apply_correction_device(mg2d_t* mg, void* fine, int fsize, int f_pitch, const void* error, int esize, int e_pitch);
+int mg2d_set_device(mg2d_t* mg, void* v, int size, int pitch, double value, int modify_border);
+int mg2d_residual_device(mg2d_t* mg, int level, void* dev_out); /* pitched like the level itself */
 
 /* ------------------------------------------------------------------ 1D equation ------------ */
 /* MultiGrid1D::MultiGrid1D + InitGrids (N1/MultiGrid1D.cpp:5-31) */
@@ -213,6 +233,13 @@ int mg1d_interpolate_host(mg1d_t* mg, void* fine, int fsize, const void* coarse,
 int mg1d_apply_correction_host(mg1d_t* mg, void* fine, int fsize, const void* error, int esize);
 int mg1d_set_to_value_host(mg1d_t* mg, void* grid, int size, double value, int modify_boundaries);
 int mg1d_vcycle_host(mg1d_t* mg, void* v_host, const void* f_host, int v1, int v2, int cycles);
+/* the CUDA_TESI faces (CUDA_TESI/CUDA 1D/MultiGrid1D.h:16-23, Grid1D.h:15-18): DEVICE arrays */
+int mg1d_level_device_ptr(mg1d_t* mg, int level, int field, void** ptr);
+int mg1d_restrict_device(mg1d_t* mg, const void* fine, int fsize, void* coarse, int csize);
+int mg1d_interpolate_device(mg1d_t* mg, void* fine, int fsize, const void* coarse, int csize);
+int mg1d_apply_correction_device(mg1d_t* mg, void* fine, int fsize, const void* error, int esize);
+int mg1d_set_device(mg1d_t* mg, void* d_v, int size, double value, int modify_boundaries);
+int mg1d_residual_device(mg1d_t* mg, int level, void* dev_out);
 
 #ifdef __cplusplus
 }

@@ -398,6 +398,68 @@ int mg1d_set_to_value_host(mg1d_t* mg, void* grid, int n, double value, int modi
     return st;
 }
 
+/* ---- the CUDA_TESI faces (C1/MultiGrid1D.h:16-23, C1/Grid1D.h:15-18): operators on DEVICE arrays.  The engine's 1D fields
+        are dense device arrays already, so a level's d_v / d_f are the engine's own storage. ------------------------- */
+int mg1d_level_device_ptr(mg1d_t* mg, int level, int field, void** ptr)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (!ptr || (field != MG_FIELD_V && field != MG_FIELD_F)) return mg_fail(MG_ERR_ARG, "bad field/pointer");
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
+    const long long off = field == MG_FIELD_V ? mg->H.off_v[level] : mg->H.off_f[level];
+    *ptr = (char*)mg->arena + (size_t)off * mg_esize(mg->dtype);
+    return MG_OK;
+}
+
+static int dev1_done(mg1d_t* mg, int k)
+{
+    if (k < 0) return mg_fail(MG_ERR_CUDA, "operator launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    mg->launches += k;
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
+    return MG_OK;
+}
+
+int mg1d_restrict_device(mg1d_t* mg, const void* fine, int fn, void* coarse, int cn)
+{
+    if (!mg || !fine || !coarse) return mg_fail(MG_ERR_ARG, "null argument");
+    if (fn < 3 || cn != (fn - 1) / 2 + 1) return mg_fail(MG_ERR_ARG, "csize != (fsize-1)/2+1");
+    MG_CUDA(cudaDeviceSynchronize());
+    return dev1_done(mg, mgk1d_restrict(mg->stream, mg->dtype, fine, fn, coarse, cn));
+}
+
+int mg1d_interpolate_device(mg1d_t* mg, void* fine, int fn, const void* coarse, int cn)
+{
+    if (!mg || !fine || !coarse) return mg_fail(MG_ERR_ARG, "null argument");
+    if (fn < 3 || cn != (fn - 1) / 2 + 1) return mg_fail(MG_ERR_ARG, "csize != (fsize-1)/2+1");
+    MG_CUDA(cudaDeviceSynchronize());
+    return dev1_done(mg, mgk1d_interpolate(mg->stream, mg->dtype, fine, fn, coarse, cn, 0));
+}
+
+int mg1d_apply_correction_device(mg1d_t* mg, void* fine, int fn, const void* error, int en)
+{
+    if (!mg || !fine || !error) return mg_fail(MG_ERR_ARG, "null argument");
+    if (fn != en || fn < 1) return mg_fail(MG_ERR_ARG, "fsize != esize");
+    MG_CUDA(cudaDeviceSynchronize());
+    return dev1_done(mg, mgk1d_apply_correction(mg->stream, mg->dtype, fine, error, fn));
+}
+
+int mg1d_set_device(mg1d_t* mg, void* d_v, int n, double value, int modify_boundaries)
+{
+    if (!mg || !d_v || n < 1) return mg_fail(MG_ERR_ARG, "bad argument");
+    MG_CUDA(cudaDeviceSynchronize());
+    return dev1_done(mg, mgk1d_set(mg->stream, mg->dtype, d_v, n, value, modify_boundaries));
+}
+
+/* CalculateResidual(grid) into a caller-owned DEVICE array (C1/MultiGrid1D.cu:86-104) */
+int mg1d_residual_device(mg1d_t* mg, int level, void* dev_out)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (!dev_out) return mg_fail(MG_ERR_ARG, "null output");
+    MG_CUDA(cudaDeviceSynchronize());
+    return dev1_done(mg, mgk1d_residual(mg->stream, mg->dtype, mg->arena, mg->H, level, mg->mode == MG_CORRECTED, dev_out));
+}
+
 int mg1d_vcycle_host(mg1d_t* mg, void* v_host, const void* f_host, int v1, int v2, int cycles)
 {
     if (!mg || !v_host || !f_host) return mg_fail(MG_ERR_ARG, "null argument");

@@ -539,6 +539,82 @@ int mg2d_set_to_value_host(mg2d_t* mg, void* grid, const int s[2], double value,
     return st;
 }
 
+/* ---- the CUDA_TESI faces (C2/MultiGrid2D.h:20-25, C2/Grid2D.h:19-22): operators on pitched DEVICE arrays given as
+        (pointer, size, pitch in elements).  The engine's own 2D layout is pitched as well, so the kernels run on the
+        caller's arrays in place, and a level's fields can be handed out without a copy. ---------------------------------- */
+int mg2d_level_device_ptr(mg2d_t* mg, int level, int field, void** ptr, int* pitch_elems)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (!ptr || (field != MG_FIELD_V && field != MG_FIELD_F)) return mg_fail(MG_ERR_ARG, "bad field/pointer");
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
+    *ptr = field == MG_FIELD_V ? mg->lv[level].v : mg->lv[level].f;
+    if (pitch_elems) *pitch_elems = mg->lv[level].g.pitch;
+    return MG_OK;
+}
+
+static int dev2_args(mg2d_t* mg, const void* a, int an, int ap, const void* b, int bn, int bp, int need_b)
+{
+    if (!mg || !a || (need_b && !b)) return mg_fail(MG_ERR_ARG, "null argument");
+    if (an < 3 || ap < an || (need_b && (bn < 3 || bp < bn))) return mg_fail(MG_ERR_ARG, "size >= 3 and pitch >= size required");
+    MG_CUDA(cudaDeviceSynchronize()); /* the caller's arrays may have been produced on any stream */
+    return MG_OK;
+}
+
+static int dev2_done(mg2d_t* mg, int k)
+{
+    if (k < 0) return mg_fail(MG_ERR_CUDA, "operator launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    mg->launches += k;
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
+    return MG_OK;
+}
+
+int mg2d_restrict_device(mg2d_t* mg, const void* fine, int fsize, int f_pitch, void* coarse, int csize, int c_pitch)
+{
+    int st = dev2_args(mg, fine, fsize, f_pitch, coarse, csize, c_pitch, 1);
+    if (st) return st;
+    if (csize != (fsize - 1) / 2 + 1) return mg_fail(MG_ERR_ARG, "csize != (fsize-1)/2+1");
+    mg_geom2d gf = {fsize, f_pitch}, gc = {csize, c_pitch};
+    return dev2_done(mg, mgk2d_restrict(mg->stream, mg->dtype, fine, gf, coarse, gc));
+}
+
+int mg2d_interpolate_device(mg2d_t* mg, void* fine, int fsize, int f_pitch, const void* coarse, int csize, int c_pitch)
+{
+    int st = dev2_args(mg, fine, fsize, f_pitch, coarse, csize, c_pitch, 1);
+    if (st) return st;
+    if (csize != (fsize - 1) / 2 + 1) return mg_fail(MG_ERR_ARG, "csize != (fsize-1)/2+1");
+    mg_geom2d gf = {fsize, f_pitch}, gc = {csize, c_pitch};
+    return dev2_done(mg, mgk2d_interpolate(mg->stream, mg->dtype, fine, gf, coarse, gc, 0));
+}
+
+int mg2d_apply_correction_device(mg2d_t* mg, void* fine, int fsize, int f_pitch, const void* error, int esize, int e_pitch)
+{
+    int st = dev2_args(mg, fine, fsize, f_pitch, error, esize, e_pitch, 1);
+    if (st) return st;
+    if (fsize != esize || f_pitch != e_pitch) return mg_fail(MG_ERR_ARG, "fine and error must have the same size and pitch");
+    mg_geom2d g = {fsize, f_pitch};
+    return dev2_done(mg, mgk2d_apply_correction(mg->stream, mg->dtype, fine, error, g));
+}
+
+int mg2d_set_device(mg2d_t* mg, void* v, int size, int pitch, double value, int modify_border)
+{
+    int st = dev2_args(mg, v, size, pitch, NULL, 0, 0, 0);
+    if (st) return st;
+    mg_geom2d g = {size, pitch};
+    return dev2_done(mg, mgk2d_set(mg->stream, mg->dtype, v, g, value, modify_border));
+}
+
+/* CalculateResidual(grid) into a caller-owned pitched DEVICE array with the level's own pitch (C2/MultiGrid2D.cu:105-127) */
+int mg2d_residual_device(mg2d_t* mg, int level, void* dev_out)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (!dev_out) return mg_fail(MG_ERR_ARG, "null output");
+    mg_level2d* L = &mg->lv[level];
+    MG_CUDA(cudaDeviceSynchronize());
+    return dev2_done(mg, mgk2d_residual(mg->stream, mg->dtype, L->v, L->f, dev_out, L->g, L->c));
+}
+
 int mg2d_vcycle_host(mg2d_t* mg, void* v_host, const void* f_host, int v1, int v2, int cycles)
 {
     if (!mg || !v_host || !f_host) return mg_fail(MG_ERR_ARG, "null argument");

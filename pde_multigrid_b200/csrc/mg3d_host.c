@@ -1550,6 +1550,115 @@ int mg3d_set_to_value_host(mg3d_t* mg, void* grid, const int s[3], double value,
     return st;
 }
 
+/* ---- the CUDA_TESI faces: the same operators on DEVICE arrays in the reference's dense layout (C3/MultiGrid3D.h:16-24,
+        C3/Grid3D.h:11,26-27: d_v / d_f / device-pointer operands).  No host trip: one repack kernel each way. ---------- */
+
+static int dense_in(mg3d_t* mg, void* dev, const mg_geom3d* g, const void* dense_dev, int zl_lo, int zl_hi)
+{
+    MG_LAUNCH(mg->launches, mgk3d_repack(mg->stream, mg->dtype, dev, *g, (void*)dense_dev, 1, zl_lo, zl_hi));
+    return MG_OK;
+}
+
+static int dense_out(mg3d_t* mg, void* dense_dev, const void* dev, const mg_geom3d* g, int zl_lo, int zl_hi)
+{
+    MG_LAUNCH(mg->launches, mgk3d_repack(mg->stream, mg->dtype, (void*)dev, *g, dense_dev, 0, zl_lo, zl_hi));
+    MG_CUDA(cudaStreamSynchronize(mg->stream)); /* the caller's next access may be on any stream (the reference uses the default one) */
+    return halo_error_check(mg);
+}
+
+int mg3d_set_field_device(mg3d_t* mg, int level, int field, const void* dev_dense)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (!dev_dense || (field != MG_FIELD_V && field != MG_FIELD_F)) return mg_fail(MG_ERR_ARG, "bad field/pointer");
+    mg_level3d* L = &mg->lv[level];
+    MG_CUDA(cudaDeviceSynchronize()); /* whatever produced the caller's array (any stream) is complete */
+    st = dense_in(mg, field_ptr(L, field), &L->g, dev_dense, L->own_lo, L->own_hi);
+    if (!st) st = exchange(mg, level, field_ptr(L, field), 3, MG_GHOST_LO, MG_GHOST_HI);
+    if (st) return st;
+    if (field == MG_FIELD_V) {
+        L->vg_valid = L->vg_deep = 1;
+        if ((st = mirror_v_ghosts(mg, level))) return st;
+    }
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
+    return MG_OK;
+}
+
+int mg3d_get_field_device(mg3d_t* mg, int level, int field, void* dev_dense)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (!dev_dense || (field != MG_FIELD_V && field != MG_FIELD_F)) return mg_fail(MG_ERR_ARG, "bad field/pointer");
+    mg_level3d* L = &mg->lv[level];
+    return dense_out(mg, dev_dense, field_ptr(L, field), &L->g, L->own_lo, L->own_hi);
+}
+
+/* CalculateResidual(grid) -> caller-owned DEVICE array (C3/MultiGrid3D.cu:202-233) */
+int mg3d_residual_device(mg3d_t* mg, int level, void* dev_dense_out)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (!dev_dense_out) return mg_fail(MG_ERR_ARG, "null output");
+    mg_level3d* L = &mg->lv[level];
+    if ((st = ensure_v_ghosts(mg, level))) return st;
+    void* r = NULL;
+    MG_CUDA(cudaMalloc(&r, field_bytes(L, mg->dtype)));
+    int k = mgk3d_residual(mg->stream, mg->dtype, L->v, L->f, r, L->g, L->c, mg->mode == MG_CORRECTED, L->own_lo, L->own_hi);
+    if (k < 0) { cudaFree(r); return mg_fail(MG_ERR_CUDA, "residual launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    mg->launches += k;
+    st = dense_out(mg, dev_dense_out, r, &L->g, L->own_lo, L->own_hi);
+    cudaFree(r);
+    return st;
+}
+
+/* which: 0 Restrict(fine -> coarse), 1 Interpolate(coarse -> fine interior), 2 ApplyCorrection(fine += b), 3 Set(a = value) */
+static int device_op(mg3d_t* mg, int which, void* a, const int as[3], void* b, const int bs[3], double value, int modify_boundaries)
+{
+    int an = 0, bn = 0, st;
+    if (!mg || !a || (which != 3 && !b)) return mg_fail(MG_ERR_ARG, "null argument");
+    if ((st = cubic(as, &an)) || (which != 3 && (st = cubic(bs, &bn)))) return st;
+    if ((which == 0 || which == 1) && bn != (an - 1) / 2 + 1) return mg_fail(MG_ERR_ARG, "csize != (fsize-1)/2+1");
+    if (which == 2 && an != bn) return mg_fail(MG_ERR_ARG, "fsize != esize");
+    mg_geom3d ga, gb;
+    temp_geom(an, mg->dtype, &ga);
+    if (which != 3) temp_geom(bn, mg->dtype, &gb);
+    void *da = NULL, *db = NULL;
+    if ((st = temp_alloc(mg, &ga, &da))) return st;
+    if (which != 3 && (st = temp_alloc(mg, &gb, &db))) { cudaFree(da); return st; }
+    MG_CUDA(cudaDeviceSynchronize());
+    st = dense_in(mg, da, &ga, a, 0, an);
+    if (!st && which != 3 && which != 0) st = dense_in(mg, db, &gb, b, 0, bn);
+    int k = 0;
+    if (!st) {
+        if (which == 0) k = mgk3d_restrict(mg->stream, mg->dtype, da, ga, db, gb, 0, bn);
+        else if (which == 1) k = mgk3d_interpolate(mg->stream, mg->dtype, da, ga, db, gb, 0, 3, 1, an - 1);
+        else if (which == 2) k = mgk3d_apply_correction(mg->stream, mg->dtype, da, db, ga, 1, an - 1);
+        else k = mgk3d_set(mg->stream, mg->dtype, da, ga, value, modify_boundaries, 0, an);
+        if (k < 0) st = mg_fail(MG_ERR_CUDA, "operator launch failed"); else mg->launches += k;
+    }
+    if (!st) st = which == 0 ? dense_out(mg, b, db, &gb, 0, bn) : dense_out(mg, a, da, &ga, 0, an);
+    cudaFree(da);
+    if (db) cudaFree(db);
+    return st;
+}
+
+int mg3d_restrict_device(mg3d_t* mg, const void* d_fine, const int fs[3], void* d_coarse, const int cs[3])
+{
+    return device_op(mg, 0, (void*)d_fine, fs, d_coarse, cs, 0.0, 0);
+}
+int mg3d_interpolate_device(mg3d_t* mg, void* d_fine, const int fs[3], const void* d_coarse, const int cs[3])
+{
+    return device_op(mg, 1, d_fine, fs, (void*)d_coarse, cs, 0.0, 0);
+}
+int mg3d_apply_correction_device(mg3d_t* mg, void* d_fine, const int fs[3], const void* d_error, const int es[3])
+{
+    return device_op(mg, 2, d_fine, fs, (void*)d_error, es, 0.0, 0);
+}
+int mg3d_set_device(mg3d_t* mg, void* d_v, const int size_xyz[3], double value, int modify_border)
+{
+    return device_op(mg, 3, d_v, size_xyz, NULL, NULL, value, modify_border);
+}
+
 /* end to end with HOST buffers: v,f hold the planes this rank owns (the whole grid on one GPU) */
 int mg3d_vcycle_host(mg3d_t* mg, void* v_host, const void* f_host, int v1, int v2, int cycles)
 {
