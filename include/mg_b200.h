@@ -221,6 +221,8 @@ int mg1d_init_problem(mg1d_t* mg); /* Grid1D::InitV/InitF, N1/Grid1D.cpp:30-43 *
 int mg1d_relax(mg1d_t* mg, int level, int ncycles);
 int mg1d_residual(mg1d_t* mg, int level, void* host_out);
 int mg1d_residual_norm(mg1d_t* mg, int level, double* l2, double* linf);
+/* Grid1D::PrintDiffApproxReal (N1/Grid1D.cpp:46-60) as a device reduction: mean and max of |approxsol - realsol| */
+int mg1d_abs_error(mg1d_t* mg, int level, double* mean_abs, double* max_abs);
 int mg1d_restrict(mg1d_t* mg, int fine_level, int field);
 int mg1d_residual_restrict(mg1d_t* mg, int fine_level);
 int mg1d_interpolate(mg1d_t* mg, int fine_level);

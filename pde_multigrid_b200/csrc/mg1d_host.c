@@ -229,6 +229,46 @@ int mg1d_residual(mg1d_t* mg, int level, void* host_out)
     return MG_OK;
 }
 
+/* Grid1D::PrintDiffApproxReal (N1/Grid1D.cpp:46-60) as a reduction: mean and max over all points of |approxsol - realsol|,
+   realsol = (exp(xj) + xj - 3)/(1 + exp(-xj)) with the host libm in the grid's precision (float: expf, like the reference) */
+int mg1d_abs_error(mg1d_t* mg, int level, double* mean_abs, double* max_abs)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    const int n = mg->H.n[level];
+    const size_t es = mg_esize(mg->dtype);
+    void* host = malloc((size_t)n * es);
+    if (!host) return mg_fail(MG_ERR_NOMEM, "host allocation failed");
+    if (mg->dtype == MG_F32) {
+        float x_a = (float)mg->range[0], h_x = ((float)mg->range[1] - x_a) / (float)(n - 1);
+        for (int j = 0; j < n; j++) {
+            float xj = x_a + j * h_x;
+            ((float*)host)[j] = (expf(xj) + xj - 3) / (1 + expf(-xj));
+        }
+    } else {
+        double x_a = mg->range[0], h_x = (mg->range[1] - x_a) / (double)(n - 1);
+        for (int j = 0; j < n; j++) {
+            double xj = x_a + j * h_x;
+            ((double*)host)[j] = (exp(xj) + xj - 3) / (1 + exp(-xj));
+        }
+    }
+    void* d = NULL;
+    cudaError_t e = cudaMalloc(&d, (size_t)n * es);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d, host, (size_t)n * es, cudaMemcpyHostToDevice, mg->stream);
+    if (e != cudaSuccess) { free(host); if (d) cudaFree(d); return mg_fail(MG_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e)); }
+    const char* v = (const char*)mg->arena + (size_t)mg->H.off_v[level] * es;
+    int k = mgk1d_abs_error(mg->stream, mg->dtype, v, d, n, mg->d_out2);
+    if (k >= 0) e = cudaMemcpyAsync(mg->h_out2, mg->d_out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, mg->stream);
+    if (k >= 0 && e == cudaSuccess) e = cudaStreamSynchronize(mg->stream);
+    free(host);
+    cudaFree(d);
+    if (k < 0 || e != cudaSuccess) return mg_fail(MG_ERR_CUDA, "abs error reduction failed: %s", cudaGetErrorString(cudaGetLastError()));
+    mg->launches += k;
+    if (mean_abs) *mean_abs = mg->h_out2[0] / n;
+    if (max_abs) *max_abs = mg->h_out2[1];
+    return MG_OK;
+}
+
 int mg1d_residual_norm(mg1d_t* mg, int level, double* l2, double* linf)
 {
     int st = check_level(mg, level);

@@ -253,6 +253,31 @@ int ops(cudaStream_t s, int dtype, void* arena, const mg_hier1d& H, int op, int 
 
 }  // namespace
 
+// |v - table| reduced to {sum, max} by one block (N1/Grid1D.cpp:46-60 as a reduction; `table` holds the analytic solution
+// computed with the host libm, in the grid's own precision; the difference is taken in that precision too)
+template <typename T>
+__global__ void __launch_bounds__(256) k_abs_error1(const T* __restrict__ v, const T* __restrict__ table, int n, double* __restrict__ out2)
+{
+    __shared__ double ss[256], sm[256];
+    double s = 0.0, m = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double d = fabs((double)mgx::sub(v[i], table[i]));
+        s += d;
+        m = fmax(m, d);
+    }
+    ss[threadIdx.x] = s;
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            ss[threadIdx.x] += ss[threadIdx.x + o];
+            sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out2[0] = ss[0]; out2[1] = sm[0]; }
+}
+
 extern "C" {
 
 int mgk1d_relax(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int level, int ncycles)
@@ -286,6 +311,13 @@ int mgk1d_level_op(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int leve
     /* which: 0 Restrict(f) fine->coarse, 1 Interpolate into v, 2 Interpolate + ApplyCorrection */
     return ops(s, dtype, arena, H, which == 0 ? OP_RESTRICT_F : (which == 1 ? OP_INTERP : OP_INTERP_ADD), level, 0, 0, 0, 0,
                nullptr, nullptr);
+}
+
+int mgk1d_abs_error(cudaStream_t s, int dtype, const void* v, const void* table, int n, double* out2)
+{
+    if (dtype == 0) k_abs_error1<float><<<1, 256, 0, s>>>((const float*)v, (const float*)table, n, out2);
+    else k_abs_error1<double><<<1, 256, 0, s>>>((const double*)v, (const double*)table, n, out2);
+    return launch_ok();
 }
 
 int mgk1d_restrict(cudaStream_t s, int dtype, const void* fine, int fn, void* coarse, int cn)

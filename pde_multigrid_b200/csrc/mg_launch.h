@@ -206,6 +206,8 @@ int mgk1d_residual_norm(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int
 /* level operators inside the arena: which = 0 Restrict(f) level->level+1, 1 Interpolate level+1 -> v of level,
    2 Interpolate + ApplyCorrection */
 int mgk1d_level_op(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int level, int which);
+/* {sum, max} of |v - table| over n points, one block (table: the analytic solution from the host libm) */
+int mgk1d_abs_error(cudaStream_t s, int dtype, const void* v, const void* table, int n, double* out2);
 int mgk1d_restrict(cudaStream_t s, int dtype, const void* fine, int fn, void* coarse, int cn);
 int mgk1d_residual_restrict(cudaStream_t s, int dtype, void* arena, mg_hier1d H, int level, int corrected);
 int mgk1d_interpolate(cudaStream_t s, int dtype, void* fine, int fn, const void* coarse, int cn, int add);

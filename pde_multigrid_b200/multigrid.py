@@ -298,3 +298,9 @@ class MultiGrid1D(_MultiGridBase):
         check(self._L.mg1d_create(ctypes.byref(h), ctypes.c_int(int(finestGridSize)), rg, _dtype_code(dtype),
                                   int(residual_mode)))
         self._h = h
+
+    def abs_error(self, level=0):
+        """(mean, max) over all points of |approxsol - realsol|: Grid1D::PrintDiffApproxReal as a reduction."""
+        mean, mx = ctypes.c_double(), ctypes.c_double()
+        self._call("abs_error", ctypes.c_int(level), ctypes.byref(mean), ctypes.byref(mx))
+        return mean.value, mx.value

@@ -172,3 +172,32 @@ def test_argument_errors(mg):
     with pytest.raises(mg.MGError):
         eng.Relax(4, 1)
     eng.close()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_abs_error_is_printdiffapproxreal_reduced(mg, dtype):
+    """mg1d_abs_error against Grid1D::PrintDiffApproxReal's arithmetic (N1/Grid1D.cpp:46-60) restated with the same libm;
+    SURVEY.md 4 quotes max|v-u| = 9.164e-4 for the float FMG(2,1000,1000) solve at n = 1025."""
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.expf.restype, libm.expf.argtypes = ctypes.c_float, [ctypes.c_float]
+    libm.exp.restype, libm.exp.argtypes = ctypes.c_double, [ctypes.c_double]
+    n = 1025
+    eng = mg.MultiGrid1D(n, dtype=dtype)
+    eng.FullMultiGridVCycle(0, 2, 1000, 1000)
+    v = eng.get_v(0)
+    t = dtype
+    h = t(1.0) / t(n - 1)
+    real = np.empty(n, dtype=dtype)
+    for j in range(n):
+        xj = t(0.0) + t(j) * h
+        if dtype == np.float32:
+            real[j] = (t(libm.expf(xj)) + xj - t(3)) / (t(1) + t(libm.expf(-xj)))
+        else:
+            real[j] = (libm.exp(xj) + xj - 3) / (1 + libm.exp(-xj))
+    diff = np.abs((v - real).astype(np.float64))
+    mean, mx = eng.abs_error(0)
+    assert mx == diff.max()
+    assert abs(mean - diff.mean()) <= 1e-12 * diff.mean()
+    assert abs(mx - 9.164e-4) < 5e-6
+    eng.close()
