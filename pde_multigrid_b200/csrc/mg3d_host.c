@@ -1217,8 +1217,12 @@ static int residual_restrict_level(mg3d_t* mg, int fine_level, int defer_f_halo)
     }
     PROF_BEGIN(mg, fine_level, MG_OP_RESIDUAL_RESTRICT);
     if (F->has_tma && mg->smoother != MG_SMOOTHER_COLOUR)
-        MG_LAUNCH(mg->launches, mgk3d_residual_restrict_tma(mg->stream, mg->dtype, F->tmap_rr[F->cur][0], F->tmap_rr[F->cur][1], F->f, F->g, F->c,
+    {
+        const void* fmaps[2] = {F->tmap_pf[0], F->tmap_pf[1]};
+        MG_LAUNCH(mg->launches, mgk3d_residual_restrict_tma(mg->stream, mg->dtype, F->tmap_rr[F->cur][0], F->tmap_rr[F->cur][1],
+                                                            getenv("MG_B200_RR_NO_PREFETCH") ? NULL : fmaps, F->f, F->g, F->c,
                                                             mg->mode == MG_CORRECTED, C->f, C->v, C->g, lo, hi));
+    }
     else
         MG_LAUNCH(mg->launches, mgk3d_residual_restrict(mg->stream, mg->dtype, F->v, F->f, F->g, F->c, mg->mode == MG_CORRECTED,
                                                         C->f, C->v, C->g, lo, hi));

@@ -54,6 +54,7 @@ template <typename T> struct VBox {
 template <typename T, bool FAST, bool NORM>
 __global__ void __launch_bounds__(NT, 2)
 k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid_constant__ CUtensorMap map_c1,
+                        const __grid_constant__ CUtensorMap map_f0, const __grid_constant__ CUtensorMap map_f1, int f_prefetch,
                         const T* __restrict__ f, mg_geom3d gf, Coef3<T> c, int corrected, T* __restrict__ cf,
                         T* __restrict__ cv, mg_geom3d gc, int czl_lo, int czl_hi, int zchunk, double* __restrict__ part)
 {
@@ -100,8 +101,18 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
         mbar_wait(&bars[k % RING], (k / RING) & 1);
     };
     auto slot_of = [&](int p) -> const T* { return vring + ((unsigned)(p - pbase) % RING) * VSLOT; };
-    if (tid == 0)
+    // f is read with plain loads one plane ahead of its use; an L2 prefetch of its tile a few planes further ahead (TMA
+    // prefetch, no shared memory, one thread) turns those loads into L2 hits
+    auto prefetch_f = [&](int p) {
+        const int pl = p - gf.z0;
+        if (!f_prefetch || pl < 0 || pl >= gf.nzl || p > zf1) return;
+        asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&map_f0), "r"(cx0), "r"(fy0), "r"(pl) : "memory");
+        asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&map_f1), "r"(cx0), "r"(fy0), "r"(pl) : "memory");
+    };
+    if (tid == 0) {
         for (int p = pbase; p <= min(pbase + RING - 1, zf1 + 1); p++) issue(p);
+        for (int p = zf0; p <= zf0 + RING; p++) prefetch_f(p);
+    }
 
     static_assert(CXT == 32 && CYT == 8 && NT == 256, "thread mapping: one coarse point = one 2x2 fine column per thread");
     const int w = tid >> 5, lane = tid & 31;
@@ -270,6 +281,8 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
         if (tid == 0) {
             if (z + RING - 1 <= zf1 + 1) issue(z + RING - 1);
             if (z + RING <= zf1 + 1) issue(z + RING);
+            prefetch_f(z + RING + 1);
+            prefetch_f(z + RING + 2);
         }
         if constexpr (NORM) continue;
         const int cz = z >> 1, czl = cz - gc.z0;
@@ -326,29 +339,32 @@ static void tile_grid(const mg_geom3d& gc, int czl_lo, int czl_hi, dim3& grid, i
 }
 
 template <typename T, bool FAST, bool NORM>
-int launch_k(cudaStream_t s, const CUtensorMap& m0, const CUtensorMap& m1, const T* f, mg_geom3d gf, mg_coef3d c, int corrected, T* cf,
+int launch_k(cudaStream_t s, const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap* mf, const T* f, mg_geom3d gf, mg_coef3d c, int corrected, T* cf,
              T* cv, mg_geom3d gc, int czl_lo, int czl_hi, dim3 grid, int zchunk, double* part)
 {
     const size_t smem = smem_bytes_t<T>();
     MG_SET_SMEM_LIMIT((k_residual_restrict_tma<T, FAST, NORM>), smem_bytes_t<T>());
-    k_residual_restrict_tma<T, FAST, NORM><<<grid, NT, smem, s>>>(m0, m1, f, gf, narrow<T>(c), corrected, cf, cv, gc, czl_lo, czl_hi, zchunk, part);
+    k_residual_restrict_tma<T, FAST, NORM><<<grid, NT, smem, s>>>(m0, m1, mf ? mf[0] : m0, mf ? mf[1] : m1, mf != nullptr, f, gf, narrow<T>(c), corrected, cf, cv,
+                                                                 gc, czl_lo, czl_hi, zchunk, part);
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 
 template <typename T>
-int launch(cudaStream_t s, const void* tmap_c0, const void* tmap_c1, const T* f, mg_geom3d gf, mg_coef3d c, int corrected, T* cf, T* cv,
-           mg_geom3d gc, int czl_lo, int czl_hi)
+int launch(cudaStream_t s, const void* tmap_c0, const void* tmap_c1, const void* const tmap_f[2], const T* f, mg_geom3d gf, mg_coef3d c,
+           int corrected, T* cf, T* cv, mg_geom3d gc, int czl_lo, int czl_hi)
 {
     if (czl_hi <= czl_lo) return 0;
     static_assert(NT == CXT * CYT, "one coarse point per thread");
     dim3 grid;
     int zchunk;
     tile_grid(gc, czl_lo, czl_hi, grid, zchunk);
-    CUtensorMap m0, m1;
+    CUtensorMap m0, m1, mf[2];
     memcpy(&m0, tmap_c0, sizeof m0);
     memcpy(&m1, tmap_c1, sizeof m1);
-    if (c.fast_h) return launch_k<T, true, false>(s, m0, m1, f, gf, c, corrected, cf, cv, gc, czl_lo, czl_hi, grid, zchunk, nullptr);
-    return launch_k<T, false, false>(s, m0, m1, f, gf, c, corrected, cf, cv, gc, czl_lo, czl_hi, grid, zchunk, nullptr);
+    const bool pf = tmap_f && tmap_f[0] && tmap_f[1];
+    if (pf) { memcpy(&mf[0], tmap_f[0], sizeof m0); memcpy(&mf[1], tmap_f[1], sizeof m0); }
+    if (c.fast_h) return launch_k<T, true, false>(s, m0, m1, pf ? mf : nullptr, f, gf, c, corrected, cf, cv, gc, czl_lo, czl_hi, grid, zchunk, nullptr);
+    return launch_k<T, false, false>(s, m0, m1, pf ? mf : nullptr, f, gf, c, corrected, cf, cv, gc, czl_lo, czl_hi, grid, zchunk, nullptr);
 }
 
 template <typename T>
@@ -364,19 +380,19 @@ int launch_norm(cudaStream_t s, const void* tmap_c0, const void* tmap_c1, const 
     CUtensorMap m0, m1;
     memcpy(&m0, tmap_c0, sizeof m0);
     memcpy(&m1, tmap_c1, sizeof m1);
-    if (c.fast_h) return launch_k<T, true, true>(s, m0, m1, f, gf, c, corrected, nullptr, nullptr, gc, czl_lo, czl_hi, grid, zchunk, part);
-    return launch_k<T, false, true>(s, m0, m1, f, gf, c, corrected, nullptr, nullptr, gc, czl_lo, czl_hi, grid, zchunk, part);
+    if (c.fast_h) return launch_k<T, true, true>(s, m0, m1, nullptr, f, gf, c, corrected, nullptr, nullptr, gc, czl_lo, czl_hi, grid, zchunk, part);
+    return launch_k<T, false, true>(s, m0, m1, nullptr, f, gf, c, corrected, nullptr, nullptr, gc, czl_lo, czl_hi, grid, zchunk, part);
 }
 
 }  // namespace
 
-extern "C" int mgk3d_residual_restrict_tma(cudaStream_t s, int dtype, const void* tmap_v_c0, const void* tmap_v_c1, const void* f,
-                                           mg_geom3d gf, mg_coef3d c, int corrected, void* coarse_f, void* coarse_v, mg_geom3d gc,
+extern "C" int mgk3d_residual_restrict_tma(cudaStream_t s, int dtype, const void* tmap_v_c0, const void* tmap_v_c1, const void* const tmap_f[2],
+                                           const void* f, mg_geom3d gf, mg_coef3d c, int corrected, void* coarse_f, void* coarse_v, mg_geom3d gc,
                                            int czl_lo, int czl_hi)
 {
     if (dtype == 0)
-        return launch<float>(s, tmap_v_c0, tmap_v_c1, (const float*)f, gf, c, corrected, (float*)coarse_f, (float*)coarse_v, gc, czl_lo, czl_hi);
-    return launch<double>(s, tmap_v_c0, tmap_v_c1, (const double*)f, gf, c, corrected, (double*)coarse_f, (double*)coarse_v, gc, czl_lo, czl_hi);
+        return launch<float>(s, tmap_v_c0, tmap_v_c1, tmap_f, (const float*)f, gf, c, corrected, (float*)coarse_f, (float*)coarse_v, gc, czl_lo, czl_hi);
+    return launch<double>(s, tmap_v_c0, tmap_v_c1, tmap_f, (const double*)f, gf, c, corrected, (double*)coarse_f, (double*)coarse_v, gc, czl_lo, czl_hi);
 }
 
 /* residual norm of the fine planes under the coarse planes [czl_lo, czl_hi) with the staging of the kernel above: partials into

@@ -124,7 +124,8 @@ int mgk3d_residual_restrict(cudaStream_t s, int dtype, const void* v, const void
 #define MGK3D_RR_CYT 8
 #define MGK3D_RR_BOX_Y (2 * MGK3D_RR_CYT + 3)
 #define MGK3D_RR_BOX_I(esize) ((MGK3D_RR_CXT + 2 * (16 / (int)(esize))) / (16 / (int)(esize)) * (16 / (int)(esize)))
-int mgk3d_residual_restrict_tma(cudaStream_t s, int dtype, const void* tmap_v_c0, const void* tmap_v_c1, const void* f,
+/* tmap_f: NULL, or the tensor maps of the two colour arrays of the fine f with the box of mgk3d_relax_pipe2 (L2 prefetch only) */
+int mgk3d_residual_restrict_tma(cudaStream_t s, int dtype, const void* tmap_v_c0, const void* tmap_v_c1, const void* const tmap_f[2], const void* f,
                                 mg_geom3d gf, mg_coef3d c, int corrected, void* coarse_f, void* coarse_v, mg_geom3d gc,
                                 int czl_lo, int czl_hi);
 /* fine interior = Interpolate(coarse) (add == 0) or fine interior += Interpolate(coarse) (add != 0);
