@@ -54,7 +54,9 @@ typedef struct {
     unsigned char tmap_fu[2][2][128] __attribute__((aligned(64))); /* fused-smoother boxes of v */
     unsigned char tmap_ff[2][128] __attribute__((aligned(64)));    /* fused-smoother boxes of f: [colour] */
     unsigned char tmap_pp[2][128] __attribute__((aligned(64)));    /* pipelined smoother: colour-1 array of v, [buffer] */
-    unsigned char tmap_pf[2][128] __attribute__((aligned(64)));    /* pipelined smoother: f (L2 prefetch), [colour] */
+    unsigned char tmap_pf[2][128] __attribute__((aligned(64)));    /* pipelined smoother: f, [colour] */
+    unsigned char tmap_pc[2][2][128] __attribute__((aligned(64))); /* this level's v as the COARSE operand of the finer level's pass: [buffer][colour] */
+    int has_pc;
     int iso;        /* hx2 == hy2 == hz2 */
     /* distributed levels: 1 = the ghost planes of v (both colours, 2 below / 1 above) hold the neighbours' current values.
        Every operator leaves it 1 except the temporally blocked smoother, whose pass only writes the planes a rank owns;
@@ -117,6 +119,7 @@ struct mg3d_s {
     double omega;   /* weight of MG_SMOOTHER_JACOBI */
     int arith;           /* MG_ARITH_EXACT / MG_ARITH_FAST */
     int no_pipe;         /* MG_B200_NO_PIPE: MG_SMOOTHER_AUTO without temporal blocking (the round-1 default) */
+    int no_corr_fuse;    /* MG_B200_NO_CORR_FUSE: prolongation + correction as a kernel of their own even where the pass could take them */
     unsigned int* d_flag; /* {exactness flag of the pipelined smoother, completion counter of its fallback} */
     int no_tail;         /* MG_B200_NO_TAIL: coarse levels as separate launches */
     int full_correction; /* MG_B200_FULL_CORRECTION: correct both colours after prolongation inside a cycle */
@@ -518,6 +521,7 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
     mg->omega = 6.0 / 7.0;
     mg->no_tail = getenv("MG_B200_NO_TAIL") != NULL;
     mg->no_pipe = getenv("MG_B200_NO_PIPE") != NULL;
+    mg->no_corr_fuse = getenv("MG_B200_NO_CORR_FUSE") != NULL;
     mg->arith = MG_ARITH_EXACT;
     mg->full_correction = getenv("MG_B200_FULL_CORRECTION") != NULL;
     memcpy(mg->range, range, sizeof mg->range);
@@ -599,6 +603,19 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
         L->iso = L->c.hx2 == L->c.hy2 && L->c.hy2 == L->c.hz2;
         if (st) { mg3d_destroy(mg); return st; }
         L->has_tma = 1;
+    }
+    /* a level below one with tensor maps is the coarse operand of that level's fused prolongation */
+    for (int l = 1; l < mg->nlevels && !st; l++) {
+        mg_level3d* L = &mg->lv[l];
+        if (!mg->lv[l - 1].has_tma) continue;
+        const int es = (int)mg_esize(dtype);
+        for (int b = 0; b < 2 && !st; b++) {
+            if (!L->vbuf[b]) continue;
+            for (int col = 0; col < 2 && !st; col++)
+                st = mg_tma_make_colour_map(L->tmap_pc[b][col], dtype, plane_ptr(mg, L, L->vbuf[b], col, 0), &L->g, MGK3D_PP_CBOX_I(es), MGK3D_PP_CBOX_Y);
+        }
+        if (st) { mg3d_destroy(mg); return st; }
+        L->has_pc = 1;
     }
     /* pad elements of the layout are never used by a kernel, but keep them defined */
     if (cudaMemsetAsync(mg->arena_raw, 0, total + 2 * MG_ARENA_SLACK, mg->stream) != cudaSuccess) {
@@ -980,7 +997,20 @@ static int relax_jacobi_level(mg3d_t* mg, int level, int ncycles)
     return MG_OK;
 }
 
-static int relax_level(mg3d_t* mg, int level, int ncycles)
+static int relax_level_ex(mg3d_t* mg, int level, int ncycles, int correct_first);
+
+static int relax_level(mg3d_t* mg, int level, int ncycles) { return relax_level_ex(mg, level, ncycles, 0); }
+
+/* 1 when VCycle's Interpolate + ApplyCorrection on `level` can ride on the first pass of the post-smoothing */
+static int correction_fuses(const mg3d_t* mg, int level, int v2)
+{
+    const mg_level3d* L = &mg->lv[level];
+    return v2 >= 2 && level + 1 < mg->nlevels && level_takes_pipe(mg, L) && mg->lv[level + 1].has_pc && !mg->full_correction && !mg->no_corr_fuse;
+}
+
+/* correct_first: the first two-sweep pass starts from v + Interpolate(v of level+1) on the colour-1 points (the caller has
+   checked correction_fuses) */
+static int relax_level_ex(mg3d_t* mg, int level, int ncycles, int correct_first)
 {
     mg_level3d* L = &mg->lv[level];
     int lo, hi, st;
@@ -998,12 +1028,32 @@ static int relax_level(mg3d_t* mg, int level, int ncycles)
             /* slab: four planes of colour 1 from each neighbour -- all the pass reads of v beyond the planes it owns (one
                exchange per two sweeps instead of four; the halo planes are swept redundantly, bit-identical on both sides) */
             if (L->dist && !L->vg_deep && (st = exchange(mg, level, L->v, 2, MG_GHOST_LO, MG_GHOST_HI))) return st;
+            mg_level3d* C = correct_first ? &mg->lv[level + 1] : NULL;
+            const void* cmaps[2] = {C ? C->tmap_pc[C->cur][0] : NULL, C ? C->tmap_pc[C->cur][1] : NULL};
+            int elo = 0, ehi = 0; /* planes the pass reads of v: the owned ones and four on each side, inside the grid */
+            if (C) {
+                /* the halo planes of the slab are corrected here as well (the neighbour's own correction never reaches memory):
+                   coarse planes up to two below and three above the coarse slab */
+                if (C->dist) {
+                    if ((st = exchange(mg, level + 1, C->v, 3, 2, 3))) return st;
+                    C->vg_valid = 1;
+                }
+                const int first = 1 - L->g.z0, last = L->g.n - 2 - L->g.z0;
+                elo = L->own_lo - 4 > first ? L->own_lo - 4 : first;
+                ehi = (L->own_hi + 4 < last + 1 ? L->own_hi + 4 : last + 1);
+                if (elo < 0) elo = 0;
+                if (ehi > L->g.nzl) ehi = L->g.nzl;
+            }
             PROF_BEGIN(mg, level, MG_OP_RELAX);
             MG_LAUNCH(mg->launches, mgk3d_relax_pipe2(mg->stream, mg->dtype, maps3, L->vbuf[L->cur], L->f, L->vbuf[L->cur ^ 1], L->g, L->c,
-                                                      L->own_lo, L->own_hi, mg->arith == MG_ARITH_FAST, mg->d_flag));
-            if (mg->arith != MG_ARITH_FAST) /* conditional on the range guard; reads the same input planes, no exchange of its own */
+                                                      L->own_lo, L->own_hi, mg->arith == MG_ARITH_FAST, mg->d_flag, C ? cmaps : NULL, C ? &C->g : NULL));
+            if (mg->arith != MG_ARITH_FAST) { /* conditional on the range guard; reads the same input planes, no exchange of its own */
+                if (C) /* ... after the correction the pass applied on the fly has been applied to the input buffer for real */
+                    MG_LAUNCH(mg->launches, mgk3d_interpolate(mg->stream, mg->dtype, L->v, L->g, C->v, C->g, 1, 2, elo, ehi, mg->d_flag));
                 MG_LAUNCH(mg->launches, mgk3d_relax_fused2(mg->stream, mg->dtype, maps4, L->vbuf[L->cur ^ 1], L->g, L->c, L->own_lo, L->own_hi, mg->d_flag));
+            }
             PROF_END(mg);
+            correct_first = 0;
             L->cur ^= 1;
             L->v = L->vbuf[L->cur];
             L->vg_valid = L->vg_deep = 0; /* only the owned planes of the new buffer were written */
@@ -1255,7 +1305,7 @@ static int interpolate_level(mg3d_t* mg, int fine_level, int add, int colour_mas
     interior_range(F, &lo, &hi);
     if ((st = ensure_v_ghosts(mg, fine_level + 1))) return st; /* the last fine plane of a slab reads the coarse plane above */
     PROF_BEGIN(mg, fine_level, MG_OP_INTERPOLATE);
-    MG_LAUNCH(mg->launches, mgk3d_interpolate(mg->stream, mg->dtype, F->v, F->g, C->v, C->g, add, colour_mask, lo, hi));
+    MG_LAUNCH(mg->launches, mgk3d_interpolate(mg->stream, mg->dtype, F->v, F->g, C->v, C->g, add, colour_mask, lo, hi, NULL));
     PROF_END(mg);
     if (!F->dist) return MG_OK;
     /* a level the temporally blocked smoother takes next fetches its (deeper) ghost planes itself */
@@ -1330,6 +1380,8 @@ static int vcycle_rec(mg3d_t* mg, int level, int v1, int v2)
     if (level != mg->nlevels - 1) {
         if ((st = residual_restrict_level(mg, level, v1 > 0 && relax_overlaps(mg, level + 1)))) return st;
         if ((st = vcycle_rec(mg, level + 1, v1, v2))) return st;
+        /* prolongation + correction ride on the first pass of the post-smoothing where the temporally blocked smoother runs */
+        if (correction_fuses(mg, level, v2)) return relax_level_ex(mg, level, v2, 1);
         /* the colour-0 half of the correction is dead when a red-black post-smoothing sweep follows */
         if ((st = interpolate_level(mg, level, 1, (v2 > 0 && mg->smoother != MG_SMOOTHER_JACOBI && !mg->full_correction) ? 2 : 3,
                                     v2 > 0 && relax_overlaps(mg, level))))
@@ -1505,7 +1557,7 @@ int mg3d_interpolate_host(mg3d_t* mg, void* fine, const int fs[3], const void* c
     st = copy_in(mg, df, &gf, fine, 0, fn); /* boundary of fine is kept */
     if (!st) st = copy_in(mg, dc, &gc, coarse, 0, cn);
     if (!st) {
-        int k = mgk3d_interpolate(mg->stream, mg->dtype, df, gf, dc, gc, 0, 3, 1, fn - 1);
+        int k = mgk3d_interpolate(mg->stream, mg->dtype, df, gf, dc, gc, 0, 3, 1, fn - 1, NULL);
         if (k < 0) st = mg_fail(MG_ERR_CUDA, "interpolate launch failed"); else mg->launches += k;
     }
     if (!st) st = copy_out(mg, fine, df, &gf, 0, fn);
@@ -1635,7 +1687,7 @@ static int device_op(mg3d_t* mg, int which, void* a, const int as[3], void* b, c
     int k = 0;
     if (!st) {
         if (which == 0) k = mgk3d_restrict(mg->stream, mg->dtype, da, ga, db, gb, 0, bn);
-        else if (which == 1) k = mgk3d_interpolate(mg->stream, mg->dtype, da, ga, db, gb, 0, 3, 1, an - 1);
+        else if (which == 1) k = mgk3d_interpolate(mg->stream, mg->dtype, da, ga, db, gb, 0, 3, 1, an - 1, NULL);
         else if (which == 2) k = mgk3d_apply_correction(mg->stream, mg->dtype, da, db, ga, 1, an - 1);
         else k = mgk3d_set(mg->stream, mg->dtype, da, ga, value, modify_boundaries, 0, an);
         if (k < 0) st = mg_fail(MG_ERR_CUDA, "operator launch failed"); else mg->launches += k;

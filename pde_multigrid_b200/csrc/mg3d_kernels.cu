@@ -223,8 +223,9 @@ k_residual_restrict(const T* __restrict__ v, const T* __restrict__ f, mg_geom3d 
 template <typename T, int MASK>
 __global__ void __launch_bounds__(256, MASK == 2 ? 6 : 4)
 k_interp_octet(T* __restrict__ fine, mg_geom3d gf, const T* __restrict__ coarse, mg_geom3d gc, int add_, int zl_lo,
-               int zl_hi, int cz_first, int cz_last, int kchunk)
+               int zl_hi, int cz_first, int cz_last, int kchunk, const unsigned int* __restrict__ cond)
 {
+    if (cond && *cond == 0u) return;  // conditional launch: see mgk3d_interpolate
     const int cx = blockIdx.x * blockDim.x + threadIdx.x;
     const int cy = blockIdx.y * blockDim.y + threadIdx.y;
     if (cx > gc.n - 2 || cy > gc.n - 2) return;
@@ -487,7 +488,7 @@ int mgk3d_residual_restrict(cudaStream_t s, int dtype, const void* v, const void
 }
 
 int mgk3d_interpolate(cudaStream_t s, int dtype, void* fine, mg_geom3d gf, const void* coarse, mg_geom3d gc, int add,
-                      int colour_mask, int zl_lo, int zl_hi)
+                      int colour_mask, int zl_lo, int zl_hi, const unsigned int* cond)
 {
     if (zl_hi <= zl_lo || gf.n < 3) return 0;
     const int cells = gc.n - 1;  // coarse cells per axis: cell c covers fine 2c, 2c+1
@@ -500,15 +501,15 @@ int mgk3d_interpolate(cudaStream_t s, int dtype, void* fine, mg_geom3d gf, const
     int by = 256 / bx;
     if (by > cells) by = cells;
     const int ncz = cz_last - cz_first + 1;
-    int kchunk = 8;
+    int kchunk = cond ? 64 : 8;  // a conditional launch almost always exits at once: few, long CTAs
     while (kchunk > 1 && (long long)((cells + bx - 1) / bx) * ((cells + by - 1) / by) * ((ncz + kchunk - 1) / kchunk) < 148 * 8) kchunk /= 2;
     dim3 block(bx, by, 1), grid((cells + bx - 1) / bx, (cells + by - 1) / by, (ncz + kchunk - 1) / kchunk);
     if (dtype == 0)
-        if (colour_mask == 2) k_interp_octet<float, 2><<<grid, block, 0, s>>>((float*)fine, gf, (const float*)coarse, gc, add, zl_lo, zl_hi, cz_first, cz_last, kchunk);
-        else k_interp_octet<float, 3><<<grid, block, 0, s>>>((float*)fine, gf, (const float*)coarse, gc, add, zl_lo, zl_hi, cz_first, cz_last, kchunk);
+        if (colour_mask == 2) k_interp_octet<float, 2><<<grid, block, 0, s>>>((float*)fine, gf, (const float*)coarse, gc, add, zl_lo, zl_hi, cz_first, cz_last, kchunk, cond);
+        else k_interp_octet<float, 3><<<grid, block, 0, s>>>((float*)fine, gf, (const float*)coarse, gc, add, zl_lo, zl_hi, cz_first, cz_last, kchunk, cond);
     else
-        if (colour_mask == 2) k_interp_octet<double, 2><<<grid, block, 0, s>>>((double*)fine, gf, (const double*)coarse, gc, add, zl_lo, zl_hi, cz_first, cz_last, kchunk);
-        else k_interp_octet<double, 3><<<grid, block, 0, s>>>((double*)fine, gf, (const double*)coarse, gc, add, zl_lo, zl_hi, cz_first, cz_last, kchunk);
+        if (colour_mask == 2) k_interp_octet<double, 2><<<grid, block, 0, s>>>((double*)fine, gf, (const double*)coarse, gc, add, zl_lo, zl_hi, cz_first, cz_last, kchunk, cond);
+        else k_interp_octet<double, 3><<<grid, block, 0, s>>>((double*)fine, gf, (const double*)coarse, gc, add, zl_lo, zl_hi, cz_first, cz_last, kchunk, cond);
     return launch_ok();
 }
 

@@ -68,6 +68,18 @@ template <typename T> struct PBox {
 struct PipeMaps {
     CUtensorMap vblack;  // colour-1 array of the input v, box (W, TYT, 1)
     CUtensorMap f[2];    // colour arrays of f, same box
+    CUtensorMap cv[2];   // CORR: colour arrays of the next coarser level's v, box (CBox::CW, CROWS, 1)
+};
+
+// CORR: the coarse tile under a fine tile.  Fine half-index i IS the coarse x (x = 2i, 2i+1 -> X = i), so the tile needs coarse
+// X = i0-HXI .. i0-HXI+LW (half-indices X >> 1 of the coarse colour arrays) and coarse rows (y0-HY)/2 .. +TYT/2.
+constexpr int CROWS = TYT / 2 + 1;
+constexpr int NCR = 4;  // coarse planes in flight: Z0, Z0+1 in use, two ahead
+template <typename T> struct CBox {
+    static constexpr int A = 16 / (int)sizeof(T);                 // TMA inner-coordinate alignment in elements
+    static constexpr int CW = MGK3D_PP_CBOX_I(sizeof(T));         // 18 doubles / 20 floats
+    static constexpr int CSUB = (CW * CROWS * (int)sizeof(T) + 127) / 128 * 128 / (int)sizeof(T);
+    static constexpr int CSLOT = 2 * CSUB;
 };
 
 // range check of a value that enters a stage: +0, or lo <= |x| <= hi in exponent terms.  Everything else -- tiny, huge,
@@ -103,10 +115,15 @@ __device__ __forceinline__ T gs_update(T own, T nbx, T N, T S, T D, T U, T f, T 
     }
 }
 
-template <typename T, int ARITH>
+// CORR: the pass starts from v + Interpolate(coarse v) on the interior colour-1 points instead of v -- the prolongation and
+// ApplyCorrection of the V-cycle (N3/MultiGrid3D.cpp:186-335, :649-676) folded into the load stage of the post-smoothing
+// pass: every raw colour-1 value is corrected once, in its ring slot, by the thread that owns the site, before anybody reads
+// it.  (Colour 0 is not corrected at all: the first half-sweep overwrites it unread.)  Saves the separate prolongation
+// kernel's read and write of the colour-1 array.
+template <typename T, int ARITH, bool CORR>
 __global__ void __launch_bounds__(NT, 1)
 k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in, T* __restrict__ v_out, mg_geom3d g, T h2, T y6,
-              int zchunk, int zlo, int zhi, unsigned glo, unsigned gspan, unsigned int* __restrict__ flag)
+              int zchunk, int zlo, int zhi, unsigned glo, unsigned gspan, unsigned int* __restrict__ flag, mg_geom3d gc)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int PADL = PBox<T>::PADL, W = PBox<T>::W, SLOT = PBox<T>::SLOT, NSLOT = PBox<T>::NSLOT, GUARD = PBox<T>::GUARD;
@@ -115,7 +132,9 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
     constexpr bool CHECK_MID = ARITH == 0 && sizeof(T) == 4;
     constexpr int GUARD_AL = (GUARD * (int)sizeof(T) + 127) / 128 * 128 / (int)sizeof(T);
     T* base = reinterpret_cast<T*>(smem_raw) + GUARD_AL;  // slot 0
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)NSLOT * SLOT + GUARD_AL);
+    constexpr int CSUB = CBox<T>::CSUB, CSLOT = CBox<T>::CSLOT, CW = CBox<T>::CW;
+    T* cring = base + (size_t)NSLOT * SLOT + GUARD_AL;    // CORR: NCR coarse planes, two colour sub-tiles each
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cring + (CORR ? (size_t)NCR * CSLOT : 0));  // NRING + NCR barriers
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = g.n, imax = (n - 1) / 2;
@@ -127,7 +146,8 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
         prefetch_tensormap(&maps.vblack);
         prefetch_tensormap(&maps.f[0]);
         prefetch_tensormap(&maps.f[1]);
-        for (int s = 0; s < NRING; s++) mbar_init(&bars[s], 1);
+        for (int s = 0; s < NRING + (CORR ? NCR : 0); s++) mbar_init(&bars[s], 1);
+        if (CORR) { prefetch_tensormap(&maps.cv[0]); prefetch_tensormap(&maps.cv[1]); }
         fence_barrier_init();
     }
     // Everything starts as zero: edge lanes and rows read one element / row outside their slot (results that depend on it are
@@ -149,13 +169,28 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
     };
     if (tid == 0)
         for (int k = 0; k < PF && k < nsteps; k++) issue(k, pb + k);
+    // CORR: coarse plane Z (global) lives in slot (Z - Zb) % NCR; fine plane p reads Z0 = (z0 + p) >> 1 and, on odd planes, Z0 + 1
+    const int Zb = (g.z0 + pb) >> 1, Zlast = ((g.z0 + pb + nsteps - 1) >> 1) + 1;
+    const int cxh0 = ((i0 - HXI) >> 1) & ~(CBox<T>::A - 1), cy0c = (y0 - HY) >> 1;
+    auto issue_coarse = [&](int Z) {
+        const int s = (Z - Zb) & (NCR - 1);
+        uint64_t* bar = &bars[NRING + s];
+        mbar_arrive_expect_tx(bar, 2 * CW * CROWS * (uint32_t)sizeof(T));
+        tma_load_3d(cring + (size_t)s * CSLOT, &maps.cv[0], bar, cxh0, cy0c, Z - gc.z0);
+        tma_load_3d(cring + (size_t)s * CSLOT + CSUB, &maps.cv[1], bar, cxh0, cy0c, Z - gc.z0);
+    };
+    if (CORR && tid == 0)
+        for (int Z = Zb; Z <= min(Zb + NCR - 2, Zlast); Z++) issue_coarse(Z);
 
     // ---- per-thread constants -------------------------------------------------------------------------------
     // Site (lane, row r): half-index i, row y.  On plane z its colour-c point has x = 2i + ((c + y + z) & 1).  Steps are
     // unrolled six-fold, so relative to the first plane every parity is a compile-time bit XOR s0 = (y_row0 + z0 + pb) & 1.
     const int i = i0 - HXI + lane;
     const int tr0 = R * warp, yr0 = y0 - HY + tr0;
-    const int s0 = (yr0 + g.z0 + pb) & 1;
+    const int s0 = (yr0 + g.z0 + pb) & 1;  // (yr0 is even: s0 is the same for every thread of the CTA)
+    // CORR: element of the site's coarse corner (dx, dy, dz) inside a coarse slot: colour (ipar + Yt + Z + dx + dy) & 1,
+    // column ((i + dx) >> 1) - cxh0, row Yt + dy - cy0c with Yt = yr0 / 2
+    const int ipar = i & 1, ca0 = ((i >> 1) - cxh0) + ((yr0 >> 1) - cy0c) * CW, ct = (i + (yr0 >> 1)) & 1;
     const T* sb = base + tr0 * W + lane + PADL;   // own site of row 0 in slot 0; row r: + r*W; slot j: + j*SLOT
     const T* sP = sb + (2 * s0 - 1);              // x-neighbour of row r when ((r & 1) ^ CV) == 0 ...
     const T* sM = sb - (2 * s0 - 1);              // ... and when it is 1 (CV: see step())
@@ -238,10 +273,62 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
         constexpr int X1W = (XB + 0 + E) * SLOT, X1R = (XB + 0 + (E ^ 1)) * SLOT;
         constexpr int X2W = (XB + 2 + (E ^ 1)) * SLOT, X2R = (XB + 2 + E) * SLOT;
         constexpr int X3W = (XB + 4 + E) * SLOT, X3R = (XB + 4 + (E ^ 1)) * SLOT;
+        if (CORR) {
+            static_assert(R == 2, "the fused prolongation pairs the thread's even row (oy = 0) with its odd row (oy = 1)");
+            const int zg = g.z0 + p, Z0 = zg >> 1, oz = zg & 1;
+            if (tid == 0 && oz == 0 && Z0 + NCR - 2 <= Zlast && Z0 + NCR - 2 > Zb + NCR - 2) issue_coarse(Z0 + NCR - 2);
+            const int k0 = Z0 - Zb;
+            mbar_wait(&bars[NRING + (k0 & (NCR - 1))], (unsigned)(k0 >> 2) & 1u);
+            if (oz) mbar_wait(&bars[NRING + ((k0 + 1) & (NCR - 1))], (unsigned)((k0 + 1) >> 2) & 1u);
+            // Corner (dx, dy, dz) of the site = coarse point (i + dx, Yt + dy, Z0 + dz): colour (ct + dx + dy + dz + Z0) & 1 with the
+            // per-thread bit ct = (i + Yt) & 1, column ((i + dx) >> 1), row Yt + dy.  Everything but ct is uniform over the CTA, so
+            // each plane needs two pointers: corners with dx + dy even / odd.
+            const T* q0 = cring + (size_t)(k0 & (NCR - 1)) * CSLOT + ca0;
+            const T* q1 = cring + (size_t)((k0 + 1) & (NCR - 1)) * CSLOT + ca0;
+            const int se = ((ct + Z0) & 1) * CSUB, so = CSUB - se;       // colour sub-tile of plane Z0 for dx + dy even / odd
+            const T *e0 = q0 + se, *o0 = q0 + so, *e1 = q1 + so, *o1 = q1 + se;  // plane Z0 + 1: colours swap
+            const bool oxa = (((s0 ^ CV) & 1) != 0);  // x parity of the colour-1 point in the even row (the odd row has the other)
+            T ea, eb;  // Interpolate at the colour-1 point of the even row (oy = 0) / the odd row (oy = 1), N3/MultiGrid3D.cpp:216-331
+            if (!oz) {
+                const T c000 = e0[0], c100 = o0[ipar], c010 = o0[CW];
+                if (!oxa) {  // even row PPP, odd row DDP
+                    ea = c000;
+                    eb = mul(T(0.25f), add(add(add(c000, c100), c010), e0[CW + ipar]));
+                } else {     // even row PDP, odd row DPP
+                    ea = mul(T(0.5f), add(c000, c100));
+                    eb = mul(T(0.5f), add(c000, c010));
+                }
+            } else {
+                const T c000 = e0[0], c001 = e1[0];
+                if (!oxa) {  // even row PPD, odd row DDD
+                    ea = mul(T(0.5f), add(c000, c001));
+                    T t8 = add(c000, c001);
+                    t8 = add(t8, o1[ipar]);       // C(1,0,1)
+                    t8 = add(t8, o0[ipar]);       // C(1,0,0)
+                    t8 = add(t8, o0[CW]);         // C(0,1,0)
+                    t8 = add(t8, o1[CW]);         // C(0,1,1)
+                    t8 = add(t8, e1[CW + ipar]);  // C(1,1,1)
+                    t8 = add(t8, e0[CW + ipar]);  // C(1,1,0)
+                    eb = mul(T(0.125f), t8);
+                } else {     // even row PDD, odd row DPD
+                    ea = mul(T(0.25f), add(add(add(c001, o1[ipar]), c000), o0[ipar]));
+                    eb = mul(T(0.25f), add(add(add(c000, c001), o0[CW]), o1[CW]));
+                }
+            }
+            const unsigned mzc = FAST ? ~0u : ((unsigned)(zg - 1) <= (unsigned)(n - 3)) ? mU : 0u;  // colour 1 on plane p sits at parity s_r ^ CV
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            wr[J][r] = sb[OFF_P + r * W];
-            if (ARITH == 0) guard(wr[J][r], glo, gspan, bad);
+            for (int r = 0; r < R; r++) {
+                const T rawv = sb[OFF_P + r * W];
+                wr[J][r] = (FAST || ((mzc >> r) & 1u)) ? add(rawv, r ? eb : ea) : rawv;
+                sw[OFF_P + r * W] = wr[J][r];  // the neighbours read this plane one step from now
+                if (ARITH == 0) guard(wr[J][r], glo, gspan, bad);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                wr[J][r] = sb[OFF_P + r * W];
+                if (ARITH == 0) guard(wr[J][r], glo, gspan, bad);
+            }
         }
         // One half-sweep stage on plane z for the thread's R sites: the colour being updated reads the other colour's
         // window (D, C, U = planes z-1, z, z+1 at the own sites), the neighbours on plane z in shared memory at OFF and
@@ -336,10 +423,11 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
 }
 
 template <typename T>
-size_t smem_bytes_t()
+size_t smem_bytes_t(bool corr)
 {
     const size_t guard_al = ((size_t)PBox<T>::GUARD * sizeof(T) + 127) / 128 * 128;
-    return (size_t)PBox<T>::NSLOT * PBox<T>::SLOT * sizeof(T) + 2 * guard_al + NRING * sizeof(uint64_t);
+    return (size_t)PBox<T>::NSLOT * PBox<T>::SLOT * sizeof(T) + 2 * guard_al + (corr ? (size_t)NCR * CBox<T>::CSLOT * sizeof(T) : 0) +
+           (NRING + NCR) * sizeof(uint64_t);
 }
 
 // Exponent window of the range check, h = 2^-k.  Where the scaled formula could differ from the reference:
@@ -375,22 +463,21 @@ template <> void guard_window<float>(double h2, unsigned* glo, unsigned* gspan)
     *gspan = H - L;
 }
 
-template <typename T, int ARITH>
-int launch_k(cudaStream_t s, const PipeMaps& m, const T* v_in, const T* f, T* v_out, mg_geom3d g, mg_coef3d c, dim3 grid, int zchunk,
-             int zlo, int zhi, unsigned int* flag)
+template <typename T, int ARITH, bool CORR>
+int launch_k(cudaStream_t s, const PipeMaps& m, const T* v_in, T* v_out, mg_geom3d g, mg_coef3d c, dim3 grid, int zchunk, int zlo, int zhi,
+             unsigned int* flag, mg_geom3d gc)
 {
-    MG_SET_SMEM_LIMIT((k_relax_pipe2<T, ARITH>), smem_bytes_t<T>());
+    MG_SET_SMEM_LIMIT((k_relax_pipe2<T, ARITH, CORR>), smem_bytes_t<T>(CORR));
     unsigned glo, gspan;
     guard_window<T>(c.hx2, &glo, &gspan);
     const T y6 = T(1) / T(6);
-    (void)f;  // f only enters through its tensor maps
-    k_relax_pipe2<T, ARITH><<<grid, NT, smem_bytes_t<T>(), s>>>(m, v_in, v_out, g, (T)c.hx2, y6, zchunk, zlo, zhi, glo, gspan, flag);
+    k_relax_pipe2<T, ARITH, CORR><<<grid, NT, smem_bytes_t<T>(CORR), s>>>(m, v_in, v_out, g, (T)c.hx2, y6, zchunk, zlo, zhi, glo, gspan, flag, gc);
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 
 template <typename T>
-int launch(cudaStream_t s, const void* const maps3[3], const T* v_in, const T* f, T* v_out, mg_geom3d g, mg_coef3d c, int zlo, int zhi,
-           int arith, unsigned int* flag)
+int launch(cudaStream_t s, const void* const maps3[3], const void* const cmaps2[2], const mg_geom3d* gc, const T* v_in, T* v_out, mg_geom3d g,
+           mg_coef3d c, int zlo, int zhi, int arith, unsigned int* flag)
 {
     if (zhi <= zlo) return 0;
     const int nz = zhi - zlo;
@@ -398,6 +485,10 @@ int launch(cudaStream_t s, const void* const maps3[3], const T* v_in, const T* f
     memcpy(&m.vblack, maps3[0], sizeof(CUtensorMap));
     memcpy(&m.f[0], maps3[1], sizeof(CUtensorMap));
     memcpy(&m.f[1], maps3[2], sizeof(CUtensorMap));
+    const bool corr = cmaps2 && cmaps2[0] && cmaps2[1] && gc;
+    memcpy(&m.cv[0], corr ? cmaps2[0] : maps3[0], sizeof(CUtensorMap));
+    memcpy(&m.cv[1], corr ? cmaps2[1] : maps3[0], sizeof(CUtensorMap));
+    const mg_geom3d gcv = corr ? *gc : g;
     const int tx = ((g.n + 1) / 2 + TXO - 1) / TXO, ty = (g.n + TYO - 1) / TYO;
     // z chunks: every chunk pays 2*ZH planes of warm-up plus the pipeline depth; more chunks balance the waves of one-CTA SMs
     int sms = 148;
@@ -418,8 +509,12 @@ int launch(cudaStream_t s, const void* const maps3[3], const T* v_in, const T* f
     }
     const int zchunk = (nz + nchunk - 1) / nchunk;
     dim3 grid(tx, ty, (nz + zchunk - 1) / zchunk);
-    if (arith) return launch_k<T, 1>(s, m, v_in, f, v_out, g, c, grid, zchunk, zlo, zhi, flag);
-    return launch_k<T, 0>(s, m, v_in, f, v_out, g, c, grid, zchunk, zlo, zhi, flag);
+    if (corr) {
+        if (arith) return launch_k<T, 1, true>(s, m, v_in, v_out, g, c, grid, zchunk, zlo, zhi, flag, gcv);
+        return launch_k<T, 0, true>(s, m, v_in, v_out, g, c, grid, zchunk, zlo, zhi, flag, gcv);
+    }
+    if (arith) return launch_k<T, 1, false>(s, m, v_in, v_out, g, c, grid, zchunk, zlo, zhi, flag, gcv);
+    return launch_k<T, 0, false>(s, m, v_in, v_out, g, c, grid, zchunk, zlo, zhi, flag, gcv);
 }
 
 }  // namespace
@@ -428,10 +523,15 @@ int launch(cudaStream_t s, const void* const maps3[3], const T* v_in, const T* f
    on each side of them).  maps3: tensor maps of {v_in colour 1, f colour 0, f colour 1} with box (MGK3D_PP_BOX_I(esize), MGK3D_PP_BOX_Y, 1).
    Requires c.fast_den and hx2 == hy2 == hz2 (checked by the caller).  arith 0: bit-exact, *flag is raised when a value
    left the range in which the scaled formula is provably identical to the reference's (the caller enqueues the
-   conditional literal-arithmetic pass after this one); arith 1: MG_ARITH_FAST. */
+   conditional literal-arithmetic pass after this one); arith 1: MG_ARITH_FAST.
+   coarse_maps2 / gc: NULL, or the tensor maps of the two colour arrays of the next coarser level's v with box
+   (MGK3D_PP_CBOX_I(esize), MGK3D_PP_CBOX_Y, 1) and that level's geometry: the pass then starts from
+   v + Interpolate(coarse v) on the interior colour-1 points (prolongation + correction folded into the load stage). */
 extern "C" int mgk3d_relax_pipe2(cudaStream_t s, int dtype, const void* const maps3[3], const void* v_in, const void* f, void* v_out,
-                                 mg_geom3d g, mg_coef3d c, int zl_lo, int zl_hi, int arith, unsigned int* flag)
+                                 mg_geom3d g, mg_coef3d c, int zl_lo, int zl_hi, int arith, unsigned int* flag, const void* const coarse_maps2[2],
+                                 const mg_geom3d* gc)
 {
-    if (dtype == 0) return launch<float>(s, maps3, (const float*)v_in, (const float*)f, (float*)v_out, g, c, zl_lo, zl_hi, arith, flag);
-    return launch<double>(s, maps3, (const double*)v_in, (const double*)f, (double*)v_out, g, c, zl_lo, zl_hi, arith, flag);
+    (void)f;  // f only enters through its tensor maps
+    if (dtype == 0) return launch<float>(s, maps3, coarse_maps2, gc, (const float*)v_in, (float*)v_out, g, c, zl_lo, zl_hi, arith, flag);
+    return launch<double>(s, maps3, coarse_maps2, gc, (const double*)v_in, (double*)v_out, g, c, zl_lo, zl_hi, arith, flag);
 }

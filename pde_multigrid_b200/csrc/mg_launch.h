@@ -87,8 +87,13 @@ int mgk3d_relax_fused2(cudaStream_t s, int dtype, const void* const maps4[4], vo
 #define MGK3D_PP_PADL(esize) ((int)(esize) == 8 ? 0 : 2)
 #define MGK3D_PP_BOX_I(esize) (32 + 2 * MGK3D_PP_PADL(esize))
 #define MGK3D_PP_BOX_Y (MGK3D_PP_R * MGK3D_PP_NW)
+#define MGK3D_PP_CBOX_I(esize) ((int)(esize) == 8 ? 18 : 20)
+#define MGK3D_PP_CBOX_Y (MGK3D_PP_R * MGK3D_PP_NW / 2 + 1)
+/* coarse_maps2 / gc: NULL, or the next coarser level's v (tensor maps of its two colour arrays with box (MGK3D_PP_CBOX_I(esize),
+   MGK3D_PP_CBOX_Y, 1)) and geometry: prolongation + correction of the colour-1 points folded into the load stage of the pass */
 int mgk3d_relax_pipe2(cudaStream_t s, int dtype, const void* const maps3[3], const void* v_in, const void* f, void* v_out,
-                      mg_geom3d g, mg_coef3d c, int zl_lo, int zl_hi, int arith, unsigned int* flag);
+                      mg_geom3d g, mg_coef3d c, int zl_lo, int zl_hi, int arith, unsigned int* flag, const void* const coarse_maps2[2],
+                      const mg_geom3d* gc);
 /* the coarse tail of a V-cycle in one launch (mg3d_tail.cu): V(v1,v2) on the sub-hierarchy g[0..nlev-1], g[0].n <=
    MGK3D_TAIL_N, every level resident in one CTA's shared memory */
 #define MGK3D_TAIL_N 17
@@ -130,8 +135,9 @@ int mgk3d_residual_restrict_tma(cudaStream_t s, int dtype, const void* tmap_v_c0
                                 int czl_lo, int czl_hi);
 /* fine interior = Interpolate(coarse) (add == 0) or fine interior += Interpolate(coarse) (add != 0);
    colour_mask 3 = every point, 2 = the colour-1 points only (see k_interp_octet) */
+/* cond: NULL, or a device word: the launch does nothing unless it is nonzero (the exact fallback of mgk3d_relax_pipe2) */
 int mgk3d_interpolate(cudaStream_t s, int dtype, void* fine, mg_geom3d gf, const void* coarse, mg_geom3d gc, int add,
-                      int colour_mask, int zl_lo, int zl_hi);
+                      int colour_mask, int zl_lo, int zl_hi, const unsigned int* cond);
 /* fine interior += err interior (ApplyCorrection on two fine arrays) */
 int mgk3d_apply_correction(cudaStream_t s, int dtype, void* fine, const void* err, mg_geom3d g, int zl_lo, int zl_hi);
 /* setToValue */

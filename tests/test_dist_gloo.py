@@ -179,14 +179,23 @@ def ensure_v_ghosts(L, rank, world):
         L.vg_valid = True
 
 
-def relax_pipe(L, rank, world, nu):
-    """mg3d_host.c::relax_level on a level the temporally blocked smoother takes: pairs of sweeps per pass, a remaining
-    single sweep colour by colour."""
+def relax_pipe(L, rank, world, nu, correct_from=None):
+    """mg3d_host.c::relax_level_ex on a level the temporally blocked smoother takes: pairs of sweeps per pass, a remaining
+    single sweep colour by colour.  correct_from: the coarse level whose prolongation + correction (colour 1 only) the FIRST
+    pass applies on the fly, on the owned planes AND on its four halo planes per side (the coarse level was exchanged two planes
+    up and three down for that), without ever writing the corrected input back."""
     n = L.n
     while nu >= 2:
         if not L.vg_deep:  # InitV / the zeroed coarse v left valid ghosts of full depth
             exchange(L, L.v, rank, world, 4, 4, 1)
         w = L.v.copy()
+        if correct_from is not None:
+            C = correct_from
+            if C.dist:
+                exchange(C, C.v, rank, world, 2, 3)
+                C.vg_valid = True
+            interpolate_add(w, C.v, max(L.a - 4, 1), min(L.b + 4, n - 1), 1)
+            correct_from = None
         for colour, e in ((0, 3), (1, 2), (0, 1), (1, 0)):  # R1, B1, R2, B2 on the owned planes grown by e
             lo, hi = max(L.a - e, 1), min(L.b + e, n - 1)
             relax_colour(w, L.f, colour, lo, hi)
@@ -314,6 +323,9 @@ def vcycle(levels, l, rank, world, engine_schedule=True, smoother="gs"):
             dist.broadcast(top, world - 1)
             C.f[C.n - 1] = top.numpy()[0]
         vcycle(levels, l + 1, rank, world, engine_schedule, smoother)
+        if pipe and NU_P >= 2:  # prolongation + correction ride on the first pass of the post-smoothing
+            relax_pipe(L, rank, world, NU_P, correct_from=C)
+            return
         lo, hi = L.interior()
         if smoother == "pipe":
             ensure_v_ghosts(C, rank, world)
