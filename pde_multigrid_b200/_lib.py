@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libmg_b200.so")
+# MG_B200_LIB: another build of the same library (the -DMG_DEBUG_BOUNDS one, tests/test_debug_bounds.py)
+SO_PATH = os.environ.get("MG_B200_LIB") or os.path.join(HERE, "libmg_b200.so")
 
 MG_OK, MG_ERR_ARG, MG_ERR_CUDA, MG_ERR_NOMEM, MG_ERR_STATE, MG_ERR_COMM = 0, 1, 2, 3, 4, 5
 MG_F32, MG_F64 = 0, 1

@@ -29,11 +29,19 @@ def up_to_date():
     return all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps)
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and up_to_date():
+SO_DEBUG = os.path.join(HERE, "libmg_b200_dbg.so")
+
+
+def build_debug_bounds(verbose=False):
+    """libmg_b200_dbg.so: the same library with -DMG_DEBUG_BOUNDS (index asserts in the 3D kernels, csrc/mg3d_device.cuh)."""
+    return build(force=True, verbose=verbose, extra=("-DMG_DEBUG_BOUNDS",), so=SO_DEBUG, objdir=os.path.join(HERE, "build", "dbg"))
+
+
+def build(force=False, verbose=False, extra=(), so=SO, objdir=None):
+    if so == SO and not force and up_to_date():
         return SO
     objs = []
-    objdir = os.path.join(HERE, "build")
+    objdir = objdir or os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     common = ["-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
               "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall", "-I", os.path.join(HERE, "..", "include"), "-I", CSRC]
@@ -57,10 +65,13 @@ def build(force=False, verbose=False, extra=()):
             print(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [NVCC, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
+    cmd = [NVCC, "-shared", "-o", so] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     subprocess.run(cmd, check=True)
-    return SO
+    return so
 
 
 if __name__ == "__main__":
-    print(build(force="-f" in sys.argv, verbose="-v" in sys.argv))
+    if "--debug-bounds" in sys.argv:
+        print(build_debug_bounds(verbose="-v" in sys.argv))
+    else:
+        print(build(force="-f" in sys.argv, verbose="-v" in sys.argv))

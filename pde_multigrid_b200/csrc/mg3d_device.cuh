@@ -20,6 +20,26 @@
         }                                                                                                       \
     } while (0)
 
+// -DMG_DEBUG_BOUNDS (python -m pde_multigrid_b200.build --debug-bounds -> libmg_b200_dbg.so): every global-memory access of
+// the 3D kernels asserts that its (half-index, row, plane) lies inside the field it addresses; otherwise it reports and retires the thread -- the
+// stand-in for compute-sanitizer memcheck, which is closed on the GPU pool (tests/test_debug_bounds.py runs the suite's
+// small cases against this build).  Compiled out of the product library.
+#ifdef MG_DEBUG_BOUNDS
+#include <stdio.h>
+#define MG_CHK(cond)                                                                                              \
+    do {                                                                                                          \
+        if (!(cond)) {                                                                                            \
+            printf("MG_DEBUG_BOUNDS: %s violated at %s:%d (block %d,%d,%d thread %d)\n", #cond, __FILE__, __LINE__, \
+                   (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x);                          \
+            asm volatile("exit;"); /* the thread ends here: the bad access never happens, the GPU takes no fault */  \
+        }                                                                                                         \
+    } while (0)
+#else
+#define MG_CHK(cond) ((void)0)
+#endif
+// site (half-index i, row y, local plane zl) inside the stored part of a colour array
+#define MG_CHK_SITE(g, i, y, zl) MG_CHK((i) >= 0 && (i) < (g).hp && (y) >= 0 && (y) < (g).n && (zl) >= 0 && (zl) < (g).nzl)
+
 namespace mg3 {
 using namespace mgx;
 
@@ -41,6 +61,7 @@ Coef3<T> narrow(const mg_coef3d& c)
 
 __device__ __forceinline__ long long off3(const mg_geom3d& g, int x, int y, int zl)
 {
+    MG_CHK(x >= 0 && x < g.n && y >= 0 && y < g.n && zl >= 0 && zl < g.nzl);
     const int c = (x + y + g.z0 + zl) & 1;
     return (long long)c * g.cstride + (long long)zl * g.plane + (long long)y * g.hp + (x >> 1);
 }
@@ -102,6 +123,7 @@ template <typename T, bool FAST>
 __device__ __forceinline__ T residual_at(const T* __restrict__ v, const T* __restrict__ f, const mg_geom3d& g, int x, int y,
                                          int zl, const Coef3<T>& c, int corrected)
 {
+    MG_CHK(x >= 1 && x <= g.n - 2 && y >= 1 && y <= g.n - 2 && zl >= 1 && zl <= g.nzl - 2);
     const int col = (x + y + g.z0 + zl) & 1, q = x & 1;
     const long long idx = (long long)zl * g.plane + (long long)y * g.hp + (x >> 1);
     const T* own = v + (long long)col * g.cstride + idx;

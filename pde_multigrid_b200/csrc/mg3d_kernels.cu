@@ -42,6 +42,8 @@ k_relax_colour(T* __restrict__ v, const T* __restrict__ f, mg_geom3d g, Coef3<T>
     const int q = (colour + y + g.z0 + zl) & 1;
     const int x = 2 * i + q;
     if (x < 1 || x > g.n - 2) return;
+    MG_CHK_SITE(g, i, y, zl);
+    MG_CHK(zl >= 1 && zl <= g.nzl - 2 && i + q - 1 >= 0 && i + q < g.hp);
     const long long idx = (long long)zl * g.plane + (long long)y * g.hp + i;
     const T* oth = v + (long long)(colour ^ 1) * g.cstride + idx;
     const long long own = (long long)colour * g.cstride + idx;
@@ -69,6 +71,7 @@ k_jacobi_colour(T* __restrict__ dst, const T* own, const T* __restrict__ oth, co
     const int q = (colour + y + z) & 1;
     const int x = 2 * i + q;
     if (x > g.n - 1) return;
+    MG_CHK_SITE(g, i, y, zl);
     const long long idx = (long long)zl * g.plane + (long long)y * g.hp + i;
     const T old = own[idx];
     const bool interior = x >= 1 && x <= g.n - 2 && y >= 1 && y <= g.n - 2 && z >= 1 && z <= g.n - 2;
@@ -242,6 +245,7 @@ k_interp_octet(T* __restrict__ fine, mg_geom3d gf, const T* __restrict__ coarse,
         cpar[d] = (cx + dx + cy + dy) & 1;
     }
     auto load_plane = [&](int cz, T (&dst)[4]) {
+        MG_CHK(cz - gc.z0 >= 0 && cz - gc.z0 < gc.nzl && cy + 1 < gc.n && ((cx + 1) >> 1) < gc.hp);
         const long long pz = (long long)(cz - gc.z0) * gc.plane;
 #pragma unroll
         for (int d = 0; d < 4; d++) dst[d] = coarse[(long long)((cpar[d] + cz) & 1) * gc.cstride + pz + cbase[d]];
@@ -266,6 +270,7 @@ k_interp_octet(T* __restrict__ fine, mg_geom3d gf, const T* __restrict__ coarse,
                 const int c0 = (oy + oz) & 1;  // colour of the even-x point of the pair: (2cx + y + z) & 1, a compile-time value
                 const long long idx = (long long)zl * gf.plane + (long long)y * gf.hp + cx;
                 const bool ok = zok && y >= 1;  // y <= n-2 holds for every cell row
+                if (ok) MG_CHK_SITE(gf, cx, y, zl);
                 ptr[oz * 4 + oy * 2 + 0] = (ok && cx >= 1 && ((MASK >> c0) & 1)) ? fine + (long long)c0 * gf.cstride + idx : nullptr;
                 ptr[oz * 4 + oy * 2 + 1] = (ok && ((MASK >> (c0 ^ 1)) & 1)) ? fine + (long long)(c0 ^ 1) * gf.cstride + idx : nullptr;
             }

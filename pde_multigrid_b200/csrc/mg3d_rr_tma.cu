@@ -179,6 +179,7 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
     auto load_f = [&](int z, T (&dst)[5]) {
         const int zl = z - gf.z0;
         const unsigned m = (zl >= 0 && zl < nzl) ? fl : 0u;
+        if (m & (F_FA | F_FB)) MG_CHK_SITE(gf, cx0 + lane, 2 * (cy0 + w) + ((m & F_FA) ? 0 : 1), zl);
         dst[0] = (m & F_FA) ? __ldg(fp) : T(0);
         dst[1] = (m & F_FA) ? __ldg(fp + f_c1) : T(0);
         dst[2] = (m & F_FB) ? __ldg(fp + hp) : T(0);
@@ -303,6 +304,7 @@ k_residual_restrict_tma(const __grid_constant__ CUtensorMap map_c0, const __grid
                 });
             }
             const long long ci = ((((fl / F_CP) ^ cz) & 1) ? gc.cstride : 0ll) + (long long)czl * gc.plane + c_base;
+            MG_CHK_SITE(gc, (cx0 + lane) >> 1, cy0 + w, czl);
             cf[ci] = out;
             cv[ci] = T(0);  // setToValue(coarse->h_v, 0, true), N3/MultiGrid3D.cpp:634
         }

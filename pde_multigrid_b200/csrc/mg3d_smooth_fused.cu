@@ -195,7 +195,10 @@ k_relax_fused2(const __grid_constant__ FusedMaps maps, T* __restrict__ v_out, mg
         if (ps >= zs && ps < ze) {
 #pragma unroll
             for (int s = 0; s < OPT; s++)
-                if (st_ok[s]) __stcs(v_out + st_dst[s] + (long long)ps * g.plane, ring[sb[5] + st_src[s]]);
+                if (st_ok[s]) {
+                    MG_CHK(ps >= 0 && ps < g.nzl && st_dst[s] >= 0 && st_dst[s] < g.cstride + g.plane);
+                    __stcs(v_out + st_dst[s] + (long long)ps * g.plane, ring[sb[5] + st_src[s]]);
+                }
         }
     }
     if (cond) {

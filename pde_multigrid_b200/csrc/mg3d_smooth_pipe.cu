@@ -258,7 +258,10 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
             // Dirichlet points of colour 0 on plane p (parity s_r ^ CV ^ 1): exist and are not interior
             const unsigned mz = (p >= 0 && p < g.nzl) ? ((mO >> 16) & ~(((unsigned)(zg - 1) <= (unsigned)(n - 3)) ? mO : 0u)) : 0u;
 #pragma unroll
-            for (int r = 0; r < R; r++) rr_n[r] = ((mz >> r) & 1u) ? __ldg((const T*)(va + goff[r])) : T(0);
+            for (int r = 0; r < R; r++) {
+                if ((mz >> r) & 1u) MG_CHK_SITE(g, i, yr0 + r, p);
+                rr_n[r] = ((mz >> r) & 1u) ? __ldg((const T*)(va + goff[r])) : T(0);
+            }
         }
         if (tid == 0 && (FAST || p - pb + PF < nsteps)) issue((J6 + PF) % NRING, p + PF);
         mbar_wait(&bars[J6], phase);
@@ -387,6 +390,7 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
             const unsigned m0 = zok ? (mO >> 8) : 0u, m1 = zok ? (mU >> 8) : 0u;
 #pragma unroll
             for (int r = 0; r < R; r++) {
+                if (((m0 | m1) >> r) & 1u) MG_CHK_SITE(g, i, yr0 + r, zo);
                 if ((m0 >> r) & 1u) __stcs((T*)(oa + goff[r]), w3[J2][r]);
                 if ((m1 >> r) & 1u) __stcs((T*)(ob + goff[r]), b2[r]);
             }

@@ -78,6 +78,7 @@ k_relax_colour_tma(const __grid_constant__ CUtensorMap map_other, T* __restrict_
         for (int rr = 0; rr < RPT; rr++) {
             const int y = y0 + r0 + rr;
             const int x = 2 * i + ((colour + y + g.z0 + z) & 1);
+            if (y <= g.n - 2 && x >= 1 && x <= g.n - 2) MG_CHK_SITE(g, i, y, z);
             dst[rr] = (y <= g.n - 2 && x >= 1 && x <= g.n - 2) ? __ldg(f_own + zbase + (long long)y * g.hp + i) : T(0);
         }
     };
@@ -108,6 +109,7 @@ k_relax_colour_tma(const __grid_constant__ CUtensorMap map_other, T* __restrict_
             const int q = (colour + y + g.z0 + z) & 1;
             const int x = 2 * i + q;
             if (y <= g.n - 2 && x >= 1 && x <= g.n - 2) {
+                MG_CHK_SITE(g, i, y, z);
                 const int cc = (r + 1) * BW + il + A;  // smem index of (i, y) in a slot
                 const T O = sC[cc - 1 + q], E = sC[cc + q], N = sC[cc - BW], S = sC[cc + BW], D = sD[cc], U = sU[cc];
                 __stcs(v_own + zbase + (long long)y * g.hp + i, relax_point<T, FAST>(O, E, N, S, D, U, fcur[rr], c));
