@@ -119,6 +119,7 @@ struct mg3d_s {
     double omega;   /* weight of MG_SMOOTHER_JACOBI */
     int arith;           /* MG_ARITH_EXACT / MG_ARITH_FAST */
     int no_pipe;         /* MG_B200_NO_PIPE: MG_SMOOTHER_AUTO without temporal blocking (the round-1 default) */
+    int no_deep_merge;   /* MG_B200_NO_DEEP_MERGE: the post-smoothing pass fetches its colour-1 ghosts itself (one more exchange) */
     int no_corr_fuse;    /* MG_B200_NO_CORR_FUSE: prolongation + correction as a kernel of their own even where the pass could take them */
     unsigned int* d_flag; /* {exactness flag of the pipelined smoother, completion counter of its fallback} */
     int no_tail;         /* MG_B200_NO_TAIL: coarse levels as separate launches */
@@ -233,7 +234,18 @@ static char* plane_ptr(const mg3d_t* mg, const mg_level3d* L, void* field, int c
  *   down: my bottom owned plane (if `down` != 0) -> the upper ghost of rank-1
  * colour_mask: bit 0 = colour-0 array, bit 1 = colour-1 array.
  * ---------------------------------------------------------------------------------------------- */
+static int exchange_p2p2(mg3d_t* mg, int level, void* field, const int up2[2], const int down2[2], cudaStream_t xs);
+
 static int exchange_p2p(mg3d_t* mg, int level, void* field, int colour_mask, int depth_up, int depth_down, cudaStream_t xs)
+{
+    const int up2[2] = {(colour_mask & 1) ? depth_up : 0, (colour_mask & 2) ? depth_up : 0};
+    const int down2[2] = {(colour_mask & 1) ? depth_down : 0, (colour_mask & 2) ? depth_down : 0};
+    return exchange_p2p2(mg, level, field, up2, down2, xs);
+}
+
+/* per-colour depths: up2[c] top owned planes of colour c go to the lower ghosts of rank+1, down2[c] bottom owned planes to the
+   upper ghosts of rank-1 (0 = that colour does not travel in that direction); still ONE launch and one flag per direction */
+static int exchange_p2p2(mg3d_t* mg, int level, void* field, const int up2[2], const int down2[2], cudaStream_t xs)
 {
     mg_level3d* L = &mg->lv[level];
     mg_p2p* q = &mg->p2p;
@@ -246,29 +258,29 @@ static int exchange_p2p(mg3d_t* mg, int level, void* field, int colour_mask, int
     unsigned long long bytes[4] = {0, 0, 0, 0};
     unsigned int* raise[2] = {0, 0};
     int nseg = 0;
-    const int send_up = r + 1 < P && depth_up > 0, send_down = r > 0 && depth_down > 0;
+    const int any_up = up2[0] > 0 || up2[1] > 0, any_down = down2[0] > 0 || down2[1] > 0;
+    const int send_up = r + 1 < P && any_up, send_down = r > 0 && any_down;
     for (int col = 0; col < 2; col++) {
-        if (!(colour_mask & (1 << col))) continue;
-        if (send_up) { /* my top planes -> the lower ghosts of rank+1 */
+        if (send_up && up2[col] > 0) { /* my top planes -> the lower ghosts of rank+1 */
             const mg_geom3d* ng = &q->nb_geom[1][level];
-            src[nseg] = plane_ptr(mg, L, field, col, L->own_hi - depth_up);
+            src[nseg] = plane_ptr(mg, L, field, col, L->own_hi - up2[col]);
             dst[nseg] = q->peer_arena[1] + q->nb_off[1][3 * level + fi] +
-                        ((size_t)col * (size_t)ng->cstride + (size_t)(q->nb_own[1][2 * level] - depth_up) * (size_t)ng->plane) * es;
-            bytes[nseg++] = pb * depth_up;
-            mg->halo_bytes += (long long)(pb * depth_up);
+                        ((size_t)col * (size_t)ng->cstride + (size_t)(q->nb_own[1][2 * level] - up2[col]) * (size_t)ng->plane) * es;
+            bytes[nseg++] = pb * up2[col];
+            mg->halo_bytes += (long long)(pb * up2[col]);
         }
-        if (send_down) { /* my bottom planes -> the upper ghosts of rank-1 */
+        if (send_down && down2[col] > 0) { /* my bottom planes -> the upper ghosts of rank-1 */
             const mg_geom3d* ng = &q->nb_geom[0][level];
             src[nseg] = plane_ptr(mg, L, field, col, L->own_lo);
             dst[nseg] = q->peer_arena[0] + q->nb_off[0][3 * level + fi] +
                         ((size_t)col * (size_t)ng->cstride + (size_t)q->nb_own[0][2 * level + 1] * (size_t)ng->plane) * es;
-            bytes[nseg++] = pb * depth_down;
-            mg->halo_bytes += (long long)(pb * depth_down);
+            bytes[nseg++] = pb * down2[col];
+            mg->halo_bytes += (long long)(pb * down2[col]);
         }
     }
     if (send_up) raise[1] = q->peer_flags[1] + 0;    /* its "from below" word */
     if (send_down) raise[0] = q->peer_flags[0] + 32; /* its "from above" word */
-    const int recv_below = r > 0 && depth_up > 0, recv_above = r + 1 < P && depth_down > 0;
+    const int recv_below = r > 0 && any_up, recv_above = r + 1 < P && any_down;
     if (xs == mg->stream) PROF_BEGIN(mg, level, MG_OP_OTHER);
     MG_LAUNCH(mg->launches, mgk_halo_exchange(xs, src, dst, bytes, raise, recv_below, recv_above, q->flags));
     if (xs == mg->stream) PROF_END(mg);
@@ -317,6 +329,19 @@ static int exchange(mg3d_t* mg, int level, void* field, int colour_mask, int dep
     return exchange_on(mg, level, field, colour_mask, depth_up, depth_down, mg->stream);
 }
 
+/* one exchange with different depths for the two colours (one launch on the NVLink path, two grouped exchanges through NCCL) */
+static int exchange2(mg3d_t* mg, int level, void* field, const int up2[2], const int down2[2])
+{
+    mg_level3d* L = &mg->lv[level];
+    if (!L->dist) return MG_OK;
+    if (mg->p2p.enabled && (field == L->vbuf[0] || field == L->vbuf[1] || field == L->f))
+        return exchange_p2p2(mg, level, field, up2, down2, mg->stream);
+    int st = MG_OK;
+    for (int col = 0; col < 2 && !st; col++)
+        if (up2[col] > 0 || down2[col] > 0) st = exchange_on(mg, level, field, 1 << col, up2[col], down2[col], mg->stream);
+    return st;
+}
+
 /* The temporally blocked smoother writes the planes a rank owns into the OTHER v buffer and reads, of that buffer's ghost
    planes, nothing -- but a later pass out of it reads the Dirichlet points of colour 0 on its ghost planes (the exchange in
    front of a pass only moves colour 1).  Dirichlet values never change, so it is enough that whoever defines v on every stored
@@ -352,18 +377,25 @@ static int ensure_v_ghosts(mg3d_t* mg, int level)
    slab into its full-size array; gather them so that every rank holds the whole level.  The top plane
    n-1 (not covered by the equal shares) comes from the last rank when `top_from_last` is set, else the
    caller fills it. */
-static int gather_level(mg3d_t* mg, int level, void* field, int top_from_last)
+#define MG_TOP_NONE 0
+#define MG_TOP_FROM_LAST 1
+#define MG_TOP_ZERO 2
+static int gather_level(mg3d_t* mg, int level, void* field, int top_mode)
 {
     mg_level3d* L = &mg->lv[level];
     const int P = mg->nranks, m = (L->g.n - 1) / P;
     const size_t pe = (size_t)L->g.plane;
-    int st = MG_OK;
+    int st = MG_OK, st2;
     PROF_BEGIN(mg, level, MG_OP_OTHER);
+    /* both colour arrays in ONE NCCL group: one fused launch instead of two */
+    st = mg_comm_group_start(mg->comm);
     for (int col = 0; col < 2 && !st; col++) {
         st = mg_comm_allgather_inplace(mg->comm, plane_ptr(mg, L, field, col, 0), pe * m, mg->dtype, mg->stream);
         mg->halo_bytes += (long long)(pe * m * mg_esize(mg->dtype));
     }
-    if (!st && top_from_last) {
+    st2 = mg_comm_group_end(mg->comm);
+    if (!st) st = st2;
+    if (!st && top_mode == MG_TOP_FROM_LAST) {
         st = mg_comm_group_start(mg->comm);
         for (int col = 0; col < 2 && !st; col++) {
             char* top = plane_ptr(mg, L, field, col, L->g.n - 1);
@@ -373,8 +405,14 @@ static int gather_level(mg3d_t* mg, int level, void* field, int top_from_last)
                 st = mg_comm_recv(mg->comm, top, pe, mg->dtype, P - 1, mg->stream);
             }
         }
-        int st2 = mg_comm_group_end(mg->comm);
+        st2 = mg_comm_group_end(mg->comm);
         if (!st) st = st2;
+    } else if (!st && top_mode == MG_TOP_ZERO && mg->rank != P - 1) {
+        /* the restricted residual is +0 on the Dirichlet plane n-1 (injection of the zero boundary residual, N3/MultiGrid3D.cpp:113-119,
+           :705): nothing to fetch, every rank but the last (which produced it) writes the zeros itself */
+        int k = mgk3d_set(mg->stream, mg->dtype, field, L->g, 0.0, 1, L->g.n - 1, L->g.n);
+        if (k < 0) st = mg_fail(MG_ERR_CUDA, "set launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        else mg->launches += k;
     }
     PROF_END(mg);
     return st;
@@ -522,6 +560,7 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
     mg->no_tail = getenv("MG_B200_NO_TAIL") != NULL;
     mg->no_pipe = getenv("MG_B200_NO_PIPE") != NULL;
     mg->no_corr_fuse = getenv("MG_B200_NO_CORR_FUSE") != NULL;
+    mg->no_deep_merge = getenv("MG_B200_NO_DEEP_MERGE") != NULL;
     mg->arith = MG_ARITH_EXACT;
     mg->full_correction = getenv("MG_B200_FULL_CORRECTION") != NULL;
     memcpy(mg->range, range, sizeof mg->range);
@@ -1226,12 +1265,12 @@ int mg3d_halo_benchmark(mg3d_t* mg, int level, int colour_mask, int depth_up, in
 }
 
 /* what follows a restriction onto level+1: refresh ghosts (distributed) or gather (first agglomerated level) */
-static int after_restrict(mg3d_t* mg, int fine_level, void* coarse_field, int defer)
+static int after_restrict(mg3d_t* mg, int fine_level, void* coarse_field, int defer, int top_mode)
 {
     const mg_level3d *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
     if (C->dist && defer) return exchange_deferred(mg, fine_level + 1, coarse_field, 3, MG_GHOST_LO, MG_GHOST_HI);
     if (C->dist) return exchange(mg, fine_level + 1, coarse_field, 3, MG_GHOST_LO, MG_GHOST_HI);
-    if (F->dist) return gather_level(mg, fine_level + 1, coarse_field, 1);
+    if (F->dist) return gather_level(mg, fine_level + 1, coarse_field, top_mode);
     return MG_OK;
 }
 
@@ -1248,7 +1287,7 @@ int mg3d_restrict(mg3d_t* mg, int fine_level, int field)
     PROF_BEGIN(mg, fine_level, MG_OP_OTHER);
     MG_LAUNCH(mg->launches, mgk3d_restrict(mg->stream, mg->dtype, field_ptr(F, field), F->g, field_ptr(C, field), C->g, lo, hi));
     PROF_END(mg);
-    st = after_restrict(mg, fine_level, field_ptr(C, field), 0);
+    st = after_restrict(mg, fine_level, field_ptr(C, field), 0, MG_TOP_FROM_LAST);
     if (!st && field == MG_FIELD_V) C->vg_valid = C->vg_deep = 1;
     return st;
 }
@@ -1262,7 +1301,15 @@ static int residual_restrict_level(mg3d_t* mg, int fine_level, int defer_f_halo)
     coarse_share(mg, fine_level, &lo, &hi);
     /* the fused kernel reads v two planes below the slab: only plane a-2 is stale after the smoother's exchanges */
     if (F->dist) {
-        if ((st = exchange(mg, fine_level, F->v, 3, 2, F->vg_valid ? 0 : 1))) return st;
+        if (level_takes_pipe(mg, F) && !F->vg_deep && !mg->no_deep_merge) {
+            /* v does not change between here and the first pass of the post-smoothing (prolongation and correction ride on that
+               pass), so the four colour-1 planes that pass needs from each neighbour travel now, in the same launch: one
+               exchange fewer on the way up */
+            const int up2[2] = {2, MG_GHOST_LO}, down2[2] = {F->vg_valid ? 0 : 1, MG_GHOST_HI};
+            if ((st = exchange2(mg, fine_level, F->v, up2, down2))) return st;
+            F->vg_deep = 1;
+        } else if ((st = exchange(mg, fine_level, F->v, 3, 2, F->vg_valid ? 0 : 1)))
+            return st;
         F->vg_valid = 1;
     }
     PROF_BEGIN(mg, fine_level, MG_OP_RESIDUAL_RESTRICT);
@@ -1283,7 +1330,7 @@ static int residual_restrict_level(mg3d_t* mg, int fine_level, int defer_f_halo)
     }
     C->vg_valid = C->vg_deep = 1;
     PROF_END(mg);
-    return after_restrict(mg, fine_level, C->f, defer_f_halo);
+    return after_restrict(mg, fine_level, C->f, defer_f_halo, MG_TOP_ZERO);
 }
 
 int mg3d_residual_restrict(mg3d_t* mg, int fine_level)
@@ -1483,7 +1530,7 @@ static int fmg_rec(mg3d_t* mg, int level, int v0, int v1, int v2)
         PROF_BEGIN(mg, level, MG_OP_OTHER);
         MG_LAUNCH(mg->launches, mgk3d_restrict(mg->stream, mg->dtype, F->f, F->g, C->f, C->g, lo, hi));
         PROF_END(mg);
-        if ((st = after_restrict(mg, level, C->f, 0))) return st;
+        if ((st = after_restrict(mg, level, C->f, 0, MG_TOP_FROM_LAST))) return st;
         if ((st = fmg_rec(mg, level + 1, v0, v1, v2))) return st;
         if ((st = interpolate_level(mg, level, 0, 3, 0))) return st;
     } else {

@@ -276,8 +276,8 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
         constexpr int X1W = (XB + 0 + E) * SLOT, X1R = (XB + 0 + (E ^ 1)) * SLOT;
         constexpr int X2W = (XB + 2 + (E ^ 1)) * SLOT, X2R = (XB + 2 + E) * SLOT;
         constexpr int X3W = (XB + 4 + E) * SLOT, X3R = (XB + 4 + (E ^ 1)) * SLOT;
-        if (CORR) {
-            static_assert(R == 2, "the fused prolongation pairs the thread's even row (oy = 0) with its odd row (oy = 1)");
+        if constexpr (CORR) {
+            static_assert(!CORR || R == 2, "the fused prolongation pairs the thread's even row (oy = 0) with its odd row (oy = 1)");
             const int zg = g.z0 + p, Z0 = zg >> 1, oz = zg & 1;
             if (tid == 0 && oz == 0 && Z0 + NCR - 2 <= Zlast && Z0 + NCR - 2 > Zb + NCR - 2) issue_coarse(Z0 + NCR - 2);
             const int k0 = Z0 - Zb;
@@ -322,8 +322,7 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const T rawv = sb[OFF_P + r * W];
-                wr[J][r] = (FAST || ((mzc >> r) & 1u)) ? add(rawv, r ? eb : ea) : rawv;
-                sw[OFF_P + r * W] = wr[J][r];  // the neighbours read this plane one step from now
+                wr[J][r] = (FAST || ((mzc >> r) & 1u)) ? add(rawv, r ? eb : ea) : rawv;  // published at the end of the step
                 if (ARITH == 0) guard(wr[J][r], glo, gspan, bad);
             }
         } else {
@@ -369,16 +368,10 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
         using GFN = integral_constant<bool, false>;
         // R1 @ p-1: colour 0 from raw colour 1
         stage(p - 1, integral_constant<int, OFF_C>{}, integral_constant<int, F0A>{}, GFY{}, wr[J1], wr[J2], wr[J], rkeep, w1[J2]);
-#pragma unroll
-        for (int r = 0; r < R; r++) sw[X1W + r * W] = w1[J2][r];
         // B1 @ p-2: colour 1 from R1
         stage(p - 2, integral_constant<int, X1R>{}, integral_constant<int, F1A>{}, GFY{}, w1[J], w1[J1], w1[J2], wr[J1], w2[J1]);
-#pragma unroll
-        for (int r = 0; r < R; r++) sw[X2W + r * W] = w2[J1][r];
         // R2 @ p-3: colour 0 from B1
         stage(p - 3, integral_constant<int, X2R>{}, integral_constant<int, F0B>{}, GFN{}, w2[J2], w2[J], w2[J1], w1[J], w3[J]);
-#pragma unroll
-        for (int r = 0; r < R; r++) sw[X3W + r * W] = w3[J][r];
         // B2 @ p-4: colour 1 from R2; plane p-4 is final
         T b2[R];
         stage(p - 4, integral_constant<int, X3R>{}, integral_constant<int, F1B>{}, GFN{}, w3[J1], w3[J2], w3[J], w2[J2], b2);
@@ -394,6 +387,16 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
                 if ((m0 >> r) & 1u) __stcs((T*)(oa + goff[r]), w3[J2][r]);
                 if ((m1 >> r) & 1u) __stcs((T*)(ob + goff[r]), b2[r]);
             }
+        }
+        // Publish this step's stage outputs (and, CORR, the corrected raw plane) for the neighbours' reads of the NEXT step.  All
+        // shared-memory stores of a step come after all of its loads: the four stages only read what the previous step
+        // published (different exchange slots), so the compiler is free to hoist every load and interleave the four stages.
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (CORR) sw[OFF_P + r * W] = wr[J][r];
+            sw[X1W + r * W] = w1[J2][r];
+            sw[X2W + r * W] = w2[J1][r];
+            sw[X3W + r * W] = w3[J][r];
         }
         va += pbytes; oa += pbytes; ob += pbytes;
         __syncthreads();
@@ -506,14 +509,16 @@ int launch(cudaStream_t s, const void* const maps3[3], const void* const cmaps2[
     double best = 1e30;
     for (int k = 1; k <= 16; k++) {
         const int zc = (nz + k - 1) / k;
-        if (k > 1 && zc < 32) break;
+        if (k > 1 && zc < 8) break;
         const long long ctas = (long long)tx * ty * ((nz + zc - 1) / zc);
         const double cost = (double)((ctas + sms - 1) / sms) * (zc + 2 * ZH + 3);
         if (cost < best) { best = cost; nchunk = k; }
     }
     const int zchunk = (nz + nchunk - 1) / nchunk;
     dim3 grid(tx, ty, (nz + zchunk - 1) / zchunk);
-    if (corr) {
+    if constexpr (R != 2) {
+        if (corr) return -1;
+    } else if (corr) {
         if (arith) return launch_k<T, 1, true>(s, m, v_in, v_out, g, c, grid, zchunk, zlo, zhi, flag, gcv);
         return launch_k<T, 0, true>(s, m, v_in, v_out, g, c, grid, zchunk, zlo, zhi, flag, gcv);
     }

@@ -82,8 +82,12 @@ int mgk3d_relax_fused2(cudaStream_t s, int dtype, const void* const maps4[4], vo
    caller follows up with mgk3d_relax_fused2(..., cond = flag)); arith 1: MG_ARITH_FAST */
 #define MGK3D_PP_HXI 2
 #define MGK3D_PP_HY 4
+#ifndef MGK3D_PP_R
 #define MGK3D_PP_R 2
+#endif
+#ifndef MGK3D_PP_NW
 #define MGK3D_PP_NW 16
+#endif
 #define MGK3D_PP_PADL(esize) ((int)(esize) == 8 ? 0 : 2)
 #define MGK3D_PP_BOX_I(esize) (32 + 2 * MGK3D_PP_PADL(esize))
 #define MGK3D_PP_BOX_Y (MGK3D_PP_R * MGK3D_PP_NW)

@@ -297,7 +297,11 @@ def vcycle(levels, l, rank, world, engine_schedule=True, smoother="gs"):
     smooth()
     if l + 1 < len(levels):
         C = levels[l + 1]
-        if smoother == "pipe":                                    # two planes up; one down as well if the ghosts are stale
+        if pipe and not L.vg_deep:                                # one launch: colour 0 two up / one down (if stale), colour 1 four
+            exchange(L, L.v, rank, world, 2, 0 if L.vg_valid else 1, 0)   # each way -- what the first pass of the post-smoothing
+            exchange(L, L.v, rank, world, 4, 4, 1)                # reads of its neighbours (v does not change until then)
+            L.vg_valid = L.vg_deep = True
+        elif smoother == "pipe":                                  # two planes up; one down as well if the ghosts are stale
             exchange(L, L.v, rank, world, 2, 0 if L.vg_valid else 1)
             L.vg_valid = True
         else:
@@ -319,9 +323,8 @@ def vcycle(levels, l, rank, world, engine_schedule=True, smoother="gs"):
             dist.all_gather(parts, torch.from_numpy(C.f[rank * m:(rank + 1) * m].copy()))
             for r, p in enumerate(parts):
                 C.f[r * m:(r + 1) * m] = p.numpy()
-            top = torch.from_numpy(C.f[C.n - 1:C.n].copy())
-            dist.broadcast(top, world - 1)
-            C.f[C.n - 1] = top.numpy()[0]
+            if rank != world - 1:                                 # the restricted residual is +0 on the Dirichlet plane n-1:
+                C.f[C.n - 1] = 0.0                                # written locally (mg3d_host.c::gather_level, MG_TOP_ZERO)
         vcycle(levels, l + 1, rank, world, engine_schedule, smoother)
         if pipe and NU_P >= 2:  # prolongation + correction ride on the first pass of the post-smoothing
             relax_pipe(L, rank, world, NU_P, correct_from=C)
