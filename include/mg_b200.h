@@ -73,6 +73,7 @@ extern "C" {
 typedef struct mg3d_s mg3d_t;
 typedef struct mg2d_s mg2d_t;
 typedef struct mg1d_s mg1d_t;
+typedef struct mg3b_s mg3b_t;
 
 const char* mg_last_error(void);
 const char* mg_version(void);
@@ -159,6 +160,35 @@ int mg3d_apply_correction_device(mg3d_t* mg, void* d_fine, const int fsize_xyz[3
 int mg3d_set_device(mg3d_t* mg, void* d_v, const int size_xyz[3], double value, int modify_border); /* Set(d_v, d_sizeXYZ, value, modifyBorder) */
 /* end-to-end: upload finest v,f -> `cycles` x VCycle(0,v1,v2) -> download finest v */
 int mg3d_vcycle_host(mg3d_t* mg, void* v_host, const void* f_host, int v1, int v2, int cycles);
+
+/* ------------------------------------------------------------------ 3D Poisson, non-cubic grids ---- */
+/* sizeX != sizeY != sizeZ (every one 2^k + 1).  The reference's constructor already takes three sizes and its hierarchy and
+   operators are written per dimension (N3/MultiGrid3D.cpp:5-8, :19-47: numGrids = (int)log2(minSize - 1), every dimension
+   halved per level), but Grid3D asserts them equal (N3/Grid3D.cpp:10-11; lifting that is the author's TODO, SURVEY.md 8f
+   rank 4).  Same operators, same arithmetic, results bit-identical to the reference compiled with its assertions off
+   (oracle/_ref ref3d_*x, tests/test_box3d_gpu.py); dense device layout, one GPU, not tuned like the cubic path. */
+int mg3b_create(mg3b_t** out, const int finest_size_xyz[3], const double range[6], int dtype, int residual_mode);
+int mg3b_destroy(mg3b_t* mg);
+int mg3b_num_levels(const mg3b_t* mg);                               /* MultiGrid3D::numGrids */
+int mg3b_level_size(const mg3b_t* mg, int level, int out_xyz[3]);    /* grids3D[level]->sizeXYZ */
+int mg3b_level_h(const mg3b_t* mg, int level, double out_xyz[3]);    /* grids3D[level]->h_x, h_y, h_z */
+int mg3b_sync(mg3b_t* mg);
+void* mg3b_stream(mg3b_t* mg);
+long long mg3b_kernel_launches(const mg3b_t* mg);
+int mg3b_set_field(mg3b_t* mg, int level, int field, const void* host_dense); /* sizeX*sizeY*sizeZ values, x fastest */
+int mg3b_get_field(mg3b_t* mg, int level, int field, void* host_dense);
+int mg3b_init_problem(mg3b_t* mg);                                   /* Grid3D::InitV/InitF, N3/Grid3D.cpp:61-96 */
+int mg3b_relax(mg3b_t* mg, int level, int ncycles);                  /* Relax */
+int mg3b_residual(mg3b_t* mg, int level, void* host_out);            /* CalculateResidual -> caller-owned array */
+int mg3b_residual_norm(mg3b_t* mg, int level, double* l2, double* linf);
+int mg3b_restrict(mg3b_t* mg, int fine_level, int field);            /* Restrict(fine->field, coarse->field) */
+int mg3b_residual_restrict(mg3b_t* mg, int fine_level);              /* Restrict(CalculateResidual(fine), coarse->h_f) + setToValue(coarse->h_v,0,true) */
+int mg3b_interpolate(mg3b_t* mg, int fine_level);                    /* Interpolate */
+int mg3b_interpolate_correct(mg3b_t* mg, int fine_level);            /* Interpolate + ApplyCorrection */
+int mg3b_set_to_value(mg3b_t* mg, int level, int field, double value, int modify_boundaries);
+int mg3b_vcycle(mg3b_t* mg, int level, int v1, int v2);              /* VCycle */
+int mg3b_fmg(mg3b_t* mg, int level, int v0, int v1, int v2);         /* FullMultiGridVCycle */
+int mg3b_vcycle_host(mg3b_t* mg, void* v_host, const void* f_host, int v1, int v2, int cycles);
 
 /* ------------------------------------------------------------------ 2D Lyapunov ------------ */
 /* MultiGrid2D::MultiGrid2D + InitGrids + InitA (N2/MultiGrid2D.cpp:5-60); A4 = row-major 2x2 by value

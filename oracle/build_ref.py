@@ -10,6 +10,8 @@ Variants (one object each, every one in its own C++ namespace):
     ref3d_f32  ref3d_f64  ref3d_f32c  ref3d_f64c     (c = CORRECTED residual signs)
     ref2d_f32  ref2d_f64
     ref1d_f32  ref1d_f64  ref1d_f32c  ref1d_f64c
+    ref3d_f32x  ref3d_f64x  ref3d_f32cx  ref3d_f64cx   the 3D variants with -DNDEBUG: assertions compiled out, sources
+                     untouched -- the reference then runs non-cubic grids (only N3/Grid3D.cpp:10-11 forbids them)
     ref3d_f64cO0   = ref3d_f64c built with -O0, i.e. as shipped (the reference's CompileAndLink passes no flags);
                      only bench.py's CPU baseline times it, next to the -O2 figure
 
@@ -88,14 +90,17 @@ def build(verbose=False):
                 variants.append((dim, prec, False))
                 if dim in PATCHES:
                     variants.append((dim, prec, True))
-        variants = [v + ("O2",) for v in variants] + [("3d", "f64", True, "O0")]
-        for dim, prec, corrected, opt in variants:
-            prefix = "ref%s_%s%s%s" % (dim, prec, "c" if corrected else "", "" if opt == "O2" else opt)
+        variants = [v + ("O2", False) for v in variants] + [("3d", "f64", True, "O0", False)]
+        variants += [("3d", prec, corr, "O2", True) for prec in ("f32", "f64") for corr in (False, True)]
+        for dim, prec, corrected, opt, ndebug in variants:
+            prefix = "ref%s_%s%s%s%s" % (dim, prec, "c" if corrected else "", "" if opt == "O2" else opt, "x" if ndebug else "")
             obj = os.path.join(OUT, prefix + ".o")
             cmd = [("-" + opt) if a == "-O2" else a for a in common]
             cmd += ["-DREF_PREFIX=" + prefix]
             if prec == "f64":
                 cmd += ["-DREF_F64"]
+            if ndebug:
+                cmd += ["-DNDEBUG"]
             if corrected:
                 cmd += ["-I", _patched_dir(dim, tmp)]
             cmd += ["-I", DIRS[dim], "-I", HERE, os.path.join(HERE, "ref_wrap%s.cpp" % dim), "-o", obj]

@@ -296,6 +296,220 @@ void FN(orc3d_fmg)(REAL** v, REAL** f, int n0, int nlevels, const double* range,
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* 3D Poisson on a NON-CUBIC grid (sizeX != sizeY != sizeZ, every one 2^k + 1)                  */
+/*                                                                                            */
+/* The reference asserts such grids away (N3/Grid3D.cpp:10-11, the author's TODO) although its */
+/* hierarchy (N3/MultiGrid3D.cpp:19-47: numGrids from the SMALLEST dimension, every dimension  */
+/* halved per level) and all its operators are written per dimension.  These functions restate */
+/* the same operators with (nx, ny, nz); pinned against the reference compiled with -DNDEBUG   */
+/* (oracle/_ref, the ref3d_*x variants) by tests/test_oracle.py.                               */
+/* ------------------------------------------------------------------------------------------ */
+
+#define IDXB(x, y, z) ((size_t)(x) + (size_t)(y) * (size_t)nx + (size_t)(z) * (size_t)nx * (size_t)ny)
+
+static void FN(orc3b_h)(int nx, int ny, int nz, const double* range, REAL* hx, REAL* hy, REAL* hz)
+{
+    REAL xr = (REAL)range[1] - (REAL)range[0];
+    REAL yr = (REAL)range[3] - (REAL)range[2];
+    REAL zr = (REAL)range[5] - (REAL)range[4];
+    *hx = xr / (REAL)(nx - 1);
+    *hy = yr / (REAL)(ny - 1);
+    *hz = zr / (REAL)(nz - 1);
+}
+
+void FN(orc3b_init_v)(REAL* v, int nx, int ny, int nz)
+{
+    size_t tot = (size_t)nx * ny * nz;
+    for (size_t i = 0; i < tot; i++) v[i] = 0.0f;
+}
+
+void FN(orc3b_init_f)(REAL* f, int nx, int ny, int nz, const double* range)
+{
+    const double PI = 3.141592653589793;
+    REAL hx, hy, hz;
+    FN(orc3b_h)(nx, ny, nz, range, &hx, &hy, &hz);
+    REAL xa = (REAL)range[0], ya = (REAL)range[2], za = (REAL)range[4];
+    for (int pz = 0; pz < nz; pz++)
+        for (int py = 0; py < ny; py++)
+            for (int px = 0; px < nx; px++) {
+                REAL x = xa + px * hx;
+                REAL y = ya + py * hy;
+                REAL z = za + pz * hz;
+                f[IDXB(px, py, pz)] = (REAL)(-3 * PI * PI * sin(PI * x) * sin(PI * y) * sin(PI * z));
+            }
+}
+
+void FN(orc3b_relax)(REAL* v, const REAL* f, int nx, int ny, int nz, const double* range, int ncycles)
+{
+    REAL h_x, h_y, h_z;
+    FN(orc3b_h)(nx, ny, nz, range, &h_x, &h_y, &h_z);
+    REAL h_x2 = h_x * h_x, h_y2 = h_y * h_y, h_z2 = h_z * h_z;
+    for (int k = 0; k < ncycles; k++)
+        for (int colour = 0; colour < 2; colour++)
+            for (int pz = 1; pz < nz - 1; pz++)
+                for (int py = 1; py < ny - 1; py++)
+                    for (int px = 1; px < nx - 1; px++) {
+                        if ((py + px + pz) % 2 != colour) continue;
+                        REAL O = v[IDXB(px - 1, py, pz)];
+                        REAL E = v[IDXB(px + 1, py, pz)];
+                        REAL N = v[IDXB(px, py - 1, pz)];
+                        REAL S = v[IDXB(px, py + 1, pz)];
+                        REAL D = v[IDXB(px, py, pz - 1)];
+                        REAL U = v[IDXB(px, py, pz + 1)];
+                        size_t idx = IDXB(px, py, pz);
+                        v[idx] = (O * (h_y2 * h_z2) + E * (h_y2 * h_z2) + N * (h_x2 * h_z2) + S * (h_x2 * h_z2) +
+                                  D * (h_x2 * h_y2) + U * (h_x2 * h_y2) - f[idx] * h_x2 * h_y2 * h_z2) /
+                                 (2 * (h_y2 * h_z2 + h_x2 * h_z2 + h_x2 * h_y2));
+                    }
+}
+
+void FN(orc3b_residual)(const REAL* v, const REAL* f, REAL* r, int nx, int ny, int nz, const double* range, int corrected)
+{
+    REAL h_x, h_y, h_z;
+    FN(orc3b_h)(nx, ny, nz, range, &h_x, &h_y, &h_z);
+    REAL h_x2 = h_x * h_x, h_y2 = h_y * h_y, h_z2 = h_z * h_z;
+    for (int pz = 0; pz < nz; pz++)
+        for (int py = 0; py < ny; py++)
+            for (int px = 0; px < nx; px++) {
+                size_t idx = IDXB(px, py, pz);
+                if (px == 0 || px == nx - 1 || py == 0 || py == ny - 1 || pz == 0 || pz == nz - 1) {
+                    r[idx] = 0.0f;
+                    continue;
+                }
+                REAL O = v[IDXB(px - 1, py, pz)];
+                REAL E = v[IDXB(px + 1, py, pz)];
+                REAL N = v[IDXB(px, py - 1, pz)];
+                REAL S = v[IDXB(px, py + 1, pz)];
+                REAL D = v[IDXB(px, py, pz - 1)];
+                REAL U = v[IDXB(px, py, pz + 1)];
+                if (corrected)
+                    r[idx] = f[idx] - ((O - 2 * v[idx] + E) / h_x2) - ((N - 2 * v[idx] + S) / h_y2) -
+                             ((D - 2 * v[idx] + U) / h_z2);
+                else
+                    r[idx] = f[idx] - ((O - 2 * v[idx] + E) / h_x2) - ((N - 2 * v[idx] - S) / h_y2) -
+                             ((D - 2 * v[idx] - U) / h_z2);
+            }
+}
+
+void FN(orc3b_restrict)(const REAL* fine, int nx, int ny, int nz, REAL* coarse)
+{
+    int cnx = (nx - 1) / 2 + 1, cny = (ny - 1) / 2 + 1, cnz = (nz - 1) / 2 + 1;
+#define F3(dx, dy, dz) fine[IDXB(fx + (dx), fy + (dy), fz + (dz))]
+    for (int cz = 0; cz < cnz; cz++)
+        for (int cy = 0; cy < cny; cy++)
+            for (int cx = 0; cx < cnx; cx++) {
+                int fx = 2 * cx, fy = 2 * cy, fz = 2 * cz;
+                size_t cidx = (size_t)cx + (size_t)cy * cnx + (size_t)cz * cnx * cny;
+                if (cx == 0 || cx == cnx - 1 || cy == 0 || cy == cny - 1 || cz == 0 || cz == cnz - 1) {
+                    coarse[cidx] = F3(0, 0, 0);
+                    continue;
+                }
+                REAL C_C = F3(0, 0, 0), N_C = F3(0, 0, 1), S_C = F3(0, 0, -1), E_C = F3(1, 0, 0), O_C = F3(-1, 0, 0);
+                REAL NE_C = F3(1, 0, 1), NO_C = F3(-1, 0, 1), SE_C = F3(1, 0, -1), SO_C = F3(-1, 0, -1);
+                REAL C_N = F3(0, -1, 0), N_N = F3(0, -1, 1), S_N = F3(0, -1, -1), E_N = F3(1, -1, 0), O_N = F3(-1, -1, 0);
+                REAL NE_N = F3(1, -1, 1), NO_N = F3(-1, -1, 1), SE_N = F3(1, -1, -1), SO_N = F3(-1, -1, -1);
+                REAL C_S = F3(0, 1, 0), N_S = F3(0, 1, 1), S_S = F3(0, 1, -1), E_S = F3(1, 1, 0), O_S = F3(-1, 1, 0);
+                REAL NE_S = F3(1, 1, 1), NO_S = F3(-1, 1, 1), SE_S = F3(1, 1, -1), SO_S = F3(-1, 1, -1);
+                coarse[cidx] = (1 / 8.0f) * (C_C) + (1 / 16.0f) * ((N_C + E_C + S_C + O_C) + (C_N + C_S)) +
+                               (1 / 32.0f) * ((NE_C + SE_C + SO_C + NO_C) + (N_N + E_N + S_N + O_N) +
+                                              (N_S + E_S + S_S + O_S)) +
+                               (1 / 64.0f) * ((NE_N + SE_N + SO_N + NO_N) + (NE_S + SE_S + SO_S + NO_S));
+            }
+#undef F3
+}
+
+void FN(orc3b_interpolate)(REAL* fine, int nx, int ny, int nz, const REAL* coarse)
+{
+    int cnx = (nx - 1) / 2 + 1, cny = (ny - 1) / 2 + 1;
+#define C3(dx, dy, dz) coarse[(size_t)(cx + (dx)) + (size_t)(cy + (dy)) * cnx + (size_t)(cz + (dz)) * cnx * cny]
+    for (int fz = 1; fz < nz - 1; fz++)
+        for (int fy = 1; fy < ny - 1; fy++)
+            for (int fx = 1; fx < nx - 1; fx++) {
+                int cx = fx / 2, cy = fy / 2, cz = fz / 2;
+                size_t fidx = IDXB(fx, fy, fz);
+                int oy = fy % 2, ox = fx % 2, oz = fz % 2;
+                if (!oy && !ox && !oz) fine[fidx] = C3(0, 0, 0);
+                else if (!oy && ox && !oz) fine[fidx] = (1 / 2.0f) * (C3(0, 0, 0) + C3(1, 0, 0));
+                else if (oy && !ox && !oz) fine[fidx] = (1 / 2.0f) * (C3(0, 0, 0) + C3(0, 1, 0));
+                else if (oy && ox && !oz)
+                    fine[fidx] = (1 / 4.0f) * (C3(0, 0, 0) + C3(1, 0, 0) + C3(0, 1, 0) + C3(1, 1, 0));
+                else if (!oy && !ox && oz) fine[fidx] = (1 / 2.0f) * (C3(0, 0, 0) + C3(0, 0, 1));
+                else if (!oy && ox && oz)
+                    fine[fidx] = (1 / 4.0f) * (C3(0, 0, 1) + C3(1, 0, 1) + C3(0, 0, 0) + C3(1, 0, 0));
+                else if (oy && !ox && oz)
+                    fine[fidx] = (1 / 4.0f) * (C3(0, 0, 0) + C3(0, 0, 1) + C3(0, 1, 0) + C3(0, 1, 1));
+                else
+                    fine[fidx] = (1 / 8.0f) * (C3(0, 0, 0) + C3(0, 0, 1) + C3(1, 0, 1) + C3(1, 0, 0) + C3(0, 1, 0) +
+                                               C3(0, 1, 1) + C3(1, 1, 1) + C3(1, 1, 0));
+            }
+#undef C3
+}
+
+void FN(orc3b_apply_correction)(REAL* fine, const REAL* err, int nx, int ny, int nz)
+{
+    for (int pz = 1; pz < nz - 1; pz++)
+        for (int py = 1; py < ny - 1; py++)
+            for (int px = 1; px < nx - 1; px++) {
+                size_t idx = IDXB(px, py, pz);
+                fine[idx] = fine[idx] + err[idx];
+            }
+}
+
+void FN(orc3b_set)(REAL* g, int nx, int ny, int nz, double value, int modify_boundaries)
+{
+    int lo = modify_boundaries ? 0 : 1, e = modify_boundaries ? 0 : 1;
+    for (int pz = lo; pz < nz - e; pz++)
+        for (int py = lo; py < ny - e; py++)
+            for (int px = lo; px < nx - e; px++) g[IDXB(px, py, pz)] = (REAL)value;
+}
+#undef IDXB
+
+static void FN(orc3b_level)(const int* n0, int level, int* nx, int* ny, int* nz)
+{
+    *nx = n0[0]; *ny = n0[1]; *nz = n0[2];
+    for (int l = 0; l < level; l++) {
+        *nx = (*nx - 1) / 2 + 1; *ny = (*ny - 1) / 2 + 1; *nz = (*nz - 1) / 2 + 1;
+    }
+}
+
+/* MultiGrid3D::VCycle, N3/MultiGrid3D.cpp:623-647, on the per-dimension hierarchy of :19-47 */
+void FN(orc3b_vcycle)(REAL** v, REAL** f, const int* n0, int nlevels, const double* range, int level, int v1, int v2,
+                      int corrected)
+{
+    int nx, ny, nz;
+    FN(orc3b_level)(n0, level, &nx, &ny, &nz);
+    FN(orc3b_relax)(v[level], f[level], nx, ny, nz, range, v1);
+    if (level != nlevels - 1) {
+        size_t tot = (size_t)nx * ny * nz;
+        REAL* tmp = (REAL*)malloc(tot * sizeof(REAL));
+        FN(orc3b_residual)(v[level], f[level], tmp, nx, ny, nz, range, corrected);
+        FN(orc3b_restrict)(tmp, nx, ny, nz, f[level + 1]);
+        FN(orc3b_set)(v[level + 1], (nx - 1) / 2 + 1, (ny - 1) / 2 + 1, (nz - 1) / 2 + 1, 0.0, 1);
+        FN(orc3b_vcycle)(v, f, n0, nlevels, range, level + 1, v1, v2, corrected);
+        FN(orc3b_interpolate)(tmp, nx, ny, nz, v[level + 1]);
+        FN(orc3b_apply_correction)(v[level], tmp, nx, ny, nz);
+        free(tmp);
+    }
+    FN(orc3b_relax)(v[level], f[level], nx, ny, nz, range, v2);
+}
+
+/* MultiGrid3D::FullMultiGridVCycle, N3/MultiGrid3D.cpp:569-585 */
+void FN(orc3b_fmg)(REAL** v, REAL** f, const int* n0, int nlevels, const double* range, int level, int v0, int v1, int v2,
+                   int corrected)
+{
+    int nx, ny, nz;
+    FN(orc3b_level)(n0, level, &nx, &ny, &nz);
+    if (level != nlevels - 1) {
+        FN(orc3b_restrict)(f[level], nx, ny, nz, f[level + 1]);
+        FN(orc3b_fmg)(v, f, n0, nlevels, range, level + 1, v0, v1, v2, corrected);
+        FN(orc3b_interpolate)(v[level], nx, ny, nz, v[level + 1]);
+    } else {
+        FN(orc3b_set)(v[level], nx, ny, nz, 0.0, 0);
+    }
+    for (int i = 0; i < v0; i++) FN(orc3b_vcycle)(v, f, n0, nlevels, range, level, v1, v2, corrected);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* 2D Lyapunov                                                                                 */
 /* ------------------------------------------------------------------------------------------ */
 

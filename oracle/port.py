@@ -170,3 +170,90 @@ class PortMG:
 
     def residual_norms(self, l=0):
         return norms(self.residual(l))
+
+
+def box_level_shapes(shape):
+    """(nx, ny, nz) per level: numGrids from the smallest dimension, every dimension halved per level (N3/MultiGrid3D.cpp:19-47)"""
+    nx, ny, nz = [int(s) for s in shape]
+    num = int(np.floor(np.log2(min(nx, ny, nz) - 1)))
+    out = [(nx, ny, nz)]
+    for _ in range(1, num):
+        nx, ny, nz = (nx - 1) // 2 + 1, (ny - 1) // 2 + 1, (nz - 1) // 2 + 1
+        out.append((nx, ny, nz))
+    return out
+
+
+class PortBox3D:
+    """The restatement on a NON-CUBIC 3D grid (orc3b_* in mg_oracle_impl.h); same interface as RefMG(3, ..., shape=...).
+    Arrays have numpy shape (nz, ny, nx): the dense x-fastest layout of the reference."""
+
+    def __init__(self, dtype, corrected=False, shape=(33, 17, 9), range=None):
+        self.dim = 3
+        self.np_dtype = np.dtype(dtype)
+        self.sfx = "_f32" if self.np_dtype == np.dtype(np.float32) else "_f64"
+        self.corrected = 1 if corrected else 0
+        self.L = lib()
+        self.creal_p = ctypes.POINTER(ctypes.c_float if self.sfx == "_f32" else ctypes.c_double)
+        self.range = (ctypes.c_double * 6)(*[float(x) for x in (range if range is not None else [0.0, 1.0] * 3)])
+        self.xyz = box_level_shapes(shape)
+        self.n0 = (ctypes.c_int * 3)(*self.xyz[0])
+        self.num_levels = len(self.xyz)
+        self.shapes = [(nz, ny, nx) for nx, ny, nz in self.xyz]
+        self._v = [np.zeros(s, dtype=self.np_dtype) for s in self.shapes]
+        self._f = [np.zeros(s, dtype=self.np_dtype) for s in self.shapes]
+        for l, (nx, ny, nz) in enumerate(self.xyz):
+            self._call("init_v", self._p(self._v[l]), nx, ny, nz)
+            self._call("init_f", self._p(self._f[l]), nx, ny, nz, self.range)
+
+    def _call(self, name, *args):
+        f = getattr(self.L, "orc3b_%s%s" % (name, self.sfx))
+        f.restype = None
+        f(*[ctypes.c_int(int(a)) if isinstance(a, (int, np.integer)) else (ctypes.c_double(a) if isinstance(a, float) else a) for a in args])
+
+    def close(self):
+        pass
+
+    def shape(self, l):
+        return self.shapes[l]
+
+    def v(self, l=0):
+        return self._v[l]
+
+    def f(self, l=0):
+        return self._f[l]
+
+    def _p(self, arr):
+        assert arr.dtype == self.np_dtype and arr.flags["C_CONTIGUOUS"]
+        return arr.ctypes.data_as(self.creal_p)
+
+    def _pp(self, arrs):
+        return (self.creal_p * len(arrs))(*[self._p(a) for a in arrs])
+
+    def relax(self, l, ncycles):
+        self._call("relax", self._p(self._v[l]), self._p(self._f[l]), *self.xyz[l], self.range, int(ncycles))
+
+    def residual(self, l=0):
+        out = np.empty(self.shapes[l], dtype=self.np_dtype)
+        self._call("residual", self._p(self._v[l]), self._p(self._f[l]), self._p(out), *self.xyz[l], self.range, self.corrected)
+        return out
+
+    def restrict(self, fine):
+        nz, ny, nx = fine.shape
+        coarse = np.zeros(((nz - 1) // 2 + 1, (ny - 1) // 2 + 1, (nx - 1) // 2 + 1), dtype=self.np_dtype)
+        self._call("restrict", self._p(fine), nx, ny, nz, self._p(coarse))
+        return coarse
+
+    def interpolate(self, fine, coarse):
+        nz, ny, nx = fine.shape
+        self._call("interpolate", self._p(fine), nx, ny, nz, self._p(coarse))
+        return fine
+
+    def vcycle(self, l, v1, v2):
+        self._call("vcycle", self._pp(self._v), self._pp(self._f), self.n0, self.num_levels, self.range, int(l), int(v1), int(v2), self.corrected)
+
+    def fmg(self, l, v0, v1, v2):
+        self._call("fmg", self._pp(self._v), self._pp(self._f), self.n0, self.num_levels, self.range, int(l), int(v0), int(v1), int(v2),
+                   self.corrected)
+
+    def residual_norms(self, l=0):
+        return norms(self.residual(l))

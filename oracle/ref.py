@@ -41,15 +41,18 @@ def norms(r):
 
 
 class RefMG:
-    def __init__(self, dim, dtype, corrected=False, n=33, range=None, A=(-1.0, -2.0, 0.0, -3.0), alfa=2, opt="O2"):
-        """opt="O0": the as-shipped build (no compiler flags), available for 3D double corrected only (timing)."""
+    def __init__(self, dim, dtype, corrected=False, n=33, range=None, A=(-1.0, -2.0, 0.0, -3.0), alfa=2, opt="O2", shape=None):
+        """opt="O0": the as-shipped build (no compiler flags), available for 3D double corrected only (timing).
+        shape=(nx, ny, nz): a non-cubic 3D grid -- the -DNDEBUG variants of the reference (build_ref.py: only the asserts at
+        N3/Grid3D.cpp:10-11 stand between the reference and such grids)."""
         self.dim = dim
         self.np_dtype = np.dtype(dtype)
         assert self.np_dtype in (np.dtype(np.float32), np.dtype(np.float64))
         prec = "f32" if self.np_dtype == np.dtype(np.float32) else "f64"
         if corrected and dim == 2:
             corrected = False  # the 2D residual has no defect
-        self.prefix = "ref%dd_%s%s%s" % (dim, prec, "c" if corrected else "", "" if opt == "O2" else opt)
+        self.prefix = "ref%dd_%s%s%s%s" % (dim, prec, "c" if corrected else "", "" if opt == "O2" else opt, "x" if shape is not None else "")
+        assert shape is None or dim == 3
         self.L = lib()
         if not hasattr(self.L, self.prefix + "_create"):
             raise RuntimeError("oracle/_ref has no variant %s" % self.prefix)
@@ -61,11 +64,21 @@ class RefMG:
         if dim == 2:
             a4 = (ctypes.c_double * 4)(*[float(x) for x in A])
             self.h = create(ctypes.c_int(n), rng, a4, ctypes.c_int(int(alfa)))
+        elif shape is not None:
+            create = self._fn("create_xyz", ctypes.c_void_p)
+            self.h = create(ctypes.c_int(int(shape[0])), ctypes.c_int(int(shape[1])), ctypes.c_int(int(shape[2])), rng)
         else:
             self.h = create(ctypes.c_int(n), rng)
         self.h = ctypes.c_void_p(self.h)
         self.num_levels = self._fn("num_levels", ctypes.c_int)(self.h)
         self.sizes = [self._fn("level_size", ctypes.c_int)(self.h, ctypes.c_int(l)) for l in np.arange(self.num_levels)]
+        self.shapes = None
+        if shape is not None:  # numpy axis order (z, y, x) of the dense x-fastest layout
+            self.shapes = []
+            for l in np.arange(self.num_levels):
+                o = (ctypes.c_int * 3)()
+                self._fn("level_size_xyz")(self.h, ctypes.c_int(l), o)
+                self.shapes.append((o[2], o[1], o[0]))
 
     def _fn(self, name, restype=None):
         f = getattr(self.L, "%s_%s" % (self.prefix, name))
@@ -84,11 +97,11 @@ class RefMG:
             pass
 
     def shape(self, l):
-        return (self.sizes[l],) * self.dim
+        return self.shapes[l] if self.shapes is not None else (self.sizes[l],) * self.dim
 
     def _view(self, which, l):
         p = self._fn("level_" + which, self.creal_p)(self.h, ctypes.c_int(int(l)))
-        n = self.sizes[l] ** self.dim
+        n = int(np.prod(self.shape(l)))
         return np.ctypeslib.as_array(p, shape=(n,)).reshape(self.shape(l))
 
     def v(self, l=0):

@@ -10,7 +10,12 @@
  *   REF_PREFIX=ref3d_f32c / ref3d_f64c   same, but MultiGrid3D.cpp is taken from a
  *       build-time patched temp copy with the two residual signs of line 723 flipped
  *       (the CORRECTED mode of SURVEY.md section 0.5; the patch lives in build_ref.py).
- * Each build sits in its own namespace so the four copies of the classes can share one .so.
+ *   REF_PREFIX=ref3d_f32x / ref3d_f64x / ref3d_f32cx / ref3d_f64cx   the same four with -DNDEBUG: the only thing that
+ *       keeps the reference from running a NON-CUBIC grid is the pair of asserts at N3/Grid3D.cpp:10-11 (its hierarchy,
+ *       N3/MultiGrid3D.cpp:19-47, and every operator already work per dimension; the author's TODO, N3/TODO!!!), so with
+ *       assertions compiled out -- no source change -- the reference itself is the oracle for sizeX != sizeY != sizeZ
+ *       (create_xyz below).
+ * Each build sits in its own namespace so the copies of the classes can share one .so.
  */
 #include "ref_wrap_common.h"
 
@@ -35,6 +40,24 @@ void* REF_FN(create)(int n, const double* range6)
     for (int l = 0; l < mg->numGrids; l++)
         mg->setToValue(mg->grids3D[l]->h_v, mg->grids3D[l]->sizeXYZ, 0.0f, false);
     return mg;
+}
+
+/* non-cubic finest grid (the *x variants only: the others abort on the reference's own assert) */
+void* REF_FN(create_xyz)(int nx, int ny, int nz, const double* range6)
+{
+    int sz[3] = {nx, ny, nz};
+    ref_real r[6];
+    for (int i = 0; i < 6; i++) r[i] = (ref_real)range6[i];
+    MultiGrid3D* mg = new MultiGrid3D(sz, r);
+    for (int l = 0; l < mg->numGrids; l++)
+        mg->setToValue(mg->grids3D[l]->h_v, mg->grids3D[l]->sizeXYZ, 0.0f, false);
+    return mg;
+}
+
+void REF_FN(level_size_xyz)(void* h, int l, int* out3)
+{
+    Grid3D* g = ((MultiGrid3D*)h)->grids3D[l];
+    out3[0] = g->sizeX; out3[1] = g->sizeY; out3[2] = g->sizeZ;
 }
 
 void REF_FN(destroy)(void* h)

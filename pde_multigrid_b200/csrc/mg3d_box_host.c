@@ -1,0 +1,432 @@
+/*
+ * mg3d_box_host.c -- C host driver of the 3D Poisson multigrid on NON-CUBIC grids (mg3b_* in include/mg_b200.h).
+ *
+ * The reference's constructor takes three sizes (MultiGrid3D(int finestGridSizeXYZ[], float range[]),
+ * N3/MultiGrid3D.cpp:5-8) and its hierarchy is already written per dimension -- numGrids = (int)log2(minSize - 1),
+ * every dimension halved per level (InitGrids, :19-47) -- but Grid3D asserts sizeX == sizeY == sizeZ
+ * (N3/Grid3D.cpp:10-11; lifting that is the author's own TODO).  This driver mirrors the same
+ * control flow (VCycle :623-647, FullMultiGridVCycle :569-585) over the kernels of mg3d_box.cu.  The coarsest level of
+ * an anisotropic hierarchy has more than one unknown (e.g. 9 x 5 x 3): like the reference it gets v1 + v2 sweeps.
+ * Fields live on the device in the reference's dense layout, so set/get are plain copies.  No CPU compute path.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "mg_host_common.h"
+
+#define MG3B_NPARTS 1024
+
+int mgk3b_relax_colour(cudaStream_t s, int dtype, void* v, const void* f, const int n[3], mg_coef3d c, int colour);
+int mgk3b_residual(cudaStream_t s, int dtype, const void* v, const void* f, void* r, const int n[3], mg_coef3d c, int corrected);
+int mgk3b_restrict(cudaStream_t s, int dtype, const void* fv, const void* ff, const int n[3], mg_coef3d c, int corrected, void* cf, void* cv,
+                   const int cn[3]);
+int mgk3b_interpolate(cudaStream_t s, int dtype, void* fv, const int n[3], const void* cv, const int cn[3], int add);
+int mgk3b_apply_correction(cudaStream_t s, int dtype, void* fv, const void* err, const int n[3]);
+int mgk3b_set(cudaStream_t s, int dtype, void* a, const int n[3], double value, int modify_boundaries);
+int mgk3b_init_f(cudaStream_t s, int dtype, void* f, const int n[3], const double* sx, const double* sy, const double* sz);
+int mgk3b_residual_norm(cudaStream_t s, int dtype, const void* v, const void* f, const int n[3], mg_coef3d c, int corrected, double* parts,
+                        int nparts, double* out2);
+
+typedef struct {
+    int n[3];
+    mg_coef3d c;
+    double h[3];
+    void* v;
+    void* f;
+} mg_level3b;
+
+struct mg3b_s {
+    int dtype, mode, nlevels;
+    double range[6];
+    cudaStream_t stream;
+    mg_level3b* lv;
+    void* arena;
+    double* d_scratch; /* 2 * MG3B_NPARTS partials + 2 outputs */
+    double* d_tables;  /* sin tables of InitF: nx + ny + nz doubles of the finest level */
+    double* h_out2;    /* pinned */
+    long long launches;
+};
+
+static size_t level_count(const mg_level3b* L) { return (size_t)L->n[0] * (size_t)L->n[1] * (size_t)L->n[2]; }
+
+/* h = range/(real)(size-1) per axis (N3/Grid3D.cpp:31-45) and the products of N3/MultiGrid3D.cpp:498-500, :532, in the level's
+   own precision exactly like the reference computes them on the host */
+static void box_coefs(int dtype, const int n[3], const double* range, double h[3], mg_coef3d* c)
+{
+    memset(c, 0, sizeof *c);
+    if (dtype == MG_F32) {
+        float xr = (float)range[1] - (float)range[0], yr = (float)range[3] - (float)range[2], zr = (float)range[5] - (float)range[4];
+        float hx = xr / (float)(n[0] - 1), hy = yr / (float)(n[1] - 1), hz = zr / (float)(n[2] - 1);
+        float hx2 = hx * hx, hy2 = hy * hy, hz2 = hz * hz;
+        float cx = hy2 * hz2, cy = hx2 * hz2, cz = hx2 * hy2;
+        float den = 2 * (cx + cy + cz);
+        h[0] = hx; h[1] = hy; h[2] = hz;
+        c->hx2 = hx2; c->hy2 = hy2; c->hz2 = hz2;
+        c->cx = cx; c->cy = cy; c->cz = cz;
+        c->den = den; c->rden = 1.0f / den;
+        c->ihx2 = 1.0f / hx2; c->ihy2 = 1.0f / hy2; c->ihz2 = 1.0f / hz2;
+    } else {
+        double xr = range[1] - range[0], yr = range[3] - range[2], zr = range[5] - range[4];
+        double hx = xr / (double)(n[0] - 1), hy = yr / (double)(n[1] - 1), hz = zr / (double)(n[2] - 1);
+        double hx2 = hx * hx, hy2 = hy * hy, hz2 = hz * hz;
+        double cx = hy2 * hz2, cy = hx2 * hz2, cz = hx2 * hy2;
+        double den = 2 * (cx + cy + cz);
+        h[0] = hx; h[1] = hy; h[2] = hz;
+        c->hx2 = hx2; c->hy2 = hy2; c->hz2 = hz2;
+        c->cx = cx; c->cy = cy; c->cz = cz;
+        c->den = den; c->rden = 1.0 / den;
+        c->ihx2 = 1.0 / hx2; c->ihy2 = 1.0 / hy2; c->ihz2 = 1.0 / hz2;
+    }
+    c->fast_h = c->fast_den = 0; /* three different mesh widths: IEEE division throughout */
+}
+
+static int check_level(const mg3b_t* mg, int level)
+{
+    if (!mg) return mg_fail(MG_ERR_ARG, "null handle");
+    if (level < 0 || level >= mg->nlevels) return mg_fail(MG_ERR_ARG, "level %d out of range [0,%d)", level, mg->nlevels);
+    return MG_OK;
+}
+
+static int pow2_plus_1(int n)
+{
+    if (n < 3) return 0;
+    int m = n - 1;
+    return (m & (m - 1)) == 0;
+}
+
+int mg3b_destroy(mg3b_t* mg)
+{
+    if (!mg) return MG_OK;
+    if (mg->stream) cudaStreamSynchronize(mg->stream);
+    if (mg->arena) cudaFree(mg->arena);
+    if (mg->d_scratch) cudaFree(mg->d_scratch);
+    if (mg->d_tables) cudaFree(mg->d_tables);
+    if (mg->h_out2) cudaFreeHost(mg->h_out2);
+    if (mg->stream) cudaStreamDestroy(mg->stream);
+    free(mg->lv);
+    free(mg);
+    return MG_OK;
+}
+
+int mg3b_create(mg3b_t** out, const int finest_size_xyz[3], const double range[6], int dtype, int residual_mode)
+{
+    if (!out || !finest_size_xyz) return mg_fail(MG_ERR_ARG, "null argument");
+    *out = NULL;
+    for (int a = 0; a < 3; a++)
+        if (!pow2_plus_1(finest_size_xyz[a]))
+            return mg_fail(MG_ERR_ARG, "size %d on axis %d is not 2^k + 1 (N3/Grid3D.cpp:13-20)", finest_size_xyz[a], a);
+    if (dtype != MG_F32 && dtype != MG_F64) return mg_fail(MG_ERR_ARG, "bad dtype");
+    if (residual_mode != MG_REF_COMPAT && residual_mode != MG_CORRECTED) return mg_fail(MG_ERR_ARG, "bad residual mode");
+    static const double unit[6] = {0, 1, 0, 1, 0, 1};
+    if (!range) range = unit;
+    if (!(range[1] > range[0]) || !(range[3] > range[2]) || !(range[5] > range[4]))
+        return mg_fail(MG_ERR_ARG, "empty range (N3/Grid3D.cpp:27-29)");
+    int st = mg_require_device();
+    if (st) return st;
+    mg3b_t* mg = (mg3b_t*)calloc(1, sizeof *mg);
+    if (!mg) return mg_fail(MG_ERR_NOMEM, "host allocation failed");
+    mg->dtype = dtype;
+    mg->mode = residual_mode;
+    memcpy(mg->range, range, sizeof mg->range);
+    int mn = finest_size_xyz[0];
+    if (finest_size_xyz[1] < mn) mn = finest_size_xyz[1];
+    if (finest_size_xyz[2] < mn) mn = finest_size_xyz[2];
+    mg->nlevels = mg_num_levels_for(mn); /* numGrids = (int)log2(minSize - 1), N3/MultiGrid3D.cpp:24-34 */
+    mg->lv = (mg_level3b*)calloc((size_t)mg->nlevels, sizeof *mg->lv);
+    if (!mg->lv) { free(mg); return mg_fail(MG_ERR_NOMEM, "host allocation failed"); }
+    size_t bytes = 0;
+    for (int l = 0; l < mg->nlevels; l++) {
+        mg_level3b* L = &mg->lv[l];
+        for (int a = 0; a < 3; a++) L->n[a] = l == 0 ? finest_size_xyz[a] : (mg->lv[l - 1].n[a] - 1) / 2 + 1;
+        box_coefs(dtype, L->n, range, L->h, &L->c);
+        bytes += 2 * mg_align256(level_count(L) * mg_esize(dtype));
+    }
+#define MG3B_TRY(call)                                                                                                        \
+    do {                                                                                                                      \
+        cudaError_t e_ = (call);                                                                                              \
+        if (e_ != cudaSuccess) {                                                                                              \
+            mg3b_destroy(mg);                                                                                                 \
+            return mg_fail(MG_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                                      \
+        }                                                                                                                     \
+    } while (0)
+    MG3B_TRY(cudaStreamCreateWithFlags(&mg->stream, cudaStreamNonBlocking));
+    MG3B_TRY(cudaMalloc(&mg->arena, bytes));
+    MG3B_TRY(cudaMalloc((void**)&mg->d_scratch, (2 * MG3B_NPARTS + 2) * sizeof(double)));
+    MG3B_TRY(cudaMalloc((void**)&mg->d_tables, (size_t)(finest_size_xyz[0] + finest_size_xyz[1] + finest_size_xyz[2]) * sizeof(double)));
+    MG3B_TRY(cudaMallocHost((void**)&mg->h_out2, 2 * sizeof(double)));
+    char* p = (char*)mg->arena;
+    for (int l = 0; l < mg->nlevels; l++) {
+        mg_level3b* L = &mg->lv[l];
+        const size_t fb = mg_align256(level_count(L) * mg_esize(dtype));
+        L->v = p; p += fb;
+        L->f = p; p += fb;
+    }
+    st = mg3b_init_problem(mg);
+    if (st) { mg3b_destroy(mg); return st; }
+    *out = mg;
+    return MG_OK;
+}
+
+int mg3b_num_levels(const mg3b_t* mg) { return mg ? mg->nlevels : 0; }
+
+int mg3b_level_size(const mg3b_t* mg, int level, int out_xyz[3])
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (!out_xyz) return mg_fail(MG_ERR_ARG, "null output");
+    memcpy(out_xyz, mg->lv[level].n, 3 * sizeof(int));
+    return MG_OK;
+}
+
+int mg3b_level_h(const mg3b_t* mg, int level, double out_xyz[3])
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (!out_xyz) return mg_fail(MG_ERR_ARG, "null output");
+    memcpy(out_xyz, mg->lv[level].h, 3 * sizeof(double));
+    return MG_OK;
+}
+
+int mg3b_sync(mg3b_t* mg)
+{
+    if (!mg) return mg_fail(MG_ERR_ARG, "null handle");
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
+    return MG_OK;
+}
+
+void* mg3b_stream(mg3b_t* mg) { return mg ? (void*)mg->stream : NULL; }
+long long mg3b_kernel_launches(const mg3b_t* mg) { return mg ? mg->launches : 0; }
+
+/* Grid3D::InitV / InitF on every level (N3/Grid3D.cpp:61-96); the interior of v is zeroed as well.
+   sin(PI x) with x = x_a + pos*h in the level's precision, evaluated by the host libm the reference calls. */
+int mg3b_init_problem(mg3b_t* mg)
+{
+    if (!mg) return mg_fail(MG_ERR_ARG, "null handle");
+    const double PI = 3.141592653589793;
+    for (int l = 0; l < mg->nlevels; l++) {
+        mg_level3b* L = &mg->lv[l];
+        const int tot = L->n[0] + L->n[1] + L->n[2];
+        double* tab = (double*)malloc((size_t)tot * sizeof(double));
+        if (!tab) return mg_fail(MG_ERR_NOMEM, "host allocation failed");
+        int o = 0;
+        for (int a = 0; a < 3; a++)
+            for (int i = 0; i < L->n[a]; i++) {
+                double x;
+                if (mg->dtype == MG_F32) {
+                    float xf = (float)mg->range[2 * a] + i * (float)L->h[a];
+                    x = xf;
+                } else {
+                    x = mg->range[2 * a] + i * L->h[a];
+                }
+                tab[o++] = sin(PI * x);
+            }
+        cudaError_t e = cudaMemcpyAsync(mg->d_tables, tab, (size_t)tot * sizeof(double), cudaMemcpyHostToDevice, mg->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(mg->stream);
+        free(tab);
+        if (e != cudaSuccess) return mg_fail(MG_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e));
+        MG_LAUNCH(mg->launches, mgk3b_set(mg->stream, mg->dtype, L->v, L->n, 0.0, 1));
+        MG_LAUNCH(mg->launches, mgk3b_init_f(mg->stream, mg->dtype, L->f, L->n, mg->d_tables, mg->d_tables + L->n[0], mg->d_tables + L->n[0] + L->n[1]));
+        MG_CUDA(cudaStreamSynchronize(mg->stream)); /* d_tables is reused by the next level */
+    }
+    return MG_OK;
+}
+
+static void* field_ptr(mg_level3b* L, int field) { return field == MG_FIELD_V ? L->v : L->f; }
+
+int mg3b_set_field(mg3b_t* mg, int level, int field, const void* host_dense)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (!host_dense || (field != MG_FIELD_V && field != MG_FIELD_F)) return mg_fail(MG_ERR_ARG, "bad field/pointer");
+    mg_level3b* L = &mg->lv[level];
+    MG_CUDA(cudaMemcpyAsync(field_ptr(L, field), host_dense, level_count(L) * mg_esize(mg->dtype), cudaMemcpyHostToDevice, mg->stream));
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
+    return MG_OK;
+}
+
+int mg3b_get_field(mg3b_t* mg, int level, int field, void* host_dense)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (!host_dense || (field != MG_FIELD_V && field != MG_FIELD_F)) return mg_fail(MG_ERR_ARG, "bad field/pointer");
+    mg_level3b* L = &mg->lv[level];
+    MG_CUDA(cudaMemcpyAsync(host_dense, field_ptr(L, field), level_count(L) * mg_esize(mg->dtype), cudaMemcpyDeviceToHost, mg->stream));
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
+    return MG_OK;
+}
+
+/* Relax: ncycles x (red half-sweep, black half-sweep), N3/MultiGrid3D.cpp:489-567 */
+static int relax_level(mg3b_t* mg, int level, int ncycles)
+{
+    mg_level3b* L = &mg->lv[level];
+    for (int k = 0; k < ncycles; k++)
+        for (int colour = 0; colour < 2; colour++)
+            MG_LAUNCH(mg->launches, mgk3b_relax_colour(mg->stream, mg->dtype, L->v, L->f, L->n, L->c, colour));
+    return MG_OK;
+}
+
+int mg3b_relax(mg3b_t* mg, int level, int ncycles)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (ncycles < 0) return mg_fail(MG_ERR_ARG, "ncycles < 0");
+    return relax_level(mg, level, ncycles);
+}
+
+int mg3b_residual(mg3b_t* mg, int level, void* host_out)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (!host_out) return mg_fail(MG_ERR_ARG, "null output");
+    mg_level3b* L = &mg->lv[level];
+    const size_t bytes = level_count(L) * mg_esize(mg->dtype);
+    void* r = NULL;
+    MG_CUDA(cudaMalloc(&r, bytes));
+    int k = mgk3b_residual(mg->stream, mg->dtype, L->v, L->f, r, L->n, L->c, mg->mode == MG_CORRECTED);
+    cudaError_t e = k < 0 ? cudaGetLastError() : cudaMemcpyAsync(host_out, r, bytes, cudaMemcpyDeviceToHost, mg->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(mg->stream);
+    cudaFree(r);
+    if (k < 0 || e != cudaSuccess) return mg_fail(MG_ERR_CUDA, "residual failed: %s", cudaGetErrorString(e));
+    mg->launches += k;
+    return MG_OK;
+}
+
+int mg3b_residual_norm(mg3b_t* mg, int level, double* l2, double* linf)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    mg_level3b* L = &mg->lv[level];
+    double* out2 = mg->d_scratch + 2 * MG3B_NPARTS;
+    MG_LAUNCH(mg->launches, mgk3b_residual_norm(mg->stream, mg->dtype, L->v, L->f, L->n, L->c, mg->mode == MG_CORRECTED, mg->d_scratch, MG3B_NPARTS, out2));
+    MG_CUDA(cudaMemcpyAsync(mg->h_out2, out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, mg->stream));
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
+    if (l2) *l2 = sqrt(mg->h_out2[0]);
+    if (linf) *linf = mg->h_out2[1];
+    return MG_OK;
+}
+
+int mg3b_restrict(mg3b_t* mg, int fine_level, int field)
+{
+    int st = check_level(mg, fine_level);
+    if (st) return st;
+    if (fine_level == mg->nlevels - 1) return mg_fail(MG_ERR_ARG, "level %d is the coarsest", fine_level);
+    if (field != MG_FIELD_V && field != MG_FIELD_F) return mg_fail(MG_ERR_ARG, "bad field");
+    mg_level3b *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
+    MG_LAUNCH(mg->launches, mgk3b_restrict(mg->stream, mg->dtype, NULL, field_ptr(F, field), F->n, F->c, 0, field_ptr(C, field), NULL, C->n));
+    return MG_OK;
+}
+
+static int residual_restrict_level(mg3b_t* mg, int fine_level)
+{
+    mg_level3b *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
+    MG_LAUNCH(mg->launches, mgk3b_restrict(mg->stream, mg->dtype, F->v, F->f, F->n, F->c, mg->mode == MG_CORRECTED, C->f, C->v, C->n));
+    return MG_OK;
+}
+
+int mg3b_residual_restrict(mg3b_t* mg, int fine_level)
+{
+    int st = check_level(mg, fine_level);
+    if (st) return st;
+    if (fine_level == mg->nlevels - 1) return mg_fail(MG_ERR_ARG, "level %d is the coarsest", fine_level);
+    return residual_restrict_level(mg, fine_level);
+}
+
+static int interpolate_level(mg3b_t* mg, int fine_level, int add)
+{
+    mg_level3b *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
+    MG_LAUNCH(mg->launches, mgk3b_interpolate(mg->stream, mg->dtype, F->v, F->n, C->v, C->n, add));
+    return MG_OK;
+}
+
+int mg3b_interpolate(mg3b_t* mg, int fine_level)
+{
+    int st = check_level(mg, fine_level);
+    if (st) return st;
+    if (fine_level == mg->nlevels - 1) return mg_fail(MG_ERR_ARG, "level %d is the coarsest", fine_level);
+    return interpolate_level(mg, fine_level, 0);
+}
+
+int mg3b_interpolate_correct(mg3b_t* mg, int fine_level)
+{
+    int st = check_level(mg, fine_level);
+    if (st) return st;
+    if (fine_level == mg->nlevels - 1) return mg_fail(MG_ERR_ARG, "level %d is the coarsest", fine_level);
+    return interpolate_level(mg, fine_level, 1);
+}
+
+int mg3b_set_to_value(mg3b_t* mg, int level, int field, double value, int modify_boundaries)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (field != MG_FIELD_V && field != MG_FIELD_F) return mg_fail(MG_ERR_ARG, "bad field");
+    mg_level3b* L = &mg->lv[level];
+    MG_LAUNCH(mg->launches, mgk3b_set(mg->stream, mg->dtype, field_ptr(L, field), L->n, value, modify_boundaries));
+    return MG_OK;
+}
+
+/* VCycle, N3/MultiGrid3D.cpp:623-647: CalculateResidual + Restrict + setToValue(coarse v, 0, true) are one kernel,
+   Interpolate + ApplyCorrection are one kernel */
+static int vcycle_rec(mg3b_t* mg, int level, int v1, int v2)
+{
+    int st = relax_level(mg, level, v1);
+    if (st) return st;
+    if (level != mg->nlevels - 1) {
+        if ((st = residual_restrict_level(mg, level))) return st;
+        if ((st = vcycle_rec(mg, level + 1, v1, v2))) return st;
+        if ((st = interpolate_level(mg, level, 1))) return st;
+    }
+    return relax_level(mg, level, v2);
+}
+
+int mg3b_vcycle(mg3b_t* mg, int level, int v1, int v2)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (v1 < 0 || v2 < 0) return mg_fail(MG_ERR_ARG, "negative sweep count");
+    return vcycle_rec(mg, level, v1, v2);
+}
+
+/* FullMultiGridVCycle, N3/MultiGrid3D.cpp:569-585 */
+static int fmg_rec(mg3b_t* mg, int level, int v0, int v1, int v2)
+{
+    int st;
+    if (level != mg->nlevels - 1) {
+        mg_level3b *F = &mg->lv[level], *C = &mg->lv[level + 1];
+        MG_LAUNCH(mg->launches, mgk3b_restrict(mg->stream, mg->dtype, NULL, F->f, F->n, F->c, 0, C->f, NULL, C->n));
+        if ((st = fmg_rec(mg, level + 1, v0, v1, v2))) return st;
+        if ((st = interpolate_level(mg, level, 0))) return st;
+    } else {
+        mg_level3b* L = &mg->lv[level];
+        MG_LAUNCH(mg->launches, mgk3b_set(mg->stream, mg->dtype, L->v, L->n, 0.0, 0));
+    }
+    for (int i = 0; i < v0; i++)
+        if ((st = vcycle_rec(mg, level, v1, v2))) return st;
+    return MG_OK;
+}
+
+int mg3b_fmg(mg3b_t* mg, int level, int v0, int v1, int v2)
+{
+    int st = check_level(mg, level);
+    if (st) return st;
+    if (v0 < 0 || v1 < 0 || v2 < 0) return mg_fail(MG_ERR_ARG, "negative count");
+    return fmg_rec(mg, level, v0, v1, v2);
+}
+
+/* end to end on HOST arrays of the finest level: upload v, f -> cycles x VCycle(0, v1, v2) -> download v */
+int mg3b_vcycle_host(mg3b_t* mg, void* v_host, const void* f_host, int v1, int v2, int cycles)
+{
+    if (!mg || !v_host || !f_host) return mg_fail(MG_ERR_ARG, "null argument");
+    if (v1 < 0 || v2 < 0 || cycles < 0) return mg_fail(MG_ERR_ARG, "negative count");
+    mg_level3b* L = &mg->lv[0];
+    const size_t bytes = level_count(L) * mg_esize(mg->dtype);
+    MG_CUDA(cudaMemcpyAsync(L->v, v_host, bytes, cudaMemcpyHostToDevice, mg->stream));
+    MG_CUDA(cudaMemcpyAsync(L->f, f_host, bytes, cudaMemcpyHostToDevice, mg->stream));
+    for (int i = 0; i < cycles; i++) {
+        int st = vcycle_rec(mg, 0, v1, v2);
+        if (st) return st;
+    }
+    MG_CUDA(cudaMemcpyAsync(v_host, L->v, bytes, cudaMemcpyDeviceToHost, mg->stream));
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
+    return MG_OK;
+}

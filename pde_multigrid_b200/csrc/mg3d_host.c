@@ -1323,10 +1323,14 @@ static int residual_restrict_level(mg3d_t* mg, int fine_level, int defer_f_halo)
     else
         MG_LAUNCH(mg->launches, mgk3d_residual_restrict(mg->stream, mg->dtype, F->v, F->f, F->g, F->c, mg->mode == MG_CORRECTED,
                                                         C->f, C->v, C->g, lo, hi));
-    if (F->dist) { /* coarse v = 0 everywhere this rank stores it (ghost planes, or the whole agglomerated level) */
-        MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, C->v, C->g, 0.0, 1, 0, C->g.nzl));
-        if (C->dist && C->vbuf[1]) /* ... and on the ghost planes of its other buffer: see mirror_v_ghosts */
+    if (F->dist && C->dist) {
+        /* coarse v = 0 everywhere this rank stores it: the kernel above zeroed the planes it restricted to (all the planes the
+           rank owns), the ghost planes are zeroed here -- and those of the other buffer too: see mirror_v_ghosts */
+        MG_LAUNCH(mg->launches, mgk3d_set_ghosts(mg->stream, mg->dtype, C->v, C->g, 0.0, C->own_lo, C->own_hi));
+        if (C->vbuf[1])
             MG_LAUNCH(mg->launches, mgk3d_set_ghosts(mg->stream, mg->dtype, C->vbuf[C->cur ^ 1], C->g, 0.0, C->own_lo, C->own_hi));
+    } else if (F->dist) { /* first agglomerated level: the kernel zeroed this rank's share only, every rank holds the whole level */
+        MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, C->v, C->g, 0.0, 1, 0, C->g.nzl));
     }
     C->vg_valid = C->vg_deep = 1;
     PROF_END(mg);

@@ -260,6 +260,40 @@ class MultiGrid3D(_MultiGridBase):
         return dict(zip(("dist", "z0", "nzl", "own_lo", "own_hi"), list(out)))
 
 
+class MultiGrid3DBox(_MultiGridBase):
+    """MultiGrid3D(finestGridSizeXYZ, range) with sizeX != sizeY != sizeZ (mg3b_* of the C ABI): the grids the reference
+    asserts away at N3/Grid3D.cpp:10-11.  Host arrays have numpy shape (sizeZ, sizeY, sizeX) -- the dense x-fastest layout."""
+    dim = 3
+    prefix = "mg3b"
+
+    def __init__(self, finestGridSizeXYZ, range=(0, 1, 0, 1, 0, 1), dtype=np.float32, residual_mode=MG_REF_COMPAT):
+        self._L = _lib.lib()
+        self._L.mg3b_stream.restype = ctypes.c_void_p
+        self._L.mg3b_kernel_launches.restype = ctypes.c_longlong
+        self.np_dtype = np.dtype(dtype)
+        sz = (ctypes.c_int * 3)(*[int(s) for s in finestGridSizeXYZ])
+        rg = (ctypes.c_double * 6)(*[float(r) for r in range])
+        h = ctypes.c_void_p()
+        self._h = None
+        check(self._L.mg3b_create(ctypes.byref(h), sz, rg, _dtype_code(dtype), int(residual_mode)))
+        self._h = h
+
+    def level_size(self, level):
+        """(sizeX, sizeY, sizeZ) of a level"""
+        o = (ctypes.c_int * 3)()
+        self._call("level_size", ctypes.c_int(level), o)
+        return tuple(o)
+
+    def level_h(self, level):
+        o = (ctypes.c_double * 3)()
+        self._call("level_h", ctypes.c_int(level), o)
+        return tuple(o)
+
+    def shape(self, level):
+        nx, ny, nz = self.level_size(level)
+        return (nz, ny, nx)
+
+
 class MultiGrid2D(_MultiGridBase):
     """MultiGrid2D(finestGridSizeXY, range, A, A_size, alfa) -- N2/MultiGrid2D.h:16."""
     dim = 2
