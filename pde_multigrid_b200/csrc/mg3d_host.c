@@ -530,7 +530,7 @@ static int create_common(mg3d_t** out, const int sz[3], const double range[6], i
     if (!out || !sz || !range) return mg_fail(MG_ERR_ARG, "null argument");
     *out = NULL;
     /* N3/Grid3D.cpp:10-29 asserts */
-    if (sz[0] != sz[1] || sz[0] != sz[2]) return mg_fail(MG_ERR_ARG, "sizeX == sizeY == sizeZ required (got %d,%d,%d)", sz[0], sz[1], sz[2]);
+    if (sz[0] != sz[1] || sz[0] != sz[2]) return mg_fail(MG_ERR_ARG, "sizeX == sizeY == sizeZ required (got %d,%d,%d; N3/Grid3D.cpp:10-11): non-cubic grids go through mg3b_create", sz[0], sz[1], sz[2]);
     const int n = sz[0];
     if (n < 3 || ((n - 1) & (n - 2)) != 0) return mg_fail(MG_ERR_ARG, "size must be 2^k+1 with k >= 1 (got %d)", n);
     if (!(range[1] > range[0]) || !(range[3] > range[2]) || !(range[5] > range[4])) return mg_fail(MG_ERR_ARG, "range must satisfy b > a on every axis");
