@@ -77,7 +77,8 @@ constexpr int CROWS = TYT / 2 + 1;
 constexpr int NCR = 4;  // coarse planes in flight: Z0, Z0+1 in use, two ahead
 template <typename T> struct CBox {
     static constexpr int A = 16 / (int)sizeof(T);                 // TMA inner-coordinate alignment in elements
-    static constexpr int CW = MGK3D_PP_CBOX_I(sizeof(T));         // 18 doubles / 20 floats
+    static constexpr int CW = MGK3D_PP_CBOX_I(sizeof(T));         // 18 doubles / 20 floats of data + CSH
+    static constexpr int CSH = MGK3D_PP_CSHIFT(sizeof(T));        // column shift of the colour-1 sub-tile (bank skew, mg_launch.h)
     static constexpr int CSUB = (CW * CROWS * (int)sizeof(T) + 127) / 128 * 128 / (int)sizeof(T);
     static constexpr int CSLOT = 2 * CSUB;
 };
@@ -132,7 +133,7 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
     constexpr bool CHECK_MID = ARITH == 0 && sizeof(T) == 4;
     constexpr int GUARD_AL = (GUARD * (int)sizeof(T) + 127) / 128 * 128 / (int)sizeof(T);
     T* base = reinterpret_cast<T*>(smem_raw) + GUARD_AL;  // slot 0
-    constexpr int CSUB = CBox<T>::CSUB, CSLOT = CBox<T>::CSLOT, CW = CBox<T>::CW;
+    constexpr int CSUB = CBox<T>::CSUB, CSLOT = CBox<T>::CSLOT, CW = CBox<T>::CW, CSH = CBox<T>::CSH;
     T* cring = base + (size_t)NSLOT * SLOT + GUARD_AL;    // CORR: NCR coarse planes, two colour sub-tiles each
     uint64_t* bars = reinterpret_cast<uint64_t*>(cring + (CORR ? (size_t)NCR * CSLOT : 0));  // NRING + NCR barriers
 
@@ -177,7 +178,7 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
         uint64_t* bar = &bars[NRING + s];
         mbar_arrive_expect_tx(bar, 2 * CW * CROWS * (uint32_t)sizeof(T));
         tma_load_3d(cring + (size_t)s * CSLOT, &maps.cv[0], bar, cxh0, cy0c, Z - gc.z0);
-        tma_load_3d(cring + (size_t)s * CSLOT + CSUB, &maps.cv[1], bar, cxh0, cy0c, Z - gc.z0);
+        tma_load_3d(cring + (size_t)s * CSLOT + CSUB, &maps.cv[1], bar, cxh0 - CSH, cy0c, Z - gc.z0);
     };
     if (CORR && tid == 0)
         for (int Z = Zb; Z <= min(Zb + NCR - 2, Zlast); Z++) issue_coarse(Z);
@@ -288,7 +289,7 @@ k_relax_pipe2(const __grid_constant__ PipeMaps maps, const T* __restrict__ v_in,
             // each plane needs two pointers: corners with dx + dy even / odd.
             const T* q0 = cring + (size_t)(k0 & (NCR - 1)) * CSLOT + ca0;
             const T* q1 = cring + (size_t)((k0 + 1) & (NCR - 1)) * CSLOT + ca0;
-            const int se = ((ct + Z0) & 1) * CSUB, so = CSUB - se;       // colour sub-tile of plane Z0 for dx + dy even / odd
+            const int se = ((ct + Z0) & 1) * (CSUB + CSH), so = (CSUB + CSH) - se;  // colour sub-tile of plane Z0 for dx + dy even / odd
             const T *e0 = q0 + se, *o0 = q0 + so, *e1 = q1 + so, *o1 = q1 + se;  // plane Z0 + 1: colours swap
             const bool oxa = (((s0 ^ CV) & 1) != 0);  // x parity of the colour-1 point in the even row (the odd row has the other)
             T ea, eb;  // Interpolate at the colour-1 point of the even row (oy = 0) / the odd row (oy = 1), N3/MultiGrid3D.cpp:216-331

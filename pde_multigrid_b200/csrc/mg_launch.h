@@ -91,7 +91,10 @@ int mgk3d_relax_fused2(cudaStream_t s, int dtype, const void* const maps4[4], vo
 #define MGK3D_PP_PADL(esize) ((int)(esize) == 8 ? 0 : 2)
 #define MGK3D_PP_BOX_I(esize) (32 + 2 * MGK3D_PP_PADL(esize))
 #define MGK3D_PP_BOX_Y (MGK3D_PP_R * MGK3D_PP_NW)
-#define MGK3D_PP_CBOX_I(esize) ((int)(esize) == 8 ? 18 : 20)
+/* the colour-1 sub-tile of the coarse planes is loaded MGK3D_PP_CSHIFT columns (64 bytes) further left, so that column c of the two
+   colour sub-tiles -- which the even and the odd lanes of a warp read in the same instruction -- falls on different banks */
+#define MGK3D_PP_CSHIFT(esize) (64 / (int)(esize))
+#define MGK3D_PP_CBOX_I(esize) (((int)(esize) == 8 ? 18 : 20) + MGK3D_PP_CSHIFT(esize))
 #define MGK3D_PP_CBOX_Y (MGK3D_PP_R * MGK3D_PP_NW / 2 + 1)
 /* coarse_maps2 / gc: NULL, or the next coarser level's v (tensor maps of its two colour arrays with box (MGK3D_PP_CBOX_I(esize),
    MGK3D_PP_CBOX_Y, 1)) and geometry: prolongation + correction of the colour-1 points folded into the load stage of the pass */
