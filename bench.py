@@ -19,7 +19,7 @@ One JSON line on stdout (rank 0):
              CPU solver itself produced at this size (tests/golden/make_hash.py).  ok == true means: this run, on this many
              GPUs, holds the reference's bits.
   other_configs  (N=1) the remaining BASELINE.json configurations, measured in the same process: 1D N=1025, 2D Lyapunov
-             1025^2, 3D 257^3; (N=8) the 2049^3 capacity run of configs[4]
+             1025^2, 3D 257^3, and a non-cubic 3D grid (1025 x 513 x 257); (N=8) the 2049^3 capacity run of configs[4]
 `--impl reference` times that CPU solver as the measured arm instead (no GPU work at all): 513^3, at most 3 cycles.
 `--profile-traffic` re-measures roofline.traffic with ncu (one launch of the dominant kernel) into profiles/roofline_traffic.json.
 
@@ -299,6 +299,17 @@ def other_configs(mg, torch, world, rank, uid, dist):
         out["3d_257_f64"] = {"vcycle_2_2_ms": ms, "vcycles_per_s": 1e3 / ms, "grid_point_updates_per_s": updates_per_cycle(257) * 1e3 / ms,
                              "algorithmic_gbs": byt / ms / 1e6, "hbm_frac": byt / ms / 1e6 / peak, "parity_ok": bool(ok) if want else None}
         e.close()
+        # a non-cubic grid (the reference asserts them away, N3/Grid3D.cpp:10-11) through mg3b_*
+        shape = (1025, 513, 257)
+        e = mg.MultiGrid3DBox(shape, dtype=np.float64, residual_mode=mg.MG_CORRECTED)
+        r0b = e.residual_norm(0)[0]
+        ms = _timed(torch, e, lambda: e.VCycle(0, 2, 2), 5, warm=2)
+        pts = shape[0] * shape[1] * shape[2]
+        out["3d_box_1025x513x257_f64"] = {"vcycle_2_2_ms": ms, "vcycles_per_s": 1e3 / ms, "algorithmic_gbs": 149.8 * pts / ms / 1e6,
+                                          "hbm_frac": 149.8 * pts / ms / 1e6 / peak, "residual_l2_initial": r0b,
+                                          "residual_l2_after_7_cycles": e.residual_norm(0)[0],
+                                          "note": "dense layout, one thread per point: not tuned like the cubic path (DESIGN.md)"}
+        e.close()
     if world == 8:
         n = 2049
         import ctypes
@@ -529,7 +540,7 @@ def main():
         # guard fired and is timed with it).  Algorithmic bytes: 3*B*N0 per RB sweep = read v, read f,
         # write v -- the pass moves fewer real bytes than that (2.5*B*N0 + halo for both sweeps), so achieved/peak can
         # exceed 1; `traffic` is what ncu saw it move.
-        two_sweep = args.smoother in ("auto", "pipe", "fused") and world == 1
+        two_sweep = args.smoother in ("auto", "pipe") or (args.smoother == "fused" and world == 1)  # slabs take the pass too
         sweeps_per_launch = 2.0 if two_sweep else 0.5
         nlaunch = (NU1 + NU2) / sweeps_per_launch
         alg_per_launch = sweeps_per_launch * 3 * B * (N0 / world)
