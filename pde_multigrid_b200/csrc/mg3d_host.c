@@ -76,6 +76,11 @@ typedef struct {
     size_t* nb_off[2];            /* neighbour's byte offset of field fi (0: v buffer 0, 1: f, 2: v buffer 1) of level l inside its arena: [3*l + fi] */
     mg_geom3d* nb_geom[2];        /* neighbour's slab geometry per level */
     int* nb_own[2];               /* neighbour's own_lo, own_hi per level: [2*l], [2*l+1] */
+    /* every rank of the job (the agglomeration gather stores into all of them): [rank]; the own entries are the local pointers */
+    char** all_arena;
+    unsigned int** all_flags;
+    size_t* all_off;              /* byte offset of field fi of level l inside rank p's arena: [(p*nlevels + l)*3 + fi] */
+    int gather_p2p;               /* 1: gather_level stores directly into the peers (MG_B200_GATHER=nccl switches it off) */
 } mg_p2p;
 
 /* CUDA-graph cache of whole V-cycles: the cycle is ~100 dependent launches, most of them tiny (coarse
@@ -386,6 +391,32 @@ static int gather_level(mg3d_t* mg, int level, void* field, int top_mode)
     const int P = mg->nranks, m = (L->g.n - 1) / P;
     const size_t pe = (size_t)L->g.plane;
     int st = MG_OK, st2;
+    if (mg->p2p.gather_p2p && field == L->f && top_mode == MG_TOP_ZERO) {
+        /* the V-cycle's gather (the restricted residual): direct stores of this rank's share into every peer's copy of the level (two small launches instead of an NCCL
+           all-gather: 0.03 against 0.09 ms for the 129^3 level on 8 GPUs) */
+        const mg_p2p* q = &mg->p2p;
+        const size_t es = mg_esize(mg->dtype), share = pe * (size_t)m * es;
+        const void* src2[2];
+        void* dst[MG_GATHER_MAX_PEERS][2];
+        unsigned int* pblk[MG_GATHER_MAX_PEERS];
+        int np = 0;
+        for (int col = 0; col < 2; col++) src2[col] = plane_ptr(mg, L, field, col, mg->rank * m);
+        for (int nr = 0; nr < P; nr++) {
+            if (nr == mg->rank) continue;
+            /* an agglomerated level is stored whole on every rank: same geometry, the rank's own arena offset */
+            char* base = q->all_arena[nr] + q->all_off[((size_t)nr * mg->nlevels + level) * 3 + 1];
+            for (int col = 0; col < 2; col++)
+                dst[np][col] = base + ((size_t)col * (size_t)L->g.cstride + (size_t)(mg->rank * m) * (size_t)L->g.plane) * es;
+            pblk[np++] = q->all_flags[nr];
+            mg->halo_bytes += (long long)(2 * share);
+        }
+        PROF_BEGIN(mg, level, MG_OP_OTHER);
+        MG_LAUNCH(mg->launches, mgk_gather_push(mg->stream, src2, (unsigned long long)share, dst, pblk, np, mg->rank, q->flags));
+        if (mg->rank != P - 1) /* the Dirichlet plane n-1 of a restricted residual is +0: written locally (see below) */
+            MG_LAUNCH(mg->launches, mgk3d_set(mg->stream, mg->dtype, field, L->g, 0.0, 1, L->g.n - 1, L->g.n));
+        PROF_END(mg);
+        return MG_OK;
+    }
     PROF_BEGIN(mg, level, MG_OP_OTHER);
     /* both colour arrays in ONE NCCL group: one fused launch instead of two */
     st = mg_comm_group_start(mg->comm);
@@ -449,6 +480,25 @@ static int p2p_setup(mg3d_t* mg, size_t arena_bytes)
             if (level_fields_for(mg->lv[l].g.n, plan[0]) == 3) off += fb;
         }
     }
+    q->all_arena = (char**)calloc((size_t)P, sizeof(char*));
+    q->all_flags = (unsigned int**)calloc((size_t)P, sizeof(unsigned int*));
+    q->all_off = (size_t*)calloc((size_t)P * 3 * (size_t)mg->nlevels, sizeof(size_t));
+    if (!q->all_arena || !q->all_flags || !q->all_off) return mg_fail(MG_ERR_NOMEM, "host allocation failed");
+    for (int nr = 0; nr < P; nr++) { /* the same allocation arithmetic for every rank of the job */
+        size_t off = 0;
+        for (int l = 0; l < mg->nlevels; l++) {
+            int plan[5];
+            mg_geom3d g;
+            mg3d_plan_level(mg->lv[l].g.n, P, nr, plan);
+            set_geom(&g, mg->lv[l].g.n, mg->dtype, plan[1], plan[2]);
+            const size_t fb = mg_align256(2 * (size_t)g.cstride * mg_esize(mg->dtype));
+            size_t* o = &q->all_off[((size_t)nr * mg->nlevels + l) * 3];
+            o[0] = off; off += fb;
+            o[1] = off; off += fb;
+            o[2] = off;
+            if (level_fields_for(mg->lv[l].g.n, plan[0]) == 3) off += fb;
+        }
+    }
     MG_CUDA(cudaMalloc((void**)&q->flags, MG_HALO_FLAG_WORDS * sizeof(unsigned int)));
     MG_CUDA(cudaMemsetAsync(q->flags, 0, MG_HALO_FLAG_WORDS * sizeof(unsigned int), mg->stream));
     /* all-gather {arena handle, flags handle} (64 B each) */
@@ -471,9 +521,13 @@ static int p2p_setup(mg3d_t* mg, size_t arena_bytes)
     if (e == cudaSuccess) e = cudaStreamSynchronize(mg->stream);
     cudaFree(d_all);
     if (e != cudaSuccess) ok = 0;
-    for (int k = 0; k < 2 && ok; k++) {
-        const int nr = k == 0 ? r - 1 : r + 1;
-        if (nr < 0 || nr >= P) continue;
+    /* map every peer once (the z-neighbours for the halo exchanges, everybody for the agglomeration gather) */
+    for (int nr = 0; nr < P && ok; nr++) {
+        if (nr == r) {
+            q->all_arena[nr] = (char*)mg->arena;
+            q->all_flags[nr] = q->flags;
+            continue;
+        }
         void *pa = NULL, *pf = NULL;
         if (cudaIpcOpenMemHandle(&pa, all[2 * nr], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
             cudaIpcOpenMemHandle(&pf, all[2 * nr + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
@@ -481,8 +535,14 @@ static int p2p_setup(mg3d_t* mg, size_t arena_bytes)
             ok = 0;
             break;
         }
-        q->peer_arena[k] = (char*)pa + MG_ARENA_SLACK;
-        q->peer_flags[k] = (unsigned int*)pf;
+        q->all_arena[nr] = (char*)pa + MG_ARENA_SLACK;
+        q->all_flags[nr] = (unsigned int*)pf;
+    }
+    for (int k = 0; k < 2 && ok; k++) {
+        const int nr = k == 0 ? r - 1 : r + 1;
+        if (nr < 0 || nr >= P) continue;
+        q->peer_arena[k] = q->all_arena[nr];
+        q->peer_flags[k] = q->all_flags[nr];
     }
     free(all);
     /* every rank must agree on the transport: all-reduce the success bit */
@@ -493,6 +553,7 @@ static int p2p_setup(mg3d_t* mg, size_t arena_bytes)
     MG_CUDA(cudaMemcpyAsync(h2, d2, sizeof h2, cudaMemcpyDeviceToHost, mg->stream));
     MG_CUDA(cudaStreamSynchronize(mg->stream));
     q->enabled = h2[0] == 0.0;
+    q->gather_p2p = q->enabled && P - 1 <= MG_GATHER_MAX_PEERS && !(getenv("MG_B200_GATHER") && !strcmp(getenv("MG_B200_GATHER"), "nccl"));
     return MG_OK;
 }
 
@@ -500,14 +561,18 @@ static void p2p_teardown(mg3d_t* mg)
 {
     mg_p2p* q = &mg->p2p;
     for (int k = 0; k < 2; k++) {
-        if (q->peer_arena[k]) cudaIpcCloseMemHandle(q->peer_arena[k] - MG_ARENA_SLACK);
-        if (q->peer_flags[k]) cudaIpcCloseMemHandle(q->peer_flags[k]);
         free(q->nb_off[k]); free(q->nb_geom[k]); free(q->nb_own[k]);
     }
     if (mg->comm && q->flags) { /* nobody unmaps or frees while a neighbour may still be pushing */
         double* d2 = mg->d_scratch + 2 * MGK_NORM_MAX_PARTS;
         if (mg_comm_allreduce_sum_max(mg->comm, d2, mg->stream) == MG_OK) cudaStreamSynchronize(mg->stream);
     }
+    for (int nr = 0; nr < mg->nranks; nr++) { /* unmap after that barrier */
+        if (nr == mg->rank) continue;
+        if (q->all_arena && q->all_arena[nr]) cudaIpcCloseMemHandle(q->all_arena[nr] - MG_ARENA_SLACK);
+        if (q->all_flags && q->all_flags[nr]) cudaIpcCloseMemHandle(q->all_flags[nr]);
+    }
+    free(q->all_arena); free(q->all_flags); free(q->all_off);
     if (q->flags) cudaFree(q->flags);
     memset(q, 0, sizeof *q);
 }

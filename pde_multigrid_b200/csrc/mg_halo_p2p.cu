@@ -79,9 +79,112 @@ __global__ void __launch_bounds__(256) k_halo_exchange(XArgs a)
     }
 }
 
+// ---- agglomeration gather by direct stores (replaces ncclAllGather on the first agglomerated level) ----
+// Every rank stores its share of the restricted right-hand side into ALL peers' copies of the level.  Unlike a halo exchange
+// the receivers are not only the schedule-coupled neighbours, so the write-after-read safety is explicit, two phases per gather:
+//   ready: rank r tells every peer "I am at gather #seq: nothing of mine reads the previous contents any more", and waits for
+//          the same word from every peer -- only then does anybody overwrite anybody's array;
+//   done:  after the stores (system fence), rank r tells every peer "my share of #seq is in your memory" and waits for all.
+// Flag words of the block (one 128-byte line of 32 words each): [256 + p] ready from rank p, [288 + p] done from rank p,
+// [320] this rank's gather sequence number, [352] push-completion counter.  nranks <= 32.
+struct GArgs {
+    const void* src[2];            // my share: colour 0, colour 1
+    unsigned long long bytes;      // per colour, multiple of 16
+    void* dst[MG_GATHER_MAX_PEERS][2];
+    unsigned int* peer_block[MG_GATHER_MAX_PEERS];
+    int npeers, me;
+    unsigned int* block;
+    long long max_cycles;
+};
+
+__device__ __forceinline__ void wait_word(const unsigned int* w, unsigned int want, long long t0, long long max_cycles, unsigned int* err)
+{
+    while (true) {
+        unsigned int cur;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(w) : "memory");
+        if ((int)(cur - want) >= 0) return;
+        if (max_cycles > 0 && clock64() - t0 > max_cycles) { *err = 1; return; }
+    }
+}
+
+__global__ void k_gather_ready(GArgs a)
+{
+    if (threadIdx.x) return;
+    unsigned int* blk = a.block;
+    const unsigned int seq = ++blk[320];
+    __threadfence_system();
+    for (int p = 0; p < a.npeers; p++) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_block[p] + 256 + a.me), "r"(seq) : "memory");
+    const long long t0 = clock64();
+    for (int p = 0; p < a.npeers; p++) {
+        const int pr = p < a.me ? p : p + 1;  // rank of peer slot p
+        wait_word(blk + 256 + pr, seq, t0, a.max_cycles, blk + 96);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gather_push(GArgs a)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    const size_t n16 = a.bytes / 16;
+    for (int c = 0; c < 2; c++) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.src[c]);
+        for (size_t i = tid; i < n16; i += nth) {
+            const uint4 v = src[i];
+            for (int p = 0; p < a.npeers; p++) reinterpret_cast<uint4*>(a.dst[p][c])[i] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    __threadfence_system();
+    unsigned int* blk = a.block;
+    const unsigned int prev = atomicAdd(blk + 352, 1u);
+    if (prev != gridDim.x - 1) return;
+    blk[352] = 0;
+    __threadfence_system();
+    const unsigned int seq = blk[320];
+    for (int p = 0; p < a.npeers; p++) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_block[p] + 288 + a.me), "r"(seq) : "memory");
+    const long long t0 = clock64();
+    for (int p = 0; p < a.npeers; p++) {
+        const int pr = p < a.me ? p : p + 1;
+        wait_word(blk + 288 + pr, seq, t0, a.max_cycles, blk + 96);
+    }
+}
+
+long long halo_max_cycles()
+{
+    static long long max_cycles = -2;
+    if (max_cycles == -2) {
+        const char* env = getenv("MG_B200_HALO_TIMEOUT_S");
+        const double sec = env ? atof(env) : 300.0;
+        max_cycles = sec > 0 ? (long long)(sec * 2.0e9) : 0;
+    }
+    return max_cycles;
+}
+
 }  // namespace
 
 extern "C" {
+
+/* All-gather of one level field by direct stores: src2 = this rank's share of the two colour arrays (`bytes` each), dst[p] = the
+   same two places inside peer slot p's copy, peer_block[p] = that peer's flag block.  Two launches (ready handshake, push + done). */
+int mgk_gather_push(cudaStream_t s, const void* const src2[2], unsigned long long bytes, void* const dst[][2], unsigned int* const peer_block[],
+                    int npeers, int me, unsigned int* flag_block)
+{
+    if (npeers < 1 || npeers > MG_GATHER_MAX_PEERS) return -1;
+    GArgs a;
+    a.src[0] = src2[0]; a.src[1] = src2[1];
+    a.bytes = bytes;
+    for (int p = 0; p < npeers; p++) { a.dst[p][0] = dst[p][0]; a.dst[p][1] = dst[p][1]; a.peer_block[p] = peer_block[p]; }
+    a.npeers = npeers; a.me = me;
+    a.block = flag_block;
+    a.max_cycles = halo_max_cycles();
+    k_gather_ready<<<1, 32, 0, s>>>(a);
+    if (cudaPeekAtLastError() != cudaSuccess) return -1;
+    unsigned long long want = (bytes / 16 + 256 * 4 - 1) / (256 * 4);
+    int grid = (int)(want < 1 ? 1 : (want > 296 ? 296 : want));
+    k_gather_push<<<grid, 256, 0, s>>>(a);
+    return cudaPeekAtLastError() == cudaSuccess ? 2 : -1;
+}
+
 
 /* One launch per halo exchange: push up to 4 (src, dst, bytes) segments into the neighbours' ghost planes,
    raise their sequence flags, then wait for the neighbours' own pushes.  peer_flag[k] == NULL: nothing is sent
@@ -104,12 +207,7 @@ int mgk_halo_exchange(cudaStream_t s, const void* const src[4], void* const dst[
     a.block = flag_block;
     /* ordinary rank skew (a neighbour busy with host work between two calls) must not become an error: five minutes by
        default, MG_B200_HALO_TIMEOUT_S seconds if set (0 = no limit) */
-    static long long max_cycles = -2;
-    if (max_cycles == -2) {
-        const char* env = getenv("MG_B200_HALO_TIMEOUT_S");
-        const double sec = env ? atof(env) : 300.0;
-        max_cycles = sec > 0 ? (long long)(sec * 2.0e9) : 0;
-    }
+    const long long max_cycles = halo_max_cycles();
     a.max_cycles = max_cycles;
     if (!total && !peer_flag[0] && !peer_flag[1] && !wait_below && !wait_above) return 0;
     unsigned long long want = (total / 16 + 256 * 8 - 1) / (256 * 8);  // ~8 x 16 B per thread

@@ -168,9 +168,13 @@ int mgk3d_repack(cudaStream_t s, int dtype, void* split, mg_geom3d g, void* dens
 
 /* P2P halo exchange (mg_halo_p2p.cu), one launch: push up to 4 segments into peer memory, raise the peers'
    sequence flags, wait for the neighbours' pushes (bounded spin); sequence counters live in flag_block */
-#define MG_HALO_FLAG_WORDS 256
+#define MG_HALO_FLAG_WORDS 384
+#define MG_GATHER_MAX_PEERS 31
 int mgk_halo_exchange(cudaStream_t s, const void* const src[4], void* const dst[4], const unsigned long long bytes[4],
                       unsigned int* const peer_flag[2], int wait_below, int wait_above, unsigned int* flag_block);
+/* all-gather of one level field by direct stores into every peer's copy (two launches: ready handshake, push + done) */
+int mgk_gather_push(cudaStream_t s, const void* const src2[2], unsigned long long bytes, void* const dst[][2], unsigned int* const peer_block[],
+                    int npeers, int me, unsigned int* flag_block);
 
 /* ---- 2D (pitched: element (x,y) at base[x + y*pitch]) ---- */
 typedef struct {
