@@ -42,6 +42,21 @@ class Grid3D
 		Grid3D(int sizeXYZ_[], float range[]) { setup(sizeXYZ_, range); InitV(); InitF(); upload(); }
 		/* used by MultiGrid3D: wraps level `level` of an existing engine handle */
 		Grid3D(int sizeXYZ_[], float range[], mg3d_t* mg, int level) { setup(sizeXYZ_, range); pull(mg, level); }
+#ifndef MG_COMPAT_CUDA_TESI
+		/* ... of a NON-CUBIC hierarchy (sizeX != sizeY != sizeZ: the reference asserts these away, N3/Grid3D.cpp:10-11; here they
+		   run through the mg3b_* entry points) */
+		Grid3D(int sizeXYZ_[], float range[], mg3b_t* mg, int level) { setup(sizeXYZ_, range); pull(mg, level); }
+		void pull(mg3b_t* mg, int level)
+		{
+			MG_CHECK(mg3b_get_field(mg, level, MG_FIELD_V, h_v));
+			MG_CHECK(mg3b_get_field(mg, level, MG_FIELD_F, h_f));
+		}
+		void push(mg3b_t* mg, int level) const
+		{
+			MG_CHECK(mg3b_set_field(mg, level, MG_FIELD_V, h_v));
+			MG_CHECK(mg3b_set_field(mg, level, MG_FIELD_F, h_f));
+		}
+#endif
 		~Grid3D()
 		{
 			free(h_v); free(h_f); free(sizeXYZ);
@@ -140,6 +155,13 @@ class Grid3D
 		{
 			double r[6];
 			for (int i = 0; i < 6; i++) r[i] = range_[i];
+			if (sizeX != sizeY || sizeX != sizeZ) { /* non-cubic: mg3b_* */
+				mg3b_t* mb = 0;
+				MG_CHECK(mg3b_create(&mb, sizeXYZ, r, MG_F32, MG_REF_COMPAT));
+				MG_CHECK(mg3b_get_field(mb, 0, field, field == MG_FIELD_V ? h_v : h_f));
+				mg3b_destroy(mb);
+				return;
+			}
 			mg3d_t* mg = 0;
 			MG_CHECK(mg3d_create(&mg, sizeXYZ, r, MG_F32, MG_REF_COMPAT));
 			MG_CHECK(mg3d_get_field(mg, 0, field, field == MG_FIELD_V ? h_v : h_f));

@@ -13,18 +13,40 @@ class MultiGrid3D
 		Grid3D** grids3D;
 		int numGrids;
 		mg3d_t* engine; // the C-ABI handle behind this object
+		mg3b_t* box;    // ... or, for sizeX != sizeY != sizeZ, the non-cubic engine (then engine == 0)
 
 		MultiGrid3D(int finestGridSizeXYZ[], float range[]) { InitGrids(finestGridSizeXYZ, range); }
 		~MultiGrid3D()
 		{
 			for (int i = 0; i < numGrids; i++) delete grids3D[i];
 			free(grids3D);
-			mg3d_destroy(engine);
+			if (engine) mg3d_destroy(engine);
+			if (box) mg3b_destroy(box);
 		}
 		void InitGrids(int finestGridSizeXYZ[], float range[])
 		{
 			double r[6];
 			for (int i = 0; i < 6; i++) r[i] = range[i];
+			engine = 0;
+			box = 0;
+			if (finestGridSizeXYZ[0] != finestGridSizeXYZ[1] || finestGridSizeXYZ[0] != finestGridSizeXYZ[2]) {
+				/* the hierarchy of N3/MultiGrid3D.cpp:19-47 as written: numGrids from the smallest size, every size halved per
+				   level -- only Grid3D's asserts (N3/Grid3D.cpp:10-11) keep the reference itself from building it */
+#ifdef MG_COMPAT_CUDA_TESI
+				fprintf(stderr, "MultiGrid3D: non-cubic grids are served by the NOCUDA_TESI face of the shim (and by mg3b_* directly)\n");
+				abort();
+#else
+				MG_CHECK(mg3b_create(&box, finestGridSizeXYZ, r, MG_F32, MG_REF_COMPAT));
+				numGrids = mg3b_num_levels(box);
+				grids3D = (Grid3D**)malloc(numGrids * sizeof(Grid3D*));
+				for (int l = 0; l < numGrids; l++) {
+					int s[3];
+					MG_CHECK(mg3b_level_size(box, l, s));
+					grids3D[l] = new Grid3D(s, range, box, l);
+				}
+				return;
+#endif
+			}
 			MG_CHECK(mg3d_create(&engine, finestGridSizeXYZ, r, MG_F32, MG_REF_COMPAT));
 			numGrids = mg3d_num_levels(engine);
 			grids3D = (Grid3D**)malloc(numGrids * sizeof(Grid3D*));
@@ -38,6 +60,14 @@ class MultiGrid3D
 		void Relax(Grid3D* curGrid, int ncycles)
 		{
 			int l = level_of(curGrid);
+#ifndef MG_COMPAT_CUDA_TESI
+			if (box) {
+				curGrid->push(box, l);
+				MG_CHECK(mg3b_relax(box, l, ncycles));
+				curGrid->pull(box, l);
+				return;
+			}
+#endif
 			curGrid->push(engine, l);
 			MG_CHECK(mg3d_relax(engine, l, ncycles));
 			curGrid->pull(engine, l);
@@ -92,29 +122,58 @@ class MultiGrid3D
 			return d_r;
 		}
 #else
-		void Restrict(float* fine, int fsizeXYZ[], float* coarse, int csizeXYZ[]) { MG_CHECK(mg3d_restrict_host(engine, fine, fsizeXYZ, coarse, csizeXYZ)); }
-		void Interpolate(float* fine, int fsizeXYZ[], float* coarse, int csizeXYZ[]) { MG_CHECK(mg3d_interpolate_host(engine, fine, fsizeXYZ, coarse, csizeXYZ)); }
-		void setToValue(float* grid, int sizeXYZ[], float value, bool modifyBoundaries) { MG_CHECK(mg3d_set_to_value_host(engine, grid, sizeXYZ, value, modifyBoundaries)); }
+		void Restrict(float* fine, int fsizeXYZ[], float* coarse, int csizeXYZ[])
+		{
+			if (box) MG_CHECK(mg3b_restrict_host(box, fine, fsizeXYZ, coarse, csizeXYZ));
+			else MG_CHECK(mg3d_restrict_host(engine, fine, fsizeXYZ, coarse, csizeXYZ));
+		}
+		void Interpolate(float* fine, int fsizeXYZ[], float* coarse, int csizeXYZ[])
+		{
+			if (box) MG_CHECK(mg3b_interpolate_host(box, fine, fsizeXYZ, coarse, csizeXYZ));
+			else MG_CHECK(mg3d_interpolate_host(engine, fine, fsizeXYZ, coarse, csizeXYZ));
+		}
+		void setToValue(float* grid, int sizeXYZ[], float value, bool modifyBoundaries)
+		{
+			if (box) MG_CHECK(mg3b_set_to_value_host(box, grid, sizeXYZ, value, modifyBoundaries));
+			else MG_CHECK(mg3d_set_to_value_host(engine, grid, sizeXYZ, value, modifyBoundaries));
+		}
 		float* CalculateResidual(Grid3D* fine) // caller owns the returned buffer, as in the reference
 		{
 			int l = level_of(fine);
-			fine->push(engine, l);
 			float* r = (float*)malloc((size_t)fine->sizeX * fine->sizeY * fine->sizeZ * sizeof(float));
+			if (box) {
+				fine->push(box, l);
+				MG_CHECK(mg3b_residual(box, l, r));
+				return r;
+			}
+			fine->push(engine, l);
 			MG_CHECK(mg3d_residual(engine, l, r));
 			return r;
 		}
-		void ApplyCorrection(float* fine, int fsizeXYZ[], float* error, int esizeXYZ[]) { MG_CHECK(mg3d_apply_correction_host(engine, fine, fsizeXYZ, error, esizeXYZ)); }
+		void ApplyCorrection(float* fine, int fsizeXYZ[], float* error, int esizeXYZ[])
+		{
+			if (box) MG_CHECK(mg3b_apply_correction_host(box, fine, fsizeXYZ, error, esizeXYZ));
+			else MG_CHECK(mg3d_apply_correction_host(engine, fine, fsizeXYZ, error, esizeXYZ));
+		}
 #endif
 
 		void VCycle(int gridID, int v1, int v2)
 		{
 			push_all();
+#ifndef MG_COMPAT_CUDA_TESI
+			if (box) MG_CHECK(mg3b_vcycle(box, gridID, v1, v2));
+			else
+#endif
 			MG_CHECK(mg3d_vcycle(engine, gridID, v1, v2));
 			pull_all();
 		}
 		void FullMultiGridVCycle(int gridID, int v0, int v1, int v2)
 		{
 			push_all();
+#ifndef MG_COMPAT_CUDA_TESI
+			if (box) MG_CHECK(mg3b_fmg(box, gridID, v0, v1, v2));
+			else
+#endif
 			MG_CHECK(mg3d_fmg(engine, gridID, v0, v1, v2));
 			pull_all();
 		}
@@ -134,7 +193,23 @@ class MultiGrid3D
 			fprintf(stderr, "MultiGrid3D: grid does not belong to this hierarchy\n");
 			abort();
 		}
-		void push_all() { for (int l = 0; l < numGrids; l++) grids3D[l]->push(engine, l); }
-		void pull_all() { for (int l = 0; l < numGrids; l++) grids3D[l]->pull(engine, l); }
+		void push_all()
+		{
+			for (int l = 0; l < numGrids; l++) {
+#ifndef MG_COMPAT_CUDA_TESI
+				if (box) { grids3D[l]->push(box, l); continue; }
+#endif
+				grids3D[l]->push(engine, l);
+			}
+		}
+		void pull_all()
+		{
+			for (int l = 0; l < numGrids; l++) {
+#ifndef MG_COMPAT_CUDA_TESI
+				if (box) { grids3D[l]->pull(box, l); continue; }
+#endif
+				grids3D[l]->pull(engine, l);
+			}
+		}
 };
 #endif

@@ -189,6 +189,11 @@ int mg3b_set_to_value(mg3b_t* mg, int level, int field, double value, int modify
 int mg3b_vcycle(mg3b_t* mg, int level, int v1, int v2);              /* VCycle */
 int mg3b_fmg(mg3b_t* mg, int level, int v0, int v1, int v2);         /* FullMultiGridVCycle */
 int mg3b_vcycle_host(mg3b_t* mg, void* v_host, const void* f_host, int v1, int v2, int cycles);
+/* the operators on caller-owned HOST arrays (N3/MultiGrid3D.h:16-27 with three different sizes) */
+int mg3b_restrict_host(mg3b_t* mg, const void* fine, const int fsize_xyz[3], void* coarse, const int csize_xyz[3]);
+int mg3b_interpolate_host(mg3b_t* mg, void* fine, const int fsize_xyz[3], const void* coarse, const int csize_xyz[3]);
+int mg3b_apply_correction_host(mg3b_t* mg, void* fine, const int fsize_xyz[3], const void* error, const int esize_xyz[3]);
+int mg3b_set_to_value_host(mg3b_t* mg, void* grid, const int size_xyz[3], double value, int modify_boundaries);
 
 /* ------------------------------------------------------------------ 2D Lyapunov ------------ */
 /* MultiGrid2D::MultiGrid2D + InitGrids + InitA (N2/MultiGrid2D.cpp:5-60); A4 = row-major 2x2 by value

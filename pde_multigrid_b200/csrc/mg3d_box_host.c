@@ -430,3 +430,86 @@ int mg3b_vcycle_host(mg3b_t* mg, void* v_host, const void* f_host, int v1, int v
     MG_CUDA(cudaStreamSynchronize(mg->stream));
     return MG_OK;
 }
+
+/* ---- reference-facing calls on caller-owned HOST arrays (N3/MultiGrid3D.h:16-27 with three different sizes): upload, run, download ---- */
+static int box_sizes_ok(const int s[3]) { return s && s[0] >= 3 && s[1] >= 3 && s[2] >= 3; }
+static int coarse_of(const int f[3], const int c[3])
+{
+    for (int a = 0; a < 3; a++)
+        if (c[a] != (f[a] - 1) / 2 + 1) return 0; /* the reference's own check, N3/MultiGrid3D.cpp:60-62 */
+    return 1;
+}
+static size_t count3(const int s[3]) { return (size_t)s[0] * (size_t)s[1] * (size_t)s[2]; }
+
+/* two temporary device arrays of na / nb elements, filled from ha / hb when given */
+static int box_tmp(mg3b_t* mg, void** da, size_t na, const void* ha, void** db, size_t nb, const void* hb)
+{
+    const size_t es = mg_esize(mg->dtype);
+    *da = *db = NULL;
+    MG_CUDA(cudaMalloc(da, na * es));
+    if (nb) {
+        cudaError_t e = cudaMalloc(db, nb * es);
+        if (e != cudaSuccess) { cudaFree(*da); return mg_fail(MG_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    }
+    if (ha) MG_CUDA(cudaMemcpyAsync(*da, ha, na * es, cudaMemcpyHostToDevice, mg->stream));
+    if (hb && nb) MG_CUDA(cudaMemcpyAsync(*db, hb, nb * es, cudaMemcpyHostToDevice, mg->stream));
+    return MG_OK;
+}
+
+static int box_finish(mg3b_t* mg, int k, void* host_out, const void* dev_out, size_t n, void* da, void* db)
+{
+    cudaError_t e = cudaSuccess;
+    if (k >= 0 && host_out) e = cudaMemcpyAsync(host_out, dev_out, n * mg_esize(mg->dtype), cudaMemcpyDeviceToHost, mg->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(mg->stream);
+    cudaFree(da);
+    if (db) cudaFree(db);
+    if (k < 0) return mg_fail(MG_ERR_CUDA, "launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (e != cudaSuccess) return mg_fail(MG_ERR_CUDA, "copy failed: %s", cudaGetErrorString(e));
+    mg->launches += k;
+    return MG_OK;
+}
+
+int mg3b_restrict_host(mg3b_t* mg, const void* fine, const int fsize_xyz[3], void* coarse, const int csize_xyz[3])
+{
+    if (!mg || !fine || !coarse || !box_sizes_ok(fsize_xyz) || !box_sizes_ok(csize_xyz) || !coarse_of(fsize_xyz, csize_xyz))
+        return mg_fail(MG_ERR_ARG, "bad arrays or sizes (coarse = (fine-1)/2+1 per axis)");
+    void *df, *dc;
+    mg_coef3d c;
+    memset(&c, 0, sizeof c);
+    int st = box_tmp(mg, &df, count3(fsize_xyz), fine, &dc, count3(csize_xyz), NULL);
+    if (st) return st;
+    int k = mgk3b_restrict(mg->stream, mg->dtype, NULL, df, fsize_xyz, c, 0, dc, NULL, csize_xyz);
+    return box_finish(mg, k, coarse, dc, count3(csize_xyz), df, dc);
+}
+
+int mg3b_interpolate_host(mg3b_t* mg, void* fine, const int fsize_xyz[3], const void* coarse, const int csize_xyz[3])
+{
+    if (!mg || !fine || !coarse || !box_sizes_ok(fsize_xyz) || !box_sizes_ok(csize_xyz) || !coarse_of(fsize_xyz, csize_xyz))
+        return mg_fail(MG_ERR_ARG, "bad arrays or sizes (coarse = (fine-1)/2+1 per axis)");
+    void *df, *dc;
+    int st = box_tmp(mg, &df, count3(fsize_xyz), fine, &dc, count3(csize_xyz), coarse); /* the boundary of fine is kept */
+    if (st) return st;
+    int k = mgk3b_interpolate(mg->stream, mg->dtype, df, fsize_xyz, dc, csize_xyz, 0);
+    return box_finish(mg, k, fine, df, count3(fsize_xyz), df, dc);
+}
+
+int mg3b_apply_correction_host(mg3b_t* mg, void* fine, const int fsize_xyz[3], const void* error, const int esize_xyz[3])
+{
+    if (!mg || !fine || !error || !box_sizes_ok(fsize_xyz) || !esize_xyz || memcmp(fsize_xyz, esize_xyz, 3 * sizeof(int)))
+        return mg_fail(MG_ERR_ARG, "bad arrays or sizes (N3/MultiGrid3D.cpp:659-661)");
+    void *df, *de;
+    int st = box_tmp(mg, &df, count3(fsize_xyz), fine, &de, count3(fsize_xyz), error);
+    if (st) return st;
+    int k = mgk3b_apply_correction(mg->stream, mg->dtype, df, de, fsize_xyz);
+    return box_finish(mg, k, fine, df, count3(fsize_xyz), df, de);
+}
+
+int mg3b_set_to_value_host(mg3b_t* mg, void* grid, const int size_xyz[3], double value, int modify_boundaries)
+{
+    if (!mg || !grid || !box_sizes_ok(size_xyz)) return mg_fail(MG_ERR_ARG, "bad array or sizes");
+    void *dg, *unused;
+    int st = box_tmp(mg, &dg, count3(size_xyz), grid, &unused, 0, NULL);
+    if (st) return st;
+    int k = mgk3b_set(mg->stream, mg->dtype, dg, size_xyz, value, modify_boundaries);
+    return box_finish(mg, k, grid, dg, count3(size_xyz), dg, NULL);
+}

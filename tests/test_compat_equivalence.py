@@ -6,7 +6,8 @@ reference (CPU part) they are built twice: with the reference's unmodified .cpp 
 tests/golden/compat_diff_?d.txt (tests/golden/make_compat_golden.py) and is repeated here -- and against include/compat/ +
 libmg_b200.so (binaries in tests/_build/, shipped to the GPU box).  On the GPU the shim binaries must write the same bytes:
 3D 17^3 FMG(2,3,3) (with the reference's own residual signs the iteration blows up, any deviation would be amplified), 2D 33^2
-FMG(1,20,20), 1D 129 FMG(2,100,100).
+FMG(1,20,20), 1D 129 FMG(2,100,100); and a non-cubic 33 x 17 x 9 grid (FMG(2,3,3) plus a hand-made cycle through the free-array
+operators) whose reference side is the same classes compiled with -DNDEBUG.
 
 The CUDA_TESI faces (-DMG_COMPAT_CUDA_TESI: d_v / d_f / d_sizeXYZ members, device-pointer operands, Set, (size, pitch)
 signatures) cannot be pinned to the twin's numbers (its smoother races); tests/compat/drv?d_cuda.cpp do the
@@ -38,7 +39,7 @@ def shim_cmd(src, out, cuda_face=False):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not mounted")
-@pytest.mark.parametrize("dim", ["1d", "2d", "3d"])
+@pytest.mark.parametrize("dim", ["1d", "2d", "3d", "3d_box"])
 def test_reference_classes_reproduce_the_committed_dump(dim, tmp_path):
     """the reference side of the comparison, re-run: the committed golden file IS what the reference's classes write"""
     exe = str(tmp_path / ("ref_drv" + dim))
@@ -48,7 +49,7 @@ def test_reference_classes_reproduce_the_committed_dump(dim, tmp_path):
     assert filecmp.cmp(str(tmp_path / "log" / "diff.txt"), os.path.join(ROOT, "tests", "golden", "compat_diff_%s.txt" % dim), shallow=False)
 
 
-@pytest.mark.parametrize("dim", ["1d", "2d", "3d"])
+@pytest.mark.parametrize("dim", ["1d", "2d", "3d", "3d_box"])
 def test_shim_side_builds(mg, dim):
     os.makedirs(BUILD, exist_ok=True)
     subprocess.run(shim_cmd(os.path.join(ROOT, "tests", "compat", "drv%s.cpp" % dim), os.path.join(BUILD, "eq_shim_" + dim)), check=True)
@@ -62,7 +63,7 @@ def test_cuda_tesi_faces_build(mg, dim):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dim", ["1d", "2d", "3d"])
+@pytest.mark.parametrize("dim", ["1d", "2d", "3d", "3d_box"])
 def test_shim_writes_the_reference_dump_byte_for_byte(dim, tmp_path):
     exe = os.path.join(BUILD, "eq_shim_" + dim)
     if not os.path.exists(exe):
