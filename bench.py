@@ -308,7 +308,7 @@ def other_configs(mg, torch, world, rank, uid, dist):
         out["3d_box_1025x513x257_f64"] = {"vcycle_2_2_ms": ms, "vcycles_per_s": 1e3 / ms, "algorithmic_gbs": 149.8 * pts / ms / 1e6,
                                           "hbm_frac": 149.8 * pts / ms / 1e6 / peak, "residual_l2_initial": r0b,
                                           "residual_l2_after_7_cycles": e.residual_norm(0)[0],
-                                          "note": "dense layout, one thread per point: not tuned like the cubic path (DESIGN.md)"}
+                                          "note": "colour-split layout, one thread per point; no TMA staging / temporal blocking (DESIGN.md section 4)"}
         e.close()
     if world == 8:
         n = 2049

@@ -166,7 +166,8 @@ int mg3d_vcycle_host(mg3d_t* mg, void* v_host, const void* f_host, int v1, int v
    operators are written per dimension (N3/MultiGrid3D.cpp:5-8, :19-47: numGrids = (int)log2(minSize - 1), every dimension
    halved per level), but Grid3D asserts them equal (N3/Grid3D.cpp:10-11; lifting that is the author's TODO, SURVEY.md 8f
    rank 4).  Same operators, same arithmetic, results bit-identical to the reference compiled with its assertions off
-   (oracle/_ref ref3d_*x, tests/test_box3d_gpu.py); dense device layout, one GPU, not tuned like the cubic path. */
+   (oracle/_ref ref3d_*x, tests/test_box3d_gpu.py); colour-split device layout like the cubic engine's, one GPU, no TMA / temporal
+   blocking. */
 int mg3b_create(mg3b_t** out, const int finest_size_xyz[3], const double range[6], int dtype, int residual_mode);
 int mg3b_destroy(mg3b_t* mg);
 int mg3b_num_levels(const mg3b_t* mg);                               /* MultiGrid3D::numGrids */

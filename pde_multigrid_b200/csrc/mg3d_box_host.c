@@ -7,7 +7,8 @@
  * (N3/Grid3D.cpp:10-11; lifting that is the author's own TODO).  This driver mirrors the same
  * control flow (VCycle :623-647, FullMultiGridVCycle :569-585) over the kernels of mg3d_box.cu.  The coarsest level of
  * an anisotropic hierarchy has more than one unknown (e.g. 9 x 5 x 3): like the reference it gets v1 + v2 sweeps.
- * Fields live on the device in the reference's dense layout, so set/get are plain copies.  No CPU compute path.
+ * Fields live on the device colour-split like the cubic engine's (mg3d_box.h); set/get repack through a dense staging field.
+ * No CPU compute path.
  */
 #include <math.h>
 #include <stdlib.h>
@@ -15,21 +16,13 @@
 
 #include "mg_host_common.h"
 
-#define MG3B_NPARTS 1024
+#include "mg3d_box.h"
 
-int mgk3b_relax_colour(cudaStream_t s, int dtype, void* v, const void* f, const int n[3], mg_coef3d c, int colour);
-int mgk3b_residual(cudaStream_t s, int dtype, const void* v, const void* f, void* r, const int n[3], mg_coef3d c, int corrected);
-int mgk3b_restrict(cudaStream_t s, int dtype, const void* fv, const void* ff, const int n[3], mg_coef3d c, int corrected, void* cf, void* cv,
-                   const int cn[3]);
-int mgk3b_interpolate(cudaStream_t s, int dtype, void* fv, const int n[3], const void* cv, const int cn[3], int add);
-int mgk3b_apply_correction(cudaStream_t s, int dtype, void* fv, const void* err, const int n[3]);
-int mgk3b_set(cudaStream_t s, int dtype, void* a, const int n[3], double value, int modify_boundaries);
-int mgk3b_init_f(cudaStream_t s, int dtype, void* f, const int n[3], const double* sx, const double* sy, const double* sz);
-int mgk3b_residual_norm(cudaStream_t s, int dtype, const void* v, const void* f, const int n[3], mg_coef3d c, int corrected, double* parts,
-                        int nparts, double* out2);
+#define MG3B_NPARTS 1024
 
 typedef struct {
     int n[3];
+    mg_geom3b g;   /* colour-split device layout of the level's fields */
     mg_coef3d c;
     double h[3];
     void* v;
@@ -42,6 +35,7 @@ struct mg3b_s {
     cudaStream_t stream;
     mg_level3b* lv;
     void* arena;
+    void* staging;     /* one dense field of the finest level: host <-> device copies pass through it (repack) */
     double* d_scratch; /* 2 * MG3B_NPARTS partials + 2 outputs */
     double* d_tables;  /* sin tables of InitF: nx + ny + nz doubles of the finest level */
     double* h_out2;    /* pinned */
@@ -49,6 +43,14 @@ struct mg3b_s {
 };
 
 static size_t level_count(const mg_level3b* L) { return (size_t)L->n[0] * (size_t)L->n[1] * (size_t)L->n[2]; }
+static size_t field_bytes(const mg_level3b* L, int dtype) { return mg_align256(2 * (size_t)L->g.cstride * mg_esize(dtype)); }
+static void set_geom3b(mg_geom3b* g, const int n[3], int dtype)
+{
+    g->nx = n[0]; g->ny = n[1]; g->nz = n[2];
+    g->hp = mg_pitch((n[0] + 1) / 2, dtype);
+    g->plane = (long long)g->hp * n[1];
+    g->cstride = g->plane * n[2];
+}
 
 /* h = range/(real)(size-1) per axis (N3/Grid3D.cpp:31-45) and the products of N3/MultiGrid3D.cpp:498-500, :532, in the level's
    own precision exactly like the reference computes them on the host */
@@ -78,7 +80,11 @@ static void box_coefs(int dtype, const int n[3], const double* range, double h[3
         c->den = den; c->rden = 1.0 / den;
         c->ihx2 = 1.0 / hx2; c->ihy2 = 1.0 / hy2; c->ihz2 = 1.0 / hz2;
     }
-    c->fast_h = c->fast_den = 0; /* three different mesh widths: IEEE division throughout */
+    /* three different mesh widths: the smoother's divisor is not of the 6*2^e form, IEEE division there; the residual's x / h^2
+       becomes the exact x * (1/h^2) when every h^2 is a power of two (mg_exact.cuh; MG_B200_IEEE_DIV switches it off) */
+    int e;
+    c->fast_den = 0;
+    c->fast_h = frexp(c->hx2, &e) == 0.5 && frexp(c->hy2, &e) == 0.5 && frexp(c->hz2, &e) == 0.5 && !getenv("MG_B200_IEEE_DIV");
 }
 
 static int check_level(const mg3b_t* mg, int level)
@@ -100,6 +106,7 @@ int mg3b_destroy(mg3b_t* mg)
     if (!mg) return MG_OK;
     if (mg->stream) cudaStreamSynchronize(mg->stream);
     if (mg->arena) cudaFree(mg->arena);
+    if (mg->staging) cudaFree(mg->staging);
     if (mg->d_scratch) cudaFree(mg->d_scratch);
     if (mg->d_tables) cudaFree(mg->d_tables);
     if (mg->h_out2) cudaFreeHost(mg->h_out2);
@@ -140,7 +147,8 @@ int mg3b_create(mg3b_t** out, const int finest_size_xyz[3], const double range[6
         mg_level3b* L = &mg->lv[l];
         for (int a = 0; a < 3; a++) L->n[a] = l == 0 ? finest_size_xyz[a] : (mg->lv[l - 1].n[a] - 1) / 2 + 1;
         box_coefs(dtype, L->n, range, L->h, &L->c);
-        bytes += 2 * mg_align256(level_count(L) * mg_esize(dtype));
+        set_geom3b(&L->g, L->n, dtype);
+        bytes += 2 * field_bytes(L, dtype);
     }
 #define MG3B_TRY(call)                                                                                                        \
     do {                                                                                                                      \
@@ -152,13 +160,15 @@ int mg3b_create(mg3b_t** out, const int finest_size_xyz[3], const double range[6
     } while (0)
     MG3B_TRY(cudaStreamCreateWithFlags(&mg->stream, cudaStreamNonBlocking));
     MG3B_TRY(cudaMalloc(&mg->arena, bytes));
+    MG3B_TRY(cudaMemsetAsync(mg->arena, 0, bytes, mg->stream)); /* the row padding is never read for a result, but keep it defined */
+    MG3B_TRY(cudaMalloc(&mg->staging, level_count(&mg->lv[0]) * mg_esize(dtype)));
     MG3B_TRY(cudaMalloc((void**)&mg->d_scratch, (2 * MG3B_NPARTS + 2) * sizeof(double)));
     MG3B_TRY(cudaMalloc((void**)&mg->d_tables, (size_t)(finest_size_xyz[0] + finest_size_xyz[1] + finest_size_xyz[2]) * sizeof(double)));
     MG3B_TRY(cudaMallocHost((void**)&mg->h_out2, 2 * sizeof(double)));
     char* p = (char*)mg->arena;
     for (int l = 0; l < mg->nlevels; l++) {
         mg_level3b* L = &mg->lv[l];
-        const size_t fb = mg_align256(level_count(L) * mg_esize(dtype));
+        const size_t fb = field_bytes(L, dtype);
         L->v = p; p += fb;
         L->f = p; p += fb;
     }
@@ -225,8 +235,8 @@ int mg3b_init_problem(mg3b_t* mg)
         if (e == cudaSuccess) e = cudaStreamSynchronize(mg->stream);
         free(tab);
         if (e != cudaSuccess) return mg_fail(MG_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e));
-        MG_LAUNCH(mg->launches, mgk3b_set(mg->stream, mg->dtype, L->v, L->n, 0.0, 1));
-        MG_LAUNCH(mg->launches, mgk3b_init_f(mg->stream, mg->dtype, L->f, L->n, mg->d_tables, mg->d_tables + L->n[0], mg->d_tables + L->n[0] + L->n[1]));
+        MG_LAUNCH(mg->launches, mgk3b_set(mg->stream, mg->dtype, L->v, L->g, 0.0, 1));
+        MG_LAUNCH(mg->launches, mgk3b_init_f(mg->stream, mg->dtype, L->f, L->g, mg->d_tables, mg->d_tables + L->n[0], mg->d_tables + L->n[0] + L->n[1]));
         MG_CUDA(cudaStreamSynchronize(mg->stream)); /* d_tables is reused by the next level */
     }
     return MG_OK;
@@ -240,7 +250,8 @@ int mg3b_set_field(mg3b_t* mg, int level, int field, const void* host_dense)
     if (st) return st;
     if (!host_dense || (field != MG_FIELD_V && field != MG_FIELD_F)) return mg_fail(MG_ERR_ARG, "bad field/pointer");
     mg_level3b* L = &mg->lv[level];
-    MG_CUDA(cudaMemcpyAsync(field_ptr(L, field), host_dense, level_count(L) * mg_esize(mg->dtype), cudaMemcpyHostToDevice, mg->stream));
+    MG_CUDA(cudaMemcpyAsync(mg->staging, host_dense, level_count(L) * mg_esize(mg->dtype), cudaMemcpyHostToDevice, mg->stream));
+    MG_LAUNCH(mg->launches, mgk3b_repack(mg->stream, mg->dtype, field_ptr(L, field), L->g, mg->staging, 1));
     MG_CUDA(cudaStreamSynchronize(mg->stream));
     return MG_OK;
 }
@@ -251,7 +262,8 @@ int mg3b_get_field(mg3b_t* mg, int level, int field, void* host_dense)
     if (st) return st;
     if (!host_dense || (field != MG_FIELD_V && field != MG_FIELD_F)) return mg_fail(MG_ERR_ARG, "bad field/pointer");
     mg_level3b* L = &mg->lv[level];
-    MG_CUDA(cudaMemcpyAsync(host_dense, field_ptr(L, field), level_count(L) * mg_esize(mg->dtype), cudaMemcpyDeviceToHost, mg->stream));
+    MG_LAUNCH(mg->launches, mgk3b_repack(mg->stream, mg->dtype, field_ptr(L, field), L->g, mg->staging, 0));
+    MG_CUDA(cudaMemcpyAsync(host_dense, mg->staging, level_count(L) * mg_esize(mg->dtype), cudaMemcpyDeviceToHost, mg->stream));
     MG_CUDA(cudaStreamSynchronize(mg->stream));
     return MG_OK;
 }
@@ -262,7 +274,7 @@ static int relax_level(mg3b_t* mg, int level, int ncycles)
     mg_level3b* L = &mg->lv[level];
     for (int k = 0; k < ncycles; k++)
         for (int colour = 0; colour < 2; colour++)
-            MG_LAUNCH(mg->launches, mgk3b_relax_colour(mg->stream, mg->dtype, L->v, L->f, L->n, L->c, colour));
+            MG_LAUNCH(mg->launches, mgk3b_relax_colour(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, colour));
     return MG_OK;
 }
 
@@ -281,14 +293,9 @@ int mg3b_residual(mg3b_t* mg, int level, void* host_out)
     if (!host_out) return mg_fail(MG_ERR_ARG, "null output");
     mg_level3b* L = &mg->lv[level];
     const size_t bytes = level_count(L) * mg_esize(mg->dtype);
-    void* r = NULL;
-    MG_CUDA(cudaMalloc(&r, bytes));
-    int k = mgk3b_residual(mg->stream, mg->dtype, L->v, L->f, r, L->n, L->c, mg->mode == MG_CORRECTED);
-    cudaError_t e = k < 0 ? cudaGetLastError() : cudaMemcpyAsync(host_out, r, bytes, cudaMemcpyDeviceToHost, mg->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(mg->stream);
-    cudaFree(r);
-    if (k < 0 || e != cudaSuccess) return mg_fail(MG_ERR_CUDA, "residual failed: %s", cudaGetErrorString(e));
-    mg->launches += k;
+    MG_LAUNCH(mg->launches, mgk3b_residual_dense(mg->stream, mg->dtype, L->v, L->f, mg->staging, L->g, L->c, mg->mode == MG_CORRECTED));
+    MG_CUDA(cudaMemcpyAsync(host_out, mg->staging, bytes, cudaMemcpyDeviceToHost, mg->stream));
+    MG_CUDA(cudaStreamSynchronize(mg->stream));
     return MG_OK;
 }
 
@@ -298,7 +305,7 @@ int mg3b_residual_norm(mg3b_t* mg, int level, double* l2, double* linf)
     if (st) return st;
     mg_level3b* L = &mg->lv[level];
     double* out2 = mg->d_scratch + 2 * MG3B_NPARTS;
-    MG_LAUNCH(mg->launches, mgk3b_residual_norm(mg->stream, mg->dtype, L->v, L->f, L->n, L->c, mg->mode == MG_CORRECTED, mg->d_scratch, MG3B_NPARTS, out2));
+    MG_LAUNCH(mg->launches, mgk3b_residual_norm(mg->stream, mg->dtype, L->v, L->f, L->g, L->c, mg->mode == MG_CORRECTED, mg->d_scratch, MG3B_NPARTS, out2));
     MG_CUDA(cudaMemcpyAsync(mg->h_out2, out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, mg->stream));
     MG_CUDA(cudaStreamSynchronize(mg->stream));
     if (l2) *l2 = sqrt(mg->h_out2[0]);
@@ -313,14 +320,14 @@ int mg3b_restrict(mg3b_t* mg, int fine_level, int field)
     if (fine_level == mg->nlevels - 1) return mg_fail(MG_ERR_ARG, "level %d is the coarsest", fine_level);
     if (field != MG_FIELD_V && field != MG_FIELD_F) return mg_fail(MG_ERR_ARG, "bad field");
     mg_level3b *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
-    MG_LAUNCH(mg->launches, mgk3b_restrict(mg->stream, mg->dtype, NULL, field_ptr(F, field), F->n, F->c, 0, field_ptr(C, field), NULL, C->n));
+    MG_LAUNCH(mg->launches, mgk3b_restrict(mg->stream, mg->dtype, NULL, field_ptr(F, field), F->g, F->c, 0, field_ptr(C, field), NULL, C->g));
     return MG_OK;
 }
 
 static int residual_restrict_level(mg3b_t* mg, int fine_level)
 {
     mg_level3b *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
-    MG_LAUNCH(mg->launches, mgk3b_restrict(mg->stream, mg->dtype, F->v, F->f, F->n, F->c, mg->mode == MG_CORRECTED, C->f, C->v, C->n));
+    MG_LAUNCH(mg->launches, mgk3b_restrict(mg->stream, mg->dtype, F->v, F->f, F->g, F->c, mg->mode == MG_CORRECTED, C->f, C->v, C->g));
     return MG_OK;
 }
 
@@ -335,7 +342,7 @@ int mg3b_residual_restrict(mg3b_t* mg, int fine_level)
 static int interpolate_level(mg3b_t* mg, int fine_level, int add)
 {
     mg_level3b *F = &mg->lv[fine_level], *C = &mg->lv[fine_level + 1];
-    MG_LAUNCH(mg->launches, mgk3b_interpolate(mg->stream, mg->dtype, F->v, F->n, C->v, C->n, add));
+    MG_LAUNCH(mg->launches, mgk3b_interpolate(mg->stream, mg->dtype, F->v, F->g, C->v, C->g, add));
     return MG_OK;
 }
 
@@ -361,7 +368,7 @@ int mg3b_set_to_value(mg3b_t* mg, int level, int field, double value, int modify
     if (st) return st;
     if (field != MG_FIELD_V && field != MG_FIELD_F) return mg_fail(MG_ERR_ARG, "bad field");
     mg_level3b* L = &mg->lv[level];
-    MG_LAUNCH(mg->launches, mgk3b_set(mg->stream, mg->dtype, field_ptr(L, field), L->n, value, modify_boundaries));
+    MG_LAUNCH(mg->launches, mgk3b_set(mg->stream, mg->dtype, field_ptr(L, field), L->g, value, modify_boundaries));
     return MG_OK;
 }
 
@@ -393,12 +400,12 @@ static int fmg_rec(mg3b_t* mg, int level, int v0, int v1, int v2)
     int st;
     if (level != mg->nlevels - 1) {
         mg_level3b *F = &mg->lv[level], *C = &mg->lv[level + 1];
-        MG_LAUNCH(mg->launches, mgk3b_restrict(mg->stream, mg->dtype, NULL, F->f, F->n, F->c, 0, C->f, NULL, C->n));
+        MG_LAUNCH(mg->launches, mgk3b_restrict(mg->stream, mg->dtype, NULL, F->f, F->g, F->c, 0, C->f, NULL, C->g));
         if ((st = fmg_rec(mg, level + 1, v0, v1, v2))) return st;
         if ((st = interpolate_level(mg, level, 0))) return st;
     } else {
         mg_level3b* L = &mg->lv[level];
-        MG_LAUNCH(mg->launches, mgk3b_set(mg->stream, mg->dtype, L->v, L->n, 0.0, 0));
+        MG_LAUNCH(mg->launches, mgk3b_set(mg->stream, mg->dtype, L->v, L->g, 0.0, 0));
     }
     for (int i = 0; i < v0; i++)
         if ((st = vcycle_rec(mg, level, v1, v2))) return st;
@@ -420,13 +427,16 @@ int mg3b_vcycle_host(mg3b_t* mg, void* v_host, const void* f_host, int v1, int v
     if (v1 < 0 || v2 < 0 || cycles < 0) return mg_fail(MG_ERR_ARG, "negative count");
     mg_level3b* L = &mg->lv[0];
     const size_t bytes = level_count(L) * mg_esize(mg->dtype);
-    MG_CUDA(cudaMemcpyAsync(L->v, v_host, bytes, cudaMemcpyHostToDevice, mg->stream));
-    MG_CUDA(cudaMemcpyAsync(L->f, f_host, bytes, cudaMemcpyHostToDevice, mg->stream));
+    MG_CUDA(cudaMemcpyAsync(mg->staging, v_host, bytes, cudaMemcpyHostToDevice, mg->stream));
+    MG_LAUNCH(mg->launches, mgk3b_repack(mg->stream, mg->dtype, L->v, L->g, mg->staging, 1));
+    MG_CUDA(cudaMemcpyAsync(mg->staging, f_host, bytes, cudaMemcpyHostToDevice, mg->stream));
+    MG_LAUNCH(mg->launches, mgk3b_repack(mg->stream, mg->dtype, L->f, L->g, mg->staging, 1));
     for (int i = 0; i < cycles; i++) {
         int st = vcycle_rec(mg, 0, v1, v2);
         if (st) return st;
     }
-    MG_CUDA(cudaMemcpyAsync(v_host, L->v, bytes, cudaMemcpyDeviceToHost, mg->stream));
+    MG_LAUNCH(mg->launches, mgk3b_repack(mg->stream, mg->dtype, L->v, L->g, mg->staging, 0));
+    MG_CUDA(cudaMemcpyAsync(v_host, mg->staging, bytes, cudaMemcpyDeviceToHost, mg->stream));
     MG_CUDA(cudaStreamSynchronize(mg->stream));
     return MG_OK;
 }
@@ -474,11 +484,9 @@ int mg3b_restrict_host(mg3b_t* mg, const void* fine, const int fsize_xyz[3], voi
     if (!mg || !fine || !coarse || !box_sizes_ok(fsize_xyz) || !box_sizes_ok(csize_xyz) || !coarse_of(fsize_xyz, csize_xyz))
         return mg_fail(MG_ERR_ARG, "bad arrays or sizes (coarse = (fine-1)/2+1 per axis)");
     void *df, *dc;
-    mg_coef3d c;
-    memset(&c, 0, sizeof c);
     int st = box_tmp(mg, &df, count3(fsize_xyz), fine, &dc, count3(csize_xyz), NULL);
     if (st) return st;
-    int k = mgk3b_restrict(mg->stream, mg->dtype, NULL, df, fsize_xyz, c, 0, dc, NULL, csize_xyz);
+    int k = mgk3b_dense_restrict(mg->stream, mg->dtype, df, fsize_xyz, dc, csize_xyz);
     return box_finish(mg, k, coarse, dc, count3(csize_xyz), df, dc);
 }
 
@@ -489,7 +497,7 @@ int mg3b_interpolate_host(mg3b_t* mg, void* fine, const int fsize_xyz[3], const 
     void *df, *dc;
     int st = box_tmp(mg, &df, count3(fsize_xyz), fine, &dc, count3(csize_xyz), coarse); /* the boundary of fine is kept */
     if (st) return st;
-    int k = mgk3b_interpolate(mg->stream, mg->dtype, df, fsize_xyz, dc, csize_xyz, 0);
+    int k = mgk3b_dense_interpolate(mg->stream, mg->dtype, df, fsize_xyz, dc, csize_xyz);
     return box_finish(mg, k, fine, df, count3(fsize_xyz), df, dc);
 }
 
@@ -500,7 +508,7 @@ int mg3b_apply_correction_host(mg3b_t* mg, void* fine, const int fsize_xyz[3], c
     void *df, *de;
     int st = box_tmp(mg, &df, count3(fsize_xyz), fine, &de, count3(fsize_xyz), error);
     if (st) return st;
-    int k = mgk3b_apply_correction(mg->stream, mg->dtype, df, de, fsize_xyz);
+    int k = mgk3b_dense_apply_correction(mg->stream, mg->dtype, df, de, fsize_xyz);
     return box_finish(mg, k, fine, df, count3(fsize_xyz), df, de);
 }
 
@@ -510,6 +518,6 @@ int mg3b_set_to_value_host(mg3b_t* mg, void* grid, const int size_xyz[3], double
     void *dg, *unused;
     int st = box_tmp(mg, &dg, count3(size_xyz), grid, &unused, 0, NULL);
     if (st) return st;
-    int k = mgk3b_set(mg->stream, mg->dtype, dg, size_xyz, value, modify_boundaries);
+    int k = mgk3b_dense_set(mg->stream, mg->dtype, dg, size_xyz, value, modify_boundaries);
     return box_finish(mg, k, grid, dg, count3(size_xyz), dg, NULL);
 }
