@@ -89,3 +89,33 @@ def test_full_size_linearity_and_kernel_variants(mg):
     x = np.sin(np.pi * np.linspace(0.0, 1.0, N))
     mid = N // 2
     assert abs(va[mid, mid, mid] - x[mid] ** 3) < 0.05
+
+
+# ---- the reference's own runs at the full size (tests/golden/make_hash.py: oracle/_ref at 1025^3, ~45 GB and minutes per cycle,
+#      run once in the build container): fp64 with the sign-corrected residual (the headline), fp64 with the reference's own
+#      residual, and float ----
+def _full_size_keys():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hashes3d.json")) as fh:
+        return sorted(k for k, v in json.load(fh).items() if not k.startswith("_") and v["n"] == N)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", _full_size_keys())
+def test_full_size_bits_equal_the_reference_run(mg, key):
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hashes3d.json")) as fh:
+        rec = json.load(fh)[key]
+    dtype = np.float64 if rec["dtype"] == "f64" else np.float32
+    eng = mg.MultiGrid3D(N, dtype=dtype, residual_mode=mg.MG_CORRECTED if rec["mode"] == "corrected" else mg.MG_REF_COMPAT)
+    for c, ent in enumerate(rec["cycles"]):
+        eng.VCycle(0, rec["v1"], rec["v2"])
+        for l in range(eng.numGrids):
+            assert "%016x" % eng.field_checksum(l) == ent["checksum_v"][l], "checksum, cycle %d level %d" % (c + 1, l)
+    for l in range(1, eng.numGrids):  # SHA-256 of the coarser levels as well (level 0 is 8.6 GB: the checksum stands for it)
+        v = np.ascontiguousarray(eng.get_v(l))
+        assert hashlib.sha256(memoryview(v.reshape(-1).view(np.uint8))).hexdigest() == rec["cycles"][-1]["sha256_v"][l], "sha256 level %d" % l
+    eng.close()
