@@ -47,7 +47,7 @@ def test_no_cpu_fallback(mg):
     L = mg.lib()
     if L.mg_device_count() > 0:
         pytest.skip("a GPU is present")
-    for ctor in (lambda: mg.MultiGrid3D(17), lambda: mg.MultiGrid2D(17), lambda: mg.MultiGrid1D(17)):
+    for ctor in (lambda: mg.MultiGrid3D(17), lambda: mg.MultiGrid2D(17), lambda: mg.MultiGrid1D(17), lambda: mg.MultiGrid3DBox((33, 17, 9))):
         with pytest.raises(mg.MGError) as ei:
             ctor()
         assert ei.value.code == 2
@@ -60,6 +60,9 @@ def test_argument_validation_precedes_device_probe(mg):
     assert ei.value.code == 1
     with pytest.raises(mg.MGError) as ei:
         mg.MultiGrid1D(100)
+    assert ei.value.code == 1
+    with pytest.raises(mg.MGError) as ei:
+        mg.MultiGrid3DBox((33, 18, 9))  # every size must be 2^k + 1
     assert ei.value.code == 1
 
 
