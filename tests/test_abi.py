@@ -15,7 +15,7 @@ HEADER = os.path.join(ROOT, "include", "mg_b200.h")
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"\b(mg(?:[123]d)?_[a-z0-9_]+)\s*\(", src)
+    names = re.findall(r"\b(mg(?:[123]d|3b)?_[a-z0-9_]+)\s*\(", src)
     return sorted(set(names))
 
 
@@ -26,6 +26,10 @@ def test_header_declares_the_reference_interface():
                    "set_to_value", "vcycle", "fmg", "restrict_host", "interpolate_host", "apply_correction_host",
                    "set_to_value_host", "vcycle_host", "residual_norm", "set_field", "get_field"):
             assert "mg%s_%s" % (dim, op) in names
+    for op in ("create", "destroy", "num_levels", "level_size", "relax", "residual", "restrict", "residual_restrict", "interpolate",
+               "interpolate_correct", "set_to_value", "vcycle", "fmg", "restrict_host", "interpolate_host", "apply_correction_host",
+               "set_to_value_host", "vcycle_host", "residual_norm", "set_field", "get_field"):
+        assert "mg3b_" + op in names  # the same interface for non-cubic grids
 
 
 def test_library_exports_every_declared_symbol(mg):
