@@ -243,7 +243,11 @@ def run_reference_arm(args):
               "(x%.5f); the reference cannot use more host threads" % (kind, n_sample, args.n, scale))
     line = {
         "impl": "reference", "metric": "3D Poisson V(2,2) cycles/s", "value": value, "unit": "V-cycles/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 / scale,
+        # ms_per_step is the wall time of one timed step of THIS run (a V(2,2) of the reference at the sample grid), so that
+        # steps x ms_per_step is the time this process really spent; `value` is that rate scaled to the named workload by
+        # grid-point updates (the factor is in `sample`), and ms_per_step_full_size_extrapolated is 1e3 / value
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "ms_per_step_full_size_extrapolated": sec * 1e3 / scale, "sample_scale": scale,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.n, 8), "sample_grid": n_sample, "host_cpu": model, "host_cores": cores},
         "grid_point_updates_per_s": updates_per_cycle(n_sample) / sec,
