@@ -29,18 +29,38 @@ struct TailArgs {
     Coef3<T> c[MAXL];
 };
 
+// A thread's interior points are the same in every half-sweep of a call: their array index and colour are worked out once
+// (the integer divisions), the sweeps then only test a colour bit.  At most MAXP points per thread (15^3 interior points of
+// the 17^3 level over 1024 threads).
+constexpr int MAXP = ((MGK3D_TAIL_N - 2) * (MGK3D_TAIL_N - 2) * (MGK3D_TAIL_N - 2) + NT - 1) / NT;
+
 template <typename T, bool FAST_DEN>
 __device__ void tail_relax(T* v, const T* f, int n, const Coef3<T>& c, int ncycles)
 {
-    const int ni = n - 2, tot = ni * ni * ni;
+    if (ncycles <= 0) return;  // (uniform over the block)
+    const int ni = n - 2, tot = ni * ni * ni, n2 = n * n;
+    int pi[MAXP];
+    unsigned valid = 0, odd = 0;
+#pragma unroll
+    for (int j = 0; j < MAXP; j++) {
+        const int idx = threadIdx.x + j * NT;
+        pi[j] = 0;
+        if (idx < tot) {
+            const int x = 1 + idx % ni, y = 1 + (idx / ni) % ni, z = 1 + idx / (ni * ni);
+            pi[j] = (z * n + y) * n + x;
+            valid |= 1u << j;
+            odd |= (unsigned)((x + y + z) & 1) << j;
+        }
+    }
     for (int k = 0; k < ncycles; k++)
         for (int colour = 0; colour < 2; colour++) {
-            for (int idx = threadIdx.x; idx < tot; idx += NT) {
-                const int x = 1 + idx % ni, y = 1 + (idx / ni) % ni, z = 1 + idx / (ni * ni);
-                if (((x + y + z) & 1) != colour) continue;
-                const int i = (z * n + y) * n + x;
-                v[i] = relax_point<T, FAST_DEN>(v[i - 1], v[i + 1], v[i - n], v[i + n], v[i - n * n], v[i + n * n], f[i], c);
-            }
+            const unsigned mine = valid & (colour ? odd : ~odd);
+#pragma unroll
+            for (int j = 0; j < MAXP; j++)
+                if ((mine >> j) & 1u) {
+                    const int i = pi[j];
+                    v[i] = relax_point<T, FAST_DEN>(v[i - 1], v[i + 1], v[i - n], v[i + n], v[i - n2], v[i + n2], f[i], c);
+                }
             __syncthreads();
         }
 }
