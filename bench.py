@@ -599,7 +599,7 @@ def main():
         e2e = {"value": 1.0 / dt, "unit": "V-cycles/s", "h2d_bytes_per_step": 2 * N0 * B, "d2h_bytes_per_step": N0 * B,
                "steps": args.e2e_steps, "ms_per_step": dt * 1e3, "pcie_gbs_per_gpu": 3 * N0 * B / world / dt / 1e9,
                "host_buffers": "pinned, allocated on the GPU's NUMA node %s (%d CPUs bound)" % (numa_node, numa_cpus) if numa_node is not None
-                               else "pinned (NUMA topology not readable: no binding)",
+                               else "pinned (the host exposes no NUMA node for the GPU -- a single-node VM: nothing to bind)",
                "call": "mg3d_vcycle_host (pinned host v,f -> device, VCycle(0,2,2), v -> host; every rank moves its own z-slab)",
                "timer": "host wall clock around the synchronous C-ABI call, barrier on both sides, max over ranks"}
         del hv, hf
