@@ -370,9 +370,9 @@ def free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("smoother", ["gs", "jacobi", "pipe"])
-def test_slab_schedule_world2_gloo(mg, monkeypatch, smoother):
-    world = 2
+@pytest.mark.parametrize("smoother,world", [("gs", 2), ("jacobi", 2), ("pipe", 2), ("pipe", 4), ("gs", 4)])
+def test_slab_schedule_gloo(mg, monkeypatch, smoother, world):
+    """world 2: every rank has one neighbour; world 4: ranks 1 and 2 have ghosts on both sides and the gather has four shares"""
     N = 129 if smoother == "pipe" else 65  # pipe: two distributed levels (129, 65), the coarse one fed by exchanged f ghosts
     monkeypatch.setenv("MG_B200_DIST_MIN_N", "65")  # distribute the small test grids too (default threshold: n >= 257)
     plans = {(n, r): mg.MultiGrid3D.plan_level(n, world, r) for n in sizes(N) for r in range(world)}
