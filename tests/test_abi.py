@@ -119,3 +119,32 @@ def test_c_example_runs_on_the_gpu():
     assert len(norms) == 3 and norms[2] < 0.2 * norms[1] < 0.04 * norms[0] * 5, out.stdout
     centre = float(out.stdout.split("v(centre) =")[1].split()[0])
     assert abs(centre - 1.0) < 0.01, out.stdout
+
+
+EXAMPLE_BOX = os.path.join(ROOT, "tests", "_build", "example_poisson3d_box")
+
+
+def test_c_example_for_a_non_cubic_grid_builds(mg):
+    os.makedirs(os.path.dirname(EXAMPLE_BOX), exist_ok=True)
+    subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "poisson3d_box.c"), "-o", EXAMPLE_BOX,
+                    "-L", os.path.join(ROOT, "pde_multigrid_b200"), "-lmg_b200",
+                    "-Wl,-rpath,$ORIGIN/../../pde_multigrid_b200", "-lm"], check=True)
+    import torch
+    if not torch.cuda.is_available():
+        out = subprocess.run([EXAMPLE_BOX], capture_output=True, text=True)
+        assert out.returncode == 1 and "no CPU fallback" in out.stderr, out.stderr
+
+
+@pytest.mark.gpu
+def test_c_example_for_a_non_cubic_grid_runs_on_the_gpu():
+    if not os.path.exists(EXAMPLE_BOX):
+        pytest.skip("tests/_build/example_poisson3d_box not built (the CPU test builds it)")
+    out = subprocess.run([EXAMPLE_BOX, "129", "65", "33", "6"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "5 levels down to 9 x 5 x 3" in out.stdout, out.stdout
+    r0 = float(out.stdout.split("||r0||_2 =")[1].split()[0])
+    r1 = float(out.stdout.split("||r||_2 =")[1].split()[0])
+    assert r1 < 0.1 * r0, out.stdout
+    centre = float(out.stdout.split("v(centre) =")[1].split()[0])
+    assert abs(centre - 1.0) < 0.01, out.stdout
